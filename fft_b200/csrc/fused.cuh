@@ -1,0 +1,285 @@
+// fused.cuh -- specialised single-pass batched FFT kernels (compile-time size and radices).
+//
+// The hot path of the library (BG, X, RF, RI): one launch does
+// what the reference does in permute (:288-293) + every fftStepN pass (:187-286) -- and, for real
+// transforms, RealFFT's pack / post-twiddle (:446-473) or pre-twiddle / unpack (:475-502) as well.
+//
+// Data flow per transform:  HBM --coalesced streaming loads--> registers --radix-R0 butterflies + twiddles-->
+//   shared memory (Stockham index = digit reversal folded into the exchange) --> registers --radix-R1 ...-->
+//   ... --> registers --coalesced streaming stores--> HBM.     Each input byte is read from HBM once and
+//   each output byte written once: algorithmic bytes == DRAM traffic (2*N*sizeof(complex) per transform).
+//
+// A thread owns E = N/TX points.  In pass p (radix R) it runs E/R butterflies b_u = t + TX*u:
+//      in  : src[b + (N/R)*j]                (lanes read consecutive addresses: conflict-free, coalesced)
+//      tw  : W_N^(P*m'*r) from a per-pass table laid out [r][m'] (HBM-resident, L1/L2-cached)
+//      out : dst[racc + P*r + P*R*m']        (padded index keeps power-of-two strides off one bank group)
+// Only a forward transform is generated; the inverse swaps re/im on load and store.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <vector>
+
+#include "codelets.cuh"
+#include "planner.h"
+#include "real_kernels.cuh"
+
+namespace ssfft {
+
+enum { FUSED_C2C = 0, FUSED_R2C = 1, FUSED_C2R = 2 };
+enum { FUSED_CONTIG = 0 };
+
+template <typename T_, int N_, int R0_, int R1_, int R2_, int R3_, int TX_, int FPB_, int MINB_, int PADSHIFT_ = 4>
+struct FusedCfg {
+    using T = T_;
+    static constexpr int N = N_, TX = TX_, FPB = FPB_, MINB = MINB_, PADSHIFT = PADSHIFT_;
+    static constexpr int NP = (R3_ > 1) ? 4 : (R2_ > 1) ? 3 : (R1_ > 1) ? 2 : 1;
+    static constexpr int E = N / TX;
+    __host__ __device__ static constexpr int radix(int i) { return i == 0 ? R0_ : i == 1 ? R1_ : i == 2 ? R2_ : R3_; }
+    __host__ __device__ static constexpr int prod(int i) { return i == 0 ? 1 : i == 1 ? R0_ : i == 2 ? R0_ * R1_ : R0_ * R1_ * R2_; }
+    __host__ __device__ static constexpr int mnext(int i) { return N / (prod(i) * radix(i)); }
+    // twiddle table offset (in cx elements) of pass i: passes 0..NP-2 have (R-1)*mnext entries
+    __host__ __device__ static constexpr int tw_off(int i) {
+        int o = 0;
+        for (int k = 0; k < i; ++k) o += (radix(k) - 1) * mnext(k);
+        return o;
+    }
+    static constexpr int tw_total = tw_off(NP - 1);
+    __host__ __device__ static constexpr int pad(int e) { return e + (e >> PADSHIFT); }
+    static constexpr int SM_STRIDE = pad(N) + 1;  // cx elements of shared memory per transform
+    static constexpr size_t smem_bytes = (size_t)SM_STRIDE * FPB * sizeof(cx<T>);
+    static_assert(R0_ * R1_ * R2_ * R3_ == N_, "radices must multiply to N");
+    static_assert(N_ % TX_ == 0, "TX must divide N");
+    static_assert(E % R0_ == 0 && E % R1_ == 0 && E % R2_ == 0 && E % R3_ == 0, "E must be a multiple of every radix");
+};
+
+#ifdef __CUDACC__
+
+template <typename T> struct vec2;
+template <> struct vec2<float> { using type = float2; };
+template <> struct vec2<double> { using type = double2; };
+
+// streaming (evict-first) global accesses: the data is touched exactly once
+template <typename T>
+__device__ __forceinline__ cx<T> ld_stream(const cx<T> *p) {
+    using V = typename vec2<T>::type;
+    V v = __ldcs(reinterpret_cast<const V *>(p));
+    return mk<T>(v.x, v.y);
+}
+template <typename T>
+__device__ __forceinline__ void st_stream(cx<T> *p, cx<T> v) {
+    using V = typename vec2<T>::type;
+    V w; w.x = v.x; w.y = v.y;
+    __stcs(reinterpret_cast<V *>(p), w);
+}
+template <typename T>
+__device__ __forceinline__ cx<T> ld_table(const cx<T> *p) {
+    using V = typename vec2<T>::type;
+    V v = __ldg(reinterpret_cast<const V *>(p));
+    return mk<T>(v.x, v.y);
+}
+
+template <typename Cfg>
+__global__ void __launch_bounds__(Cfg::TX *Cfg::FPB, Cfg::MINB)
+fused_fft_kernel(const cx<typename Cfg::T> *__restrict__ in, cx<typename Cfg::T> *__restrict__ out,
+                 const cx<typename Cfg::T> *__restrict__ tw, const cx<typename Cfg::T> *__restrict__ rtw,
+                 long long batch, int inverse, int mode) {
+    using T = typename Cfg::T;
+    constexpr int N = Cfg::N, TX = Cfg::TX, FPB = Cfg::FPB, E = Cfg::E, NP = Cfg::NP;
+    extern __shared__ __align__(16) unsigned char ssfft_smem[];
+    const int t = threadIdx.x, f = threadIdx.y;
+    cx<T> *sm = reinterpret_cast<cx<T> *>(ssfft_smem) + (size_t)f * Cfg::SM_STRIDE;
+    const long long groups = (batch + FPB - 1) / FPB;
+
+    for (long long g = blockIdx.x; g < groups; g += gridDim.x) {
+        const long long tr = g * FPB + f;
+        const bool active = tr < batch;
+        const cx<T> *gin = in + (active ? tr : 0) * N;
+        cx<T> *gout = out + (active ? tr : 0) * N;
+        cx<T> v[E];
+
+        // ---------------- C2R prologue: pre-twiddle pairs into shared memory (RealFFT::ifft :478-492)
+        if (mode == FUSED_C2R) {
+            if (active) {
+                constexpr int H2 = N / 2 + 1;
+                for (int i = t; i < H2; i += TX) {
+                    if (i == 0) {
+                        cx<T> a = ld_stream(gin);
+                        sm[Cfg::pad(0)] = mk<T>(a.x + a.y, a.x - a.y);
+                    } else {
+                        const int ci = N - i;
+                        cx<T> bi, bc;
+                        c2r_pair(ld_stream(gin + i), ld_stream(gin + ci), ld_table(rtw + i), bi, bc);
+                        sm[Cfg::pad(i)] = bi;
+                        sm[Cfg::pad(ci)] = bc;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+
+        sfor<0, NP>([&](auto pc) {
+            constexpr int p = decltype(pc)::value;
+            constexpr int R = Cfg::radix(p), P = Cfg::prod(p), MN = Cfg::mnext(p), NR = N / R, U = E / R;
+            constexpr bool first = (p == 0), last = (p == NP - 1);
+            // ---- gather inputs
+            if constexpr (first) {
+                if (mode == FUSED_C2R) {
+#pragma unroll
+                    for (int u = 0; u < U; ++u)
+#pragma unroll
+                        for (int j = 0; j < R; ++j) v[u * R + j] = cswap(sm[Cfg::pad(t + TX * u + NR * j)]);
+                    __syncthreads();
+                } else if (active) {
+                    if (inverse) {
+#pragma unroll
+                        for (int u = 0; u < U; ++u)
+#pragma unroll
+                            for (int j = 0; j < R; ++j) v[u * R + j] = cswap(ld_stream(gin + t + TX * u + NR * j));
+                    } else {
+#pragma unroll
+                        for (int u = 0; u < U; ++u)
+#pragma unroll
+                            for (int j = 0; j < R; ++j) v[u * R + j] = ld_stream(gin + t + TX * u + NR * j);
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int u = 0; u < U; ++u)
+#pragma unroll
+                    for (int j = 0; j < R; ++j) v[u * R + j] = sm[Cfg::pad(t + TX * u + NR * j)];
+                __syncthreads();  // everyone has read: the buffer may be overwritten
+            }
+            // ---- butterflies + inter-pass twiddles
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                cx<T> w[R];
+#pragma unroll
+                for (int j = 0; j < R; ++j) w[j] = v[u * R + j];
+                Dft<R>::run(w);
+                if constexpr (!last) {
+                    const int b = t + TX * u;
+                    const int mp = b / P;
+                    const cx<T> *twp = tw + Cfg::tw_off(p) + mp;
+#pragma unroll
+                    for (int r = 1; r < R; ++r) w[r] = cmul(w[r], ld_table(twp + (r - 1) * MN));
+                }
+#pragma unroll
+                for (int j = 0; j < R; ++j) v[u * R + j] = w[j];
+            }
+            // ---- scatter outputs
+            if constexpr (!last) {
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int b = t + TX * u;
+                    const int mp = b / P, racc = b - mp * P;
+                    const int o = racc + P * R * mp;
+#pragma unroll
+                    for (int r = 0; r < R; ++r) sm[Cfg::pad(o + P * r)] = v[u * R + r];
+                }
+                __syncthreads();
+            } else {
+                // last pass: P == N/R, m' == 0, racc == b  ->  natural-order index b + P*r
+                if (mode == FUSED_R2C) {
+#pragma unroll
+                    for (int u = 0; u < U; ++u)
+#pragma unroll
+                        for (int r = 0; r < R; ++r) sm[Cfg::pad(t + TX * u + P * r)] = v[u * R + r];
+                    __syncthreads();
+                    // ---------------- R2C epilogue: post-twiddle pairs (RealFFT::fft :459-472)
+                    if (active) {
+                        constexpr int H2 = N / 2 + 1;
+                        for (int i = t; i < H2; i += TX) {
+                            if (i == 0) {
+                                cx<T> z0 = sm[Cfg::pad(0)];
+                                st_stream(gout, mk<T>(z0.x + z0.y, z0.x - z0.y));
+                            } else {
+                                const int ci = N - i;
+                                cx<T> oi, oc;
+                                r2c_pair(sm[Cfg::pad(i)], sm[Cfg::pad(ci)], ld_table(rtw + i), oi, oc);
+                                st_stream(gout + i, oi);
+                                st_stream(gout + ci, oc);
+                            }
+                        }
+                    }
+                    __syncthreads();
+                } else if (active) {
+                    if (inverse) {
+#pragma unroll
+                        for (int u = 0; u < U; ++u)
+#pragma unroll
+                            for (int r = 0; r < R; ++r) st_stream(gout + t + TX * u + P * r, cswap(v[u * R + r]));
+                    } else {
+#pragma unroll
+                        for (int u = 0; u < U; ++u)
+#pragma unroll
+                            for (int r = 0; r < R; ++r) st_stream(gout + t + TX * u + P * r, v[u * R + r]);
+                    }
+                }
+            }
+        });
+    }
+}
+
+#endif  // __CUDACC__
+
+// ---------------------------------------------------------------------------------------------
+// registry: which (precision, N) have a specialised kernel, and how to launch it
+// ---------------------------------------------------------------------------------------------
+struct FusedEntry {
+    int prec;      // 0 f32, 1 f64
+    int n;
+    const char *name;
+    int tw_total;  // cx elements
+    int radix[4], np;
+    int (*launch)(const void *tw, const void *in, void *out, long long batch, int inverse, int mode, const void *rtw,
+                  cudaStream_t s);
+};
+
+const std::vector<FusedEntry> &fused_registry();
+int fused_waves();  // resident-CTA waves per launch before CTAs loop (env SSFFT_FUSED_WAVES, default 4)
+
+template <typename T>
+inline int find_fused(size_t n, int /*layout*/) {
+    const int prec = sizeof(T) == 4 ? 0 : 1;
+    const auto &reg = fused_registry();
+    for (size_t i = 0; i < reg.size(); ++i)
+        if (reg[i].prec == prec && (size_t)reg[i].n == n) return (int)i;
+    return -1;
+}
+inline const char *fused_name(int id) { return fused_registry()[id].name; }
+
+// per-pass twiddle tables laid out [r-1][m']: W_N^(P*m'*r)
+template <typename T>
+inline int build_fused_twiddles(int id, void **d_out) {
+    const FusedEntry &e = fused_registry()[id];
+    std::vector<T> h(2 * (size_t)(e.tw_total > 0 ? e.tw_total : 1));
+    size_t o = 0;
+    int P = 1;
+    for (int p = 0; p + 1 < e.np; ++p) {
+        const int R = e.radix[p], MN = e.n / (P * R);
+        for (int r = 1; r < R; ++r)
+            for (int m = 0; m < MN; ++m) {
+                unsigned long long q = (unsigned long long)P * m * r % (unsigned long long)e.n;
+                long double a = 2.0L * 3.14159265358979323846264338327950288L * (long double)q / (long double)e.n;
+                h[2 * o] = (T)cosl(a);
+                h[2 * o + 1] = (T)(-sinl(a));
+                ++o;
+            }
+        P *= R;
+    }
+    if (cudaMalloc(d_out, h.size() * sizeof(T)) != cudaSuccess) return 5;
+    if (cudaMemcpy(*d_out, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice) != cudaSuccess) return 2;
+    return 0;
+}
+
+template <typename T>
+inline int launch_fused(int id, const void *tw, const void *in, void *out, long long batch, int inverse, int mode,
+                        const void *rtw, cudaStream_t s, std::atomic<uint64_t> *counter) {
+    const FusedEntry &e = fused_registry()[id];
+    int rc = e.launch(tw, in, out, batch, inverse, mode, rtw, s);
+    if (counter) ++*counter;
+    return rc;
+}
+
+}  // namespace ssfft

@@ -1,0 +1,59 @@
+// fused_launch.cuh -- host launcher shared by the fused-kernel translation units.
+#pragma once
+#include "fused.cuh"
+
+namespace ssfft {
+
+// grid = min(#transform groups, SMs * resident CTAs per SM * waves); CTAs loop over groups.
+template <typename Cfg>
+int launch_cfg(const void *tw, const void *in, void *out, long long batch, int inverse, int mode, const void *rtw,
+               cudaStream_t s) {
+    using T = typename Cfg::T;
+    static int ready_mask = 0;      // per-device one-time setup
+    static int resident[64] = {0};  // SMs * CTAs/SM per device
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 2;
+    if (dev < 0 || dev >= 32) return 1;
+    if (!(ready_mask & (1 << dev))) {
+        if (Cfg::smem_bytes > 48 * 1024 &&
+            cudaFuncSetAttribute(fused_fft_kernel<Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)Cfg::smem_bytes) != cudaSuccess)
+            return 2;
+        int per_sm = 0, sms = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fused_fft_kernel<Cfg>, Cfg::TX * Cfg::FPB,
+                                                          Cfg::smem_bytes) != cudaSuccess)
+            return 2;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (per_sm < 1) per_sm = 1;
+        resident[dev] = per_sm * sms;
+        ready_mask |= 1 << dev;
+    }
+    const long long groups = (batch + Cfg::FPB - 1) / Cfg::FPB;
+    if (groups <= 0) return 0;
+    long long grid = groups;
+    const long long cap = (long long)resident[dev] * fused_waves();
+    if (cap > 0 && grid > cap) grid = cap;
+    dim3 block(Cfg::TX, Cfg::FPB);
+    fused_fft_kernel<Cfg><<<(unsigned)grid, block, Cfg::smem_bytes, s>>>((const cx<T> *)in, (cx<T> *)out,
+                                                                          (const cx<T> *)tw, (const cx<T> *)rtw, batch,
+                                                                          inverse, mode);
+    return cudaGetLastError() == cudaSuccess ? 0 : 2;
+}
+
+template <typename Cfg>
+FusedEntry make_entry(const char *name) {
+    FusedEntry e;
+    e.prec = sizeof(typename Cfg::T) == 4 ? 0 : 1;
+    e.n = Cfg::N;
+    e.name = name;
+    e.tw_total = Cfg::tw_total;
+    e.np = Cfg::NP;
+    for (int i = 0; i < 4; ++i) e.radix[i] = Cfg::radix(i);
+    e.launch = &launch_cfg<Cfg>;
+    return e;
+}
+
+#define SSFFT_FUSED(T, N, R0, R1, R2, R3, TX, FPB, MINB) \
+    make_entry<FusedCfg<T, N, R0, R1, R2, R3, TX, FPB, MINB>>(#T "_" #N "_" #R0 "x" #R1 "x" #R2 "x" #R3)
+
+}  // namespace ssfft

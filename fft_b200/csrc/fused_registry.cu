@@ -1,0 +1,38 @@
+// fused_registry.cu -- collects the specialised kernels of every translation unit.
+#include <cstdlib>
+
+#include "fused.cuh"
+namespace ssfft {
+void register_fused_f32_a(std::vector<FusedEntry> &);
+void register_fused_f32_b(std::vector<FusedEntry> &);
+void register_fused_f32_c(std::vector<FusedEntry> &);
+void register_fused_f64_a(std::vector<FusedEntry> &);
+void register_fused_f64_b(std::vector<FusedEntry> &);
+
+const std::vector<FusedEntry> &fused_registry() {
+    static const std::vector<FusedEntry> reg = [] {
+        std::vector<FusedEntry> v;
+        // SSFFT_DISABLE_FUSED=1 forces every size through the generic kernel (used by the parity tests
+        // to exercise both paths); it never selects a CPU path -- there is none.
+        const char *off = getenv("SSFFT_DISABLE_FUSED");
+        if (off && off[0] == '1') return v;
+        register_fused_f32_a(v);
+        register_fused_f32_b(v);
+        register_fused_f32_c(v);
+        register_fused_f64_a(v);
+        register_fused_f64_b(v);
+        return v;
+    }();
+    return reg;
+}
+
+// how many resident "waves" of CTAs a fused launch may create before CTAs start looping
+int fused_waves() {
+    static const int w = [] {
+        const char *e = getenv("SSFFT_FUSED_WAVES");
+        int v = e ? atoi(e) : 4;
+        return v < 0 ? 0 : v;
+    }();
+    return w;
+}
+}  // namespace ssfft

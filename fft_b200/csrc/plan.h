@@ -1,0 +1,59 @@
+// plan.h -- internal plan object behind the opaque ssfft_plan handle of include/ssfft.h.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstddef>
+#include <cstdint>
+#include <string>
+#include <vector>
+
+namespace ssfft {
+
+// One single-launch transform of length n through the generic pass interpreter (generic.cuh).
+struct GenericStage {
+    int n = 0;
+    std::vector<int> radix, prod;
+    void *d_roots = nullptr;  // W_n^k, k < n  (cx<T>)
+    int smem_stride = 0;
+    int tx = 0, fpb = 0;
+    int stage_input = 0;
+    size_t smem_bytes = 0;
+};
+
+// Which specialised kernel (fused.cuh) serves a length, if any.
+struct FusedChoice {
+    int id = -1;              // index into the fused-kernel registry, -1 = none
+    void *d_twiddles = nullptr;
+};
+
+}  // namespace ssfft
+
+struct ssfft_plan {
+    int kind = 0, prec = 0, device = 0;
+    size_t n_user = 0;  // as given
+    size_t n_real = 0;  // real plans: 2*(n_user/2)
+    size_t n = 0;       // complex transform length (n_user, or n_real/2)
+    size_t elem = 0;    // sizeof(cx<T>)
+
+    // complex core
+    bool four_step = false;
+    size_t n1 = 0, n2 = 0;
+    ssfft::GenericStage direct, col, row;  // direct: !four_step;  col (n1, strided) / row (n2) otherwise
+    ssfft::FusedChoice fused;              // contiguous single-pass kernel for n, when registered
+    ssfft::FusedChoice fused_col, fused_row;
+    void *d_ep_lo = nullptr, *d_ep_hi = nullptr;
+    int ep_shift = 0;
+    void *d_scratch = nullptr;  // four-step intermediate, chunk transforms
+    size_t chunk = 0;
+
+    // real wrappers
+    void *d_rtw = nullptr;  // twiddlesMinusI
+    void *d_rot = nullptr;  // modifiedRotations
+
+    // host-pointer path staging (grow-only)
+    void *d_stage_in = nullptr, *d_stage_out = nullptr;
+    size_t stage_in_bytes = 0, stage_out_bytes = 0;
+    cudaStream_t host_stream = nullptr;
+
+    std::string desc;
+};

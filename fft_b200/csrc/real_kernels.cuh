@@ -1,0 +1,124 @@
+// real_kernels.cuh -- stand-alone RealFFT pre/post-twiddle passes and small utility kernels.
+//
+// RealFFT<V>::fft post-twiddle  (signalsmith-fft.h:459-472) and RealFFT<V>::ifft pre-twiddle (:478-492),
+// plus the ModifiedRealFFT rotations (:450-452, :497-498).  These separate passes are used when the
+// complex core runs through the generic / four-step path; the fused single-pass kernels (fused.cuh) do
+// the same arithmetic in their prologue / epilogue without the extra HBM round trip.
+#pragma once
+#include "cplx.cuh"
+
+namespace ssfft {
+
+// Forward post-twiddle for one pair (i, ci): Z -> spectrum bins.  tw = twiddlesMinusI[i].
+template <typename T>
+SSFFT_HD void r2c_pair(cx<T> zi, cx<T> zc, cx<T> tw, cx<T> &oi, cx<T> &oc) {
+    const T half = (T)0.5;
+    cx<T> odd = mk<T>((zi.x + zc.x) * half, (zi.y - zc.y) * half);    // (Zi + conj Zc)/2   :466
+    cx<T> even_i = mk<T>((zi.x - zc.x) * half, (zi.y + zc.y) * half); // (Zi - conj Zc)/2   :467
+    cx<T> rot = cmul(even_i, tw);                                     // :468
+    oi = odd + rot;                                                   // :470
+    oc = cconj(odd - rot);                                            // :471
+}
+// Inverse pre-twiddle for one pair (no 1/2: result is scaled by N overall, :486-491)
+template <typename T>
+SSFFT_HD void c2r_pair(cx<T> v, cx<T> v2, cx<T> tw, cx<T> &bi, cx<T> &bc) {
+    cx<T> odd = mk<T>(v.x + v2.x, v.y - v2.y);   // v + conj v2
+    cx<T> rot = mk<T>(v.x - v2.x, v.y + v2.y);   // v - conj v2
+    cx<T> even_i = cmulc(rot, tw);               // * conj(tw)   :488
+    bi = odd + even_i;
+    bc = cconj(odd - even_i);
+}
+
+#ifdef __CUDACC__
+// In place on `data` (batch x h complex): Z -> packed half spectrum.
+template <typename T>
+__global__ void r2c_post_kernel(cx<T> *__restrict__ data, const cx<T> *__restrict__ tw, long long h, long long batch,
+                                int modified) {
+    const long long per = h / 2 + 1;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= per * batch) return;
+    const long long b = idx / per, i = idx - b * per;
+    cx<T> *z = data + b * h;
+    if (!modified) {
+        if (i == 0) {
+            cx<T> z0 = z[0];
+            z[0] = mk<T>(z0.x + z0.y, z0.x - z0.y);  // DC in .re, Nyquist in .im  (:459-462)
+            return;
+        }
+        const long long ci = h - i;
+        cx<T> oi, oc;
+        r2c_pair(z[i], z[ci], tw[i], oi, oc);
+        z[i] = oi;
+        z[ci] = oc;  // when i == ci the second write wins, as in the reference
+    } else {
+        const long long ci = h - 1 - i;
+        if (ci < i) return;
+        cx<T> oi, oc;
+        r2c_pair(z[i], z[ci], tw[i], oi, oc);
+        z[i] = oi;
+        z[ci] = oc;
+    }
+}
+
+// Out of place: packed half spectrum (batch x h) -> pre-twiddled complex buffer (batch x h).
+template <typename T>
+__global__ void c2r_pre_kernel(const cx<T> *__restrict__ in, cx<T> *__restrict__ out, const cx<T> *__restrict__ tw,
+                               long long h, long long batch, int modified) {
+    const long long per = h / 2 + 1;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= per * batch) return;
+    const long long b = idx / per, i = idx - b * per;
+    const cx<T> *x = in + b * h;
+    cx<T> *y = out + b * h;
+    if (!modified) {
+        if (i == 0) {
+            cx<T> v = x[0];
+            y[0] = mk<T>(v.x + v.y, v.x - v.y);  // :478-481
+            return;
+        }
+        const long long ci = h - i;
+        cx<T> bi, bc;
+        c2r_pair(x[i], x[ci], tw[i], bi, bc);
+        y[i] = bi;
+        y[ci] = bc;
+    } else {
+        const long long ci = h - 1 - i;
+        if (ci < i) return;
+        cx<T> bi, bc;
+        c2r_pair(x[i], x[ci], tw[i], bi, bc);
+        y[i] = bi;
+        y[ci] = bc;
+    }
+}
+
+// dst[b][i] = src[b][i] * rot[i]   (conj_rot: * conj(rot[i]))   -- ModifiedRealFFT rotations
+template <typename T>
+__global__ void rotate_kernel(cx<T> *__restrict__ dst, const cx<T> *__restrict__ src, const cx<T> *__restrict__ rot,
+                              long long h, long long total, int conj_rot) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const cx<T> r = rot[idx % h];
+    const cx<T> v = src[idx];
+    dst[idx] = conj_rot ? cmulc(v, r) : cmul(v, r);
+}
+
+// counter-based uniform [-0.5, 0.5) generator, twin of oracle_fill_uniform_* 
+__device__ __forceinline__ unsigned long long splitmix64(unsigned long long x) {
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+template <typename T>
+__global__ void fill_uniform_kernel(T *__restrict__ dst, unsigned long long count, unsigned long long seed,
+                                    unsigned long long first) {
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride) {
+        unsigned long long h = splitmix64((seed << 40) + first + i);
+        if (sizeof(T) == 4) dst[i] = (T)((float)(h >> 40) * (1.0f / 16777216.0f) - 0.5f);
+        else dst[i] = (T)((double)(h >> 11) * (1.0 / 9007199254740992.0) - 0.5);
+    }
+}
+#endif
+
+}  // namespace ssfft

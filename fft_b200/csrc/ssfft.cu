@@ -1,0 +1,499 @@
+// ssfft.cu -- plan construction, kernel dispatch and the C ABI of libssfft.so (include/ssfft.h).
+//
+// Host side of the boundary: replaces FFT<V>::setSize/setPlan (signalsmith-fft.h:139-185, :356-363),
+// RealFFT<V>::setSize (:416-435) and the run<inverse> dispatcher (:295-315).  There is no CPU path:
+// every exec entry point launches sm_100a kernels or returns an error.
+#include "../../include/ssfft.h"
+
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "fused.cuh"
+#include "generic.cuh"
+#include "plan.h"
+#include "planner.h"
+#include "real_kernels.cuh"
+
+using namespace ssfft;
+
+namespace {
+
+std::atomic<uint64_t> g_launches{0};
+thread_local char g_cuda_err[256] = "";
+
+int cuda_fail(cudaError_t e, const char *what) {
+    snprintf(g_cuda_err, sizeof(g_cuda_err), "%s: %s", what, cudaGetErrorString(e));
+    return SSFFT_ERR_CUDA;
+}
+#define CU(call)                                         \
+    do {                                                 \
+        cudaError_t e_ = (call);                         \
+        if (e_ != cudaSuccess) return cuda_fail(e_, #call); \
+    } while (0)
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) { ok = false; return; }
+        if (dev != prev && cudaSetDevice(dev) != cudaSuccess) ok = false;
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+int max_optin_smem(int device) {
+    int v = 0;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, device) != cudaSuccess) return 48 * 1024;
+    return v;
+}
+
+template <typename T>
+int upload_roots(void **d_out, size_t n, size_t count, size_t step) {
+    std::vector<T> h(2 * (count ? count : 1));
+    fill_roots<T>(h.data(), n, count, step);
+    CU(cudaMalloc(d_out, h.size() * sizeof(T)));
+    CU(cudaMemcpy(*d_out, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return SSFFT_OK;
+}
+
+// largest length one CTA can hold in the generic kernel's two padded shared buffers
+size_t generic_limit(size_t elem, int smem_max) {
+    size_t n = (size_t)smem_max / (2 * elem);
+    while (n > 1 && 2 * (size_t)(spad((int)n) + 1) * elem > (size_t)smem_max) --n;
+    return n;
+}
+
+template <typename T>
+int build_generic_stage(GenericStage &st, size_t n, int smem_max) {
+    st.n = (int)n;
+    st.radix = choose_radices(n);
+    st.prod.clear();
+    int P = 1, maxr = 1;
+    for (int r : st.radix) { st.prod.push_back(P); P *= r; if (r > maxr) maxr = r; }
+    if ((int)st.radix.size() > kMaxPasses) return SSFFT_ERR_UNSUPPORTED;
+    st.stage_input = radix_has_codelet(st.radix[0]) ? 0 : 1;
+    st.smem_stride = spad((int)n) + 1;
+    const size_t per = 2 * (size_t)st.smem_stride * sizeof(cx<T>);
+    if (per > (size_t)smem_max) return SSFFT_ERR_UNSUPPORTED;
+    // threads per transform: about one codelet butterfly each, power of two in [1, 256]
+    int want = (int)(n / (size_t)(maxr > 16 ? 1 : maxr));
+    if (!radix_has_codelet(maxr)) want = (int)n;  // any-radix passes parallelise over outputs
+    int tx = 1;
+    while (tx < want && tx < 256) tx *= 2;
+    st.tx = tx;
+    int fpb = 256 / tx;
+    if (fpb < 1) fpb = 1;
+    while (fpb > 1 && per * (size_t)fpb > (size_t)smem_max / 2) fpb /= 2;  // leave room for 2 CTAs/SM
+    st.fpb = fpb;
+    st.smem_bytes = per * (size_t)fpb;
+    int rc = upload_roots<T>(&st.d_roots, n, n, 1);
+    if (rc) return rc;
+    if (st.smem_bytes > 48 * 1024) {
+        CU(cudaFuncSetAttribute(generic_fft_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
+    }
+    return SSFFT_OK;
+}
+
+struct Layout {
+    long long in_outer, in_inner, in_es;
+    int in_cols;
+    long long out_outer, out_inner, out_es;
+    int out_cols;
+};
+
+template <typename T>
+int launch_generic(const ssfft_plan *pl, const GenericStage &st, const void *in, void *out, long long batch,
+                   const Layout &L, int inverse, bool epilogue, int ep_cols, cudaStream_t s) {
+    if (batch <= 0) return SSFFT_OK;
+    GenericParams<T> p;
+    memset(&p, 0, sizeof(p));
+    p.n = st.n;
+    p.npass = (int)st.radix.size();
+    for (int i = 0; i < p.npass; ++i) { p.radix[i] = st.radix[i]; p.prod[i] = st.prod[i]; }
+    p.roots = (const cx<T> *)st.d_roots;
+    p.in_outer = L.in_outer; p.in_inner = L.in_inner; p.in_es = L.in_es; p.in_cols = L.in_cols;
+    p.out_outer = L.out_outer; p.out_inner = L.out_inner; p.out_es = L.out_es; p.out_cols = L.out_cols;
+    p.inverse = inverse;
+    p.ep_lo = epilogue ? (const cx<T> *)pl->d_ep_lo : nullptr;
+    p.ep_hi = epilogue ? (const cx<T> *)pl->d_ep_hi : nullptr;
+    p.ep_shift = pl->ep_shift;
+    p.ep_cols = ep_cols > 0 ? ep_cols : 1;
+    p.batch = batch;
+    p.smem_stride = st.smem_stride;
+    p.stage_input = st.stage_input;
+    const long long blocks = (batch + st.fpb - 1) / st.fpb;
+    if (blocks > 0x7fffffffLL) return SSFFT_ERR_INVALID;
+    dim3 grid((unsigned)blocks), block((unsigned)st.tx, (unsigned)st.fpb);
+    generic_fft_kernel<T><<<grid, block, st.smem_bytes, s>>>((const cx<T> *)in, (cx<T> *)out, p);
+    ++g_launches;
+    CU(cudaGetLastError());
+    return SSFFT_OK;
+}
+
+// Complex core: batch contiguous transforms of length pl->n, in -> out (in == out allowed).
+template <typename T>
+int exec_complex(ssfft_plan *pl, const void *in, void *out, long long batch, int inverse, cudaStream_t s) {
+    const long long n = (long long)pl->n;
+    if (batch <= 0 || n == 0) return SSFFT_OK;
+    if (!pl->four_step) {
+        if (pl->fused.id >= 0)
+            return launch_fused<T>(pl->fused.id, pl->fused.d_twiddles, in, out, batch, inverse, FUSED_C2C, nullptr, s,
+                                   &g_launches);
+        Layout L{n, 0, 1, 1, n, 0, 1, 1};
+        return launch_generic<T>(pl, pl->direct, in, out, batch, L, inverse, false, 1, s);
+    }
+    // four-step: x[n1][n2] row-major.  (1) length-n1 FFTs down the n2 columns + twiddle W_n^(c*k1) into the
+    // L2-resident scratch, (2) length-n2 FFTs along rows, stored transposed: X[k1 + n1*k2].
+    const long long n1 = (long long)pl->n1, n2 = (long long)pl->n2;
+    const char *src = (const char *)in;
+    char *dst = (char *)out;
+    for (long long b0 = 0; b0 < batch; b0 += (long long)pl->chunk) {
+        const long long nb = (batch - b0 < (long long)pl->chunk) ? batch - b0 : (long long)pl->chunk;
+        const void *cin = src + (size_t)b0 * (size_t)n * pl->elem;
+        void *cout = dst + (size_t)b0 * (size_t)n * pl->elem;
+        Layout L1{n, 1, n2, (int)n2, n, 1, n2, (int)n2};
+        int rc = launch_generic<T>(pl, pl->col, cin, pl->d_scratch, nb * n2, L1, inverse, true, (int)n2, s);
+        if (rc) return rc;
+        Layout L2{n, n2, 1, (int)n1, n, 1, n1, (int)n1};
+        rc = launch_generic<T>(pl, pl->row, pl->d_scratch, cout, nb * n1, L2, inverse, false, 1, s);
+        if (rc) return rc;
+    }
+    return SSFFT_OK;
+}
+
+template <typename T>
+int build_plan_typed(ssfft_plan *pl) {
+    const int smem_max = max_optin_smem(pl->device);
+    pl->elem = sizeof(cx<T>);
+    const size_t n = pl->n;
+    char buf[512];
+    if (n == 0) { pl->desc = "empty"; return SSFFT_OK; }
+    const size_t limit = generic_limit(sizeof(cx<T>), smem_max);
+    if (n <= limit) {
+        pl->four_step = false;
+        int rc = build_generic_stage<T>(pl->direct, n, smem_max);
+        if (rc) return rc;
+        pl->fused.id = find_fused<T>(n, FUSED_CONTIG);
+        if (pl->fused.id >= 0) {
+            rc = build_fused_twiddles<T>(pl->fused.id, &pl->fused.d_twiddles);
+            if (rc) return rc;
+        }
+        std::string rs;
+        for (int r : pl->direct.radix) { rs += (rs.empty() ? "" : "x"); rs += std::to_string(r); }
+        snprintf(buf, sizeof(buf), "n=%zu single-pass %s radices=%s tx=%d fpb=%d smem=%zu", n,
+                 pl->fused.id >= 0 ? fused_name(pl->fused.id) : "generic", rs.c_str(), pl->direct.tx, pl->direct.fpb,
+                 pl->direct.smem_bytes);
+        pl->desc = buf;
+    } else {
+        size_t n1 = 0, n2 = 0;
+        if (!choose_split(n, limit, &n1, &n2)) return SSFFT_ERR_UNSUPPORTED;
+        pl->four_step = true;
+        pl->n1 = n1; pl->n2 = n2;
+        int rc = build_generic_stage<T>(pl->col, n1, smem_max);
+        if (rc) return rc;
+        rc = build_generic_stage<T>(pl->row, n2, smem_max);
+        if (rc) return rc;
+        // epilogue twiddle W_n^q, q < n, split q = hi * 2^shift + lo
+        int shift = 0;
+        while ((1ull << (2 * shift)) < n) ++shift;
+        pl->ep_shift = shift;
+        const size_t lo_count = (size_t)1 << shift, hi_count = (n + lo_count - 1) / lo_count;
+        rc = upload_roots<T>(&pl->d_ep_lo, n, lo_count, 1);
+        if (rc) return rc;
+        rc = upload_roots<T>(&pl->d_ep_hi, n, hi_count, lo_count);
+        if (rc) return rc;
+        // keep the intermediate of one chunk inside L2 (126 MB): 32 MiB of scratch
+        size_t per = n * sizeof(cx<T>);
+        pl->chunk = (32u << 20) / per;
+        if (pl->chunk < 1) pl->chunk = 1;
+        CU(cudaMalloc(&pl->d_scratch, pl->chunk * per));
+        snprintf(buf, sizeof(buf), "n=%zu four-step n1=%zu n2=%zu chunk=%zu (generic x generic)", n, n1, n2, pl->chunk);
+        pl->desc = buf;
+    }
+    if (pl->kind != SSFFT_C2C) {
+        const bool modified = pl->kind == SSFFT_REAL_MODIFIED;
+        std::vector<T> h(2 * (pl->n_real / 4 + 1));
+        fill_real_twiddles<T>(h.data(), pl->n_real, modified);
+        CU(cudaMalloc(&pl->d_rtw, h.size() * sizeof(T)));
+        CU(cudaMemcpy(pl->d_rtw, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+        if (modified) {
+            std::vector<T> r(2 * (pl->n_real / 2 ? pl->n_real / 2 : 1));
+            fill_modified_rotations<T>(r.data(), pl->n_real);
+            CU(cudaMalloc(&pl->d_rot, r.size() * sizeof(T)));
+            CU(cudaMemcpy(pl->d_rot, r.data(), r.size() * sizeof(T), cudaMemcpyHostToDevice));
+        }
+        pl->desc = std::string(modified ? "modified-real " : "real ") + "N=" + std::to_string(pl->n_real) + " core: " + pl->desc;
+    }
+    return SSFFT_OK;
+}
+
+inline unsigned blocks_for(long long items, int threads) { return (unsigned)((items + threads - 1) / threads); }
+
+template <typename T>
+int exec_r2c_typed(ssfft_plan *pl, const void *in, void *out, long long batch, cudaStream_t s) {
+    const long long h = (long long)pl->n;
+    if (h == 0 || batch <= 0) return SSFFT_OK;
+    const bool modified = pl->kind == SSFFT_REAL_MODIFIED;
+    if (!modified && !pl->four_step && pl->fused.id >= 0)
+        return launch_fused<T>(pl->fused.id, pl->fused.d_twiddles, in, out, batch, 0, FUSED_R2C, pl->d_rtw, s,
+                               &g_launches);
+    const void *src = in;  // N reals == h complex pairs (:449-455)
+    if (modified) {
+        rotate_kernel<T><<<blocks_for(h * batch, 256), 256, 0, s>>>((cx<T> *)out, (const cx<T> *)in,
+                                                                     (const cx<T> *)pl->d_rot, h, h * batch, 0);
+        ++g_launches;
+        CU(cudaGetLastError());
+        src = out;
+    }
+    int rc = exec_complex<T>(pl, src, out, batch, 0, s);
+    if (rc) return rc;
+    r2c_post_kernel<T><<<blocks_for((h / 2 + 1) * batch, 256), 256, 0, s>>>((cx<T> *)out, (const cx<T> *)pl->d_rtw, h,
+                                                                             batch, modified ? 1 : 0);
+    ++g_launches;
+    CU(cudaGetLastError());
+    return SSFFT_OK;
+}
+
+template <typename T>
+int exec_c2r_typed(ssfft_plan *pl, const void *in, void *out, long long batch, cudaStream_t s) {
+    const long long h = (long long)pl->n;
+    if (h == 0 || batch <= 0) return SSFFT_OK;
+    const bool modified = pl->kind == SSFFT_REAL_MODIFIED;
+    if (!modified && !pl->four_step && pl->fused.id >= 0)
+        return launch_fused<T>(pl->fused.id, pl->fused.d_twiddles, in, out, batch, 1, FUSED_C2R, pl->d_rtw, s,
+                               &g_launches);
+    c2r_pre_kernel<T><<<blocks_for((h / 2 + 1) * batch, 256), 256, 0, s>>>(
+        (const cx<T> *)in, (cx<T> *)out, (const cx<T> *)pl->d_rtw, h, batch, modified ? 1 : 0);
+    ++g_launches;
+    CU(cudaGetLastError());
+    int rc = exec_complex<T>(pl, out, out, batch, 1, s);
+    if (rc) return rc;
+    if (modified) {
+        rotate_kernel<T><<<blocks_for(h * batch, 256), 256, 0, s>>>((cx<T> *)out, (const cx<T> *)out,
+                                                                     (const cx<T> *)pl->d_rot, h, h * batch, 1);
+        ++g_launches;
+        CU(cudaGetLastError());
+    }
+    return SSFFT_OK;
+}
+
+void free_stage(GenericStage &st) {
+    if (st.d_roots) cudaFree(st.d_roots);
+    st.d_roots = nullptr;
+}
+
+}  // namespace
+
+// =============================================================================================
+// C ABI
+// =============================================================================================
+extern "C" {
+
+size_t ssfft_size_minimum(size_t size) { return size_minimum(size); }
+size_t ssfft_size_maximum(size_t size) { return size_maximum(size); }
+size_t ssfft_real_size_minimum(size_t size) { return real_size_minimum(size); }
+size_t ssfft_real_size_maximum(size_t size) { return real_size_maximum(size); }
+
+int ssfft_device_count(int *count) {
+    if (!count) return SSFFT_ERR_INVALID;
+    int c = 0;
+    cudaError_t e = cudaGetDeviceCount(&c);
+    if (e != cudaSuccess) { *count = 0; cuda_fail(e, "cudaGetDeviceCount"); return SSFFT_ERR_NO_DEVICE; }
+    *count = c;
+    return c > 0 ? SSFFT_OK : SSFFT_ERR_NO_DEVICE;
+}
+
+int ssfft_plan_create(ssfft_plan **out, int kind, int precision, size_t n, int device) {
+    if (!out) return SSFFT_ERR_INVALID;
+    *out = nullptr;
+    if (kind < SSFFT_C2C || kind > SSFFT_REAL_MODIFIED) return SSFFT_ERR_INVALID;
+    if (precision != SSFFT_F32 && precision != SSFFT_F64) return SSFFT_ERR_INVALID;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) {
+        cudaGetLastError();
+        return SSFFT_ERR_NO_DEVICE;  // no CPU fallback, by design
+    }
+    if (device < 0) CU(cudaGetDevice(&device));
+    if (device >= count) return SSFFT_ERR_INVALID;
+    DeviceGuard guard(device);
+    if (!guard.ok) return SSFFT_ERR_CUDA;
+    ssfft_plan *pl = new ssfft_plan();
+    pl->kind = kind; pl->prec = precision; pl->device = device;
+    pl->n_user = n;
+    if (kind == SSFFT_C2C) { pl->n = n; pl->n_real = 0; }
+    else { pl->n_real = (n / 2) * 2; pl->n = n / 2; }  // RealFFT::setSize :416-435 (odd sizes truncate)
+    int rc = precision == SSFFT_F32 ? build_plan_typed<float>(pl) : build_plan_typed<double>(pl);
+    if (rc) { ssfft_plan_destroy(pl); return rc; }
+    *out = pl;
+    return SSFFT_OK;
+}
+
+int ssfft_plan_destroy(ssfft_plan *pl) {
+    if (!pl) return SSFFT_OK;
+    DeviceGuard guard(pl->device);
+    free_stage(pl->direct); free_stage(pl->col); free_stage(pl->row);
+    void *ptrs[] = {pl->fused.d_twiddles, pl->fused_col.d_twiddles, pl->fused_row.d_twiddles, pl->d_ep_lo, pl->d_ep_hi,
+                    pl->d_scratch, pl->d_rtw, pl->d_rot, pl->d_stage_in, pl->d_stage_out};
+    for (void *p : ptrs)
+        if (p) cudaFree(p);
+    if (pl->host_stream) cudaStreamDestroy(pl->host_stream);
+    delete pl;
+    return SSFFT_OK;
+}
+
+size_t ssfft_plan_size(const ssfft_plan *pl) {
+    if (!pl) return 0;
+    return pl->kind == SSFFT_C2C ? pl->n : pl->n_real;
+}
+
+int ssfft_plan_describe(const ssfft_plan *pl, char *buf, size_t buflen) {
+    if (!pl || !buf || !buflen) return SSFFT_ERR_INVALID;
+    snprintf(buf, buflen, "%s %s", pl->prec == SSFFT_F32 ? "f32" : "f64", pl->desc.c_str());
+    return SSFFT_OK;
+}
+
+int ssfft_exec_c2c(ssfft_plan *pl, const void *d_in, void *d_out, size_t batch, int direction, void *stream) {
+    if (!pl || pl->kind != SSFFT_C2C) return SSFFT_ERR_INVALID;
+    if (direction != SSFFT_FORWARD && direction != SSFFT_INVERSE) return SSFFT_ERR_INVALID;
+    if (batch == 0 || pl->n == 0) return SSFFT_OK;
+    if (!d_in || !d_out) return SSFFT_ERR_INVALID;
+    DeviceGuard guard(pl->device);
+    const int inv = direction == SSFFT_INVERSE;
+    return pl->prec == SSFFT_F32 ? exec_complex<float>(pl, d_in, d_out, (long long)batch, inv, (cudaStream_t)stream)
+                                 : exec_complex<double>(pl, d_in, d_out, (long long)batch, inv, (cudaStream_t)stream);
+}
+
+int ssfft_exec_r2c(ssfft_plan *pl, const void *d_in, void *d_out, size_t batch, void *stream) {
+    if (!pl || pl->kind == SSFFT_C2C) return SSFFT_ERR_INVALID;
+    if (batch == 0 || pl->n == 0) return SSFFT_OK;
+    if (!d_in || !d_out) return SSFFT_ERR_INVALID;
+    DeviceGuard guard(pl->device);
+    return pl->prec == SSFFT_F32 ? exec_r2c_typed<float>(pl, d_in, d_out, (long long)batch, (cudaStream_t)stream)
+                                 : exec_r2c_typed<double>(pl, d_in, d_out, (long long)batch, (cudaStream_t)stream);
+}
+
+int ssfft_exec_c2r(ssfft_plan *pl, const void *d_in, void *d_out, size_t batch, void *stream) {
+    if (!pl || pl->kind == SSFFT_C2C) return SSFFT_ERR_INVALID;
+    if (batch == 0 || pl->n == 0) return SSFFT_OK;
+    if (!d_in || !d_out) return SSFFT_ERR_INVALID;
+    DeviceGuard guard(pl->device);
+    return pl->prec == SSFFT_F32 ? exec_c2r_typed<float>(pl, d_in, d_out, (long long)batch, (cudaStream_t)stream)
+                                 : exec_c2r_typed<double>(pl, d_in, d_out, (long long)batch, (cudaStream_t)stream);
+}
+
+int ssfft_exec_host(ssfft_plan *pl, int op, const void *h_in, void *h_out, size_t batch) {
+    if (!pl || op < 0 || op > 3) return SSFFT_ERR_INVALID;
+    if ((op <= 1) != (pl->kind == SSFFT_C2C)) return SSFFT_ERR_INVALID;
+    if (batch == 0 || pl->n == 0) return SSFFT_OK;
+    if (!h_in || !h_out) return SSFFT_ERR_INVALID;
+    DeviceGuard guard(pl->device);
+    // bytes per transform on each side: C2C n cx both; real: N reals == n cx on both sides as well
+    const size_t bytes = batch * pl->n * pl->elem;
+    if (!pl->host_stream) CU(cudaStreamCreateWithFlags(&pl->host_stream, cudaStreamNonBlocking));
+    if (pl->stage_in_bytes < bytes) {
+        if (pl->d_stage_in) cudaFree(pl->d_stage_in);
+        pl->d_stage_in = nullptr; pl->stage_in_bytes = 0;
+        CU(cudaMalloc(&pl->d_stage_in, bytes));
+        pl->stage_in_bytes = bytes;
+    }
+    if (pl->stage_out_bytes < bytes) {
+        if (pl->d_stage_out) cudaFree(pl->d_stage_out);
+        pl->d_stage_out = nullptr; pl->stage_out_bytes = 0;
+        CU(cudaMalloc(&pl->d_stage_out, bytes));
+        pl->stage_out_bytes = bytes;
+    }
+    // pipeline in slices so H2D, kernels and D2H overlap (PCIe is full duplex)
+    cudaStream_t s = pl->host_stream;
+    size_t slices = 1;
+    const size_t per = pl->n * pl->elem;
+    if (bytes > (64u << 20)) slices = 8;
+    if (slices > batch) slices = batch;
+    cudaStream_t extra[2] = {nullptr, nullptr};
+    if (slices > 1)
+        for (auto &e : extra) CU(cudaStreamCreateWithFlags(&e, cudaStreamNonBlocking));
+    int rc = SSFFT_OK;
+    for (size_t i = 0; i < slices && rc == SSFFT_OK; ++i) {
+        const size_t b0 = batch * i / slices, b1 = batch * (i + 1) / slices;
+        cudaStream_t cs = slices > 1 ? (i % 3 == 0 ? s : extra[i % 3 - 1]) : s;
+        const char *hi = (const char *)h_in + b0 * per;
+        char *ho = (char *)h_out + b0 * per;
+        char *di = (char *)pl->d_stage_in + b0 * per, *dout = (char *)pl->d_stage_out + b0 * per;
+        cudaError_t e = cudaMemcpyAsync(di, hi, (b1 - b0) * per, cudaMemcpyHostToDevice, cs);
+        if (e != cudaSuccess) { rc = cuda_fail(e, "H2D"); break; }
+        if (op == 0) rc = ssfft_exec_c2c(pl, di, dout, b1 - b0, SSFFT_FORWARD, cs);
+        else if (op == 1) rc = ssfft_exec_c2c(pl, di, dout, b1 - b0, SSFFT_INVERSE, cs);
+        else if (op == 2) rc = ssfft_exec_r2c(pl, di, dout, b1 - b0, cs);
+        else rc = ssfft_exec_c2r(pl, di, dout, b1 - b0, cs);
+        if (rc) break;
+        e = cudaMemcpyAsync(ho, dout, (b1 - b0) * per, cudaMemcpyDeviceToHost, cs);
+        if (e != cudaSuccess) { rc = cuda_fail(e, "D2H"); break; }
+    }
+    cudaError_t e1 = cudaStreamSynchronize(s);
+    for (auto &e : extra)
+        if (e) { cudaError_t e2 = cudaStreamSynchronize(e); if (e1 == cudaSuccess) e1 = e2; cudaStreamDestroy(e); }
+    if (rc) return rc;
+    if (e1 != cudaSuccess) return cuda_fail(e1, "cudaStreamSynchronize");
+    return SSFFT_OK;
+}
+
+int ssfft_malloc(void **d_ptr, size_t bytes) {
+    if (!d_ptr) return SSFFT_ERR_INVALID;
+    *d_ptr = nullptr;
+    if (cudaMalloc(d_ptr, bytes ? bytes : 1) != cudaSuccess) { cudaGetLastError(); return SSFFT_ERR_ALLOC; }
+    return SSFFT_OK;
+}
+int ssfft_free(void *d_ptr) {
+    if (d_ptr) CU(cudaFree(d_ptr));
+    return SSFFT_OK;
+}
+int ssfft_memcpy_h2d(void *d_dst, const void *h_src, size_t bytes, void *stream) {
+    if (!bytes) return SSFFT_OK;
+    CU(cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    return SSFFT_OK;
+}
+int ssfft_memcpy_d2h(void *h_dst, const void *d_src, size_t bytes, void *stream) {
+    if (!bytes) return SSFFT_OK;
+    CU(cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    return SSFFT_OK;
+}
+int ssfft_stream_synchronize(void *stream) {
+    CU(cudaStreamSynchronize((cudaStream_t)stream));
+    return SSFFT_OK;
+}
+int ssfft_fill_uniform(void *d_dst, size_t count, int precision, uint64_t seed, uint64_t first_idx, void *stream) {
+    if (!count) return SSFFT_OK;
+    if (!d_dst) return SSFFT_ERR_INVALID;
+    unsigned blocks = (unsigned)((count + 255) / 256 > 148 * 32 ? 148 * 32 : (count + 255) / 256);
+    if (precision == SSFFT_F32)
+        fill_uniform_kernel<float><<<blocks, 256, 0, (cudaStream_t)stream>>>((float *)d_dst, count, seed, first_idx);
+    else if (precision == SSFFT_F64)
+        fill_uniform_kernel<double><<<blocks, 256, 0, (cudaStream_t)stream>>>((double *)d_dst, count, seed, first_idx);
+    else
+        return SSFFT_ERR_INVALID;
+    ++g_launches;
+    CU(cudaGetLastError());
+    return SSFFT_OK;
+}
+
+const char *ssfft_error_string(int status) {
+    switch (status) {
+        case SSFFT_OK: return "ok";
+        case SSFFT_ERR_INVALID: return "invalid argument";
+        case SSFFT_ERR_CUDA: return "CUDA runtime error";
+        case SSFFT_ERR_UNSUPPORTED: return "unsupported size (prime factor too large for the on-chip paths)";
+        case SSFFT_ERR_NO_DEVICE: return "no CUDA device (this library has no CPU fallback)";
+        case SSFFT_ERR_ALLOC: return "device allocation failed";
+        default: return "unknown status";
+    }
+}
+const char *ssfft_last_cuda_error(void) { return g_cuda_err; }
+uint64_t ssfft_launch_count(void) { return g_launches.load(); }
+const char *ssfft_version(void) { return "ssfft-b200 0.1 (sm_100a)"; }
+
+}  // extern "C"

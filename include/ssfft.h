@@ -1,0 +1,116 @@
+/*
+ * ssfft.h -- C ABI of libssfft.so: the B200 (sm_100a) implementation of the Signalsmith FFT hot path.
+ *
+ * The reference (/root/reference/signalsmith-fft.h) is a header-only C++ class template with no FFI
+ * layer; its public surface is FFT<V> (:326-387) and RealFFT<V,flags> (:402-503).  This ABI is what a
+ * binding of that surface binds: one entry point per reference method on the transform path, plain
+ * pointers and sizes, int status returns (0 = OK), nothing thrown across the boundary.  The header-only
+ * C++ front end include/signalsmith-fft.h forwards to these symbols; INTEGRATION.md shows other bindings.
+ *
+ * Conventions (all taken from the reference):
+ *   - complex data is interleaved (re, im): float2 / double2 == std::complex<float/double>
+ *   - forward transform X[k] = sum_n x[n] exp(-2 pi i n k / N); both directions UNNORMALISED
+ *     (ifft(fft(x)) == N * x, tests/00-fft.cpp:113-128)
+ *   - out-of-place; the input is never modified (tests/00-fft.cpp:44-46); in == out is also accepted
+ *   - batches are contiguous: transform b of a C2C plan lives at in + b*N complex; a real plan reads
+ *     N reals at in + b*N and writes N/2 complex at out + b*(N/2), with bin 0 packing
+ *     (DC, Nyquist) into (.re, .im) (signalsmith-fft.h:459-462)
+ *   - there is NO CPU fallback and no cuFFT: every exec call launches hand-written sm_100a kernels
+ */
+#ifndef SSFFT_H
+#define SSFFT_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define SSFFT_API __attribute__((visibility("default")))
+#else
+#define SSFFT_API
+#endif
+
+typedef struct ssfft_plan ssfft_plan;
+
+/* status codes */
+enum {
+    SSFFT_OK = 0,
+    SSFFT_ERR_INVALID = 1,      /* bad argument (null pointer, wrong plan kind, ...) */
+    SSFFT_ERR_CUDA = 2,         /* a CUDA runtime call failed; see ssfft_last_cuda_error() */
+    SSFFT_ERR_UNSUPPORTED = 3,  /* size has a prime factor too large for the on-chip paths */
+    SSFFT_ERR_NO_DEVICE = 4,    /* no CUDA device: the library never falls back to the CPU */
+    SSFFT_ERR_ALLOC = 5
+};
+
+/* plan kinds */
+enum {
+    SSFFT_C2C = 0,           /* FFT<V>                         signalsmith-fft.h:69-387  */
+    SSFFT_REAL = 1,          /* RealFFT<V, 0>                  signalsmith-fft.h:393-503 */
+    SSFFT_REAL_MODIFIED = 2  /* RealFFT<V, halfFreqShift> == ModifiedRealFFT<V>  :389-391, :505-508 */
+};
+/* precisions */
+enum { SSFFT_F32 = 0, SSFFT_F64 = 1 };
+/* directions for ssfft_exec_c2c */
+enum { SSFFT_FORWARD = 1, SSFFT_INVERSE = -1 };
+
+/* ---- size helpers (pure integer; usable without a GPU) ---- */
+/* FFT<V>::sizeMinimum / sizeMaximum        signalsmith-fft.h:327-348 */
+SSFFT_API size_t ssfft_size_minimum(size_t size);
+SSFFT_API size_t ssfft_size_maximum(size_t size);
+/* RealFFT<V>::sizeMinimum / sizeMaximum    signalsmith-fft.h:403-408 (quirks reproduced) */
+SSFFT_API size_t ssfft_real_size_minimum(size_t size);
+SSFFT_API size_t ssfft_real_size_maximum(size_t size);
+
+/* ---- plans: replace FFT::setSize -> setPlan (:139-185, :356-363) and RealFFT::setSize (:416-435) ----
+ * n is the transform length (the REAL length for real plans; odd n truncates to 2*(n/2) like the
+ * reference).  device < 0 means the current device.  Twiddle tables are built here and live in HBM. */
+SSFFT_API int ssfft_plan_create(ssfft_plan **out, int kind, int precision, size_t n, int device);
+SSFFT_API int ssfft_plan_destroy(ssfft_plan *plan);
+/* length the plan transforms (real plans: 2*(n/2), as RealFFT::size() :442-444) */
+SSFFT_API size_t ssfft_plan_size(const ssfft_plan *plan);
+/* human-readable plan: factors, passes, kernel choice (tests pin the plan builder with this) */
+SSFFT_API int ssfft_plan_describe(const ssfft_plan *plan, char *buf, size_t buflen);
+
+/* ---- execution on DEVICE pointers, asynchronous on `stream` (a cudaStream_t, may be NULL) ---- */
+/* FFT<V>::fft (:374-379) when direction == SSFFT_FORWARD, FFT<V>::ifft (:381-386) when SSFFT_INVERSE */
+SSFFT_API int ssfft_exec_c2c(ssfft_plan *plan, const void *d_in, void *d_out, size_t batch, int direction,
+                             void *stream);
+/* RealFFT<V>::fft (:446-473): batch x N reals -> batch x N/2 complex */
+SSFFT_API int ssfft_exec_r2c(ssfft_plan *plan, const void *d_real_in, void *d_cplx_out, size_t batch,
+                             void *stream);
+/* RealFFT<V>::ifft (:475-502): batch x N/2 complex -> batch x N reals (scaled by N) */
+SSFFT_API int ssfft_exec_c2r(ssfft_plan *plan, const void *d_cplx_in, void *d_real_out, size_t batch,
+                             void *stream);
+
+/* ---- execution on HOST pointers: the call a reference user makes (fft(in, out) on host containers).
+ * Stages host -> device (pinned staging buffers owned by the plan), runs the device path above, copies
+ * back, and returns when `h_out` is complete.  kind-specific meaning of in/out as for the device calls:
+ * op = 0 C2C forward, 1 C2C inverse, 2 R2C, 3 C2R. */
+SSFFT_API int ssfft_exec_host(ssfft_plan *plan, int op, const void *h_in, void *h_out, size_t batch);
+
+/* ---- device-memory helpers so the header-only front end needs no CUDA headers ---- */
+SSFFT_API int ssfft_device_count(int *count);
+SSFFT_API int ssfft_malloc(void **d_ptr, size_t bytes);
+SSFFT_API int ssfft_free(void *d_ptr);
+SSFFT_API int ssfft_memcpy_h2d(void *d_dst, const void *h_src, size_t bytes, void *stream);
+SSFFT_API int ssfft_memcpy_d2h(void *h_dst, const void *d_src, size_t bytes, void *stream);
+SSFFT_API int ssfft_stream_synchronize(void *stream);
+/* synthetic inputs, i.i.d. uniform [-0.5, 0.5) from the counter-based generator shared with the
+ * oracle: count scalars starting at scalar index first_idx */
+SSFFT_API int ssfft_fill_uniform(void *d_dst, size_t count, int precision, uint64_t seed, uint64_t first_idx,
+                                 void *stream);
+
+/* ---- diagnostics ---- */
+SSFFT_API const char *ssfft_error_string(int status);
+SSFFT_API const char *ssfft_last_cuda_error(void);
+/* number of kernels this library has launched since load (bench.py reports it as gpu_launches) */
+SSFFT_API uint64_t ssfft_launch_count(void);
+SSFFT_API const char *ssfft_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SSFFT_H */
