@@ -1,0 +1,368 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the FFT hot path (BASELINE.json metric), one JSON line on stdout.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --steps K --warmup W    # the reference's own CPU path (oracle/_ref)
+
+A "step" is one pass of the hot path over one batch of synthetic input.  Default workload = BASELINE
+config 2: FFT<float> C2C, N=4096 x 65536 transforms per GPU (4.29 GB of algorithmic HBM traffic per step,
+34x the 126 MB L2, so no L2 flush is needed between steps).  Multi-GPU runs shard by batch (weak scaling:
+every rank transforms its own 65536 x 4096 batch; there is no collective on the data path).
+
+  value     whole-job GFLOP/s (5 N log2 N per transform), inputs resident in HBM, CUDA-event timed
+  e2e       same metric through the host-pointer call a reference user makes (ssfft_exec_host):
+            pinned host buffers, H2D + kernels + D2H all inside the timed region
+  roofline  algorithmic bytes (2 * N * sizeof(complex) per transform) / kernel time vs measured HBM peak
+  cpu_baseline  the reference's CPU implementation on this box's host cores (reported, not a target)
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "Batched fp32 C2C FFT GFLOP/s (5N·log2N) & % of HBM roofline, N=4096"
+SEED = 20261017
+
+WORKLOADS = {
+    # name: (kind, dtype, N, batch)
+    "c2": ("c2c", "float32", 4096, 65536),
+    "c3": ("real", "float32", 65536, 8192),
+    "c4-1000": ("c2c", "float32", 1000, 65536),
+    "c4-2187": ("c2c", "float32", 2187, 65536),
+    "c4-3125": ("c2c", "float32", 3125, 65536),
+    "c4-6000": ("c2c", "float32", 6000, 65536),
+    "c4-1000-f64": ("c2c", "float64", 1000, 65536),
+    "c4-2187-f64": ("c2c", "float64", 2187, 65536),
+    "c4-3125-f64": ("c2c", "float64", 3125, 65536),
+    "c4-6000-f64": ("c2c", "float64", 6000, 65536),
+    "c1": ("c2c", "float64", 1024, 1),
+}
+
+
+def flops_per_transform(kind, n):
+    # complex: 5 N log2 N; real: 2.5 N log2 N per direction, forward + inverse are both run
+    return 5.0 * n * math.log2(n) if kind == "c2c" else 2 * 2.5 * n * math.log2(n)
+
+
+def alg_bytes_per_transform(kind, n, dtype):
+    sz = 4 if dtype == "float32" else 8
+    # C2C: read N complex + write N complex.  Real fwd+inv: 2 * (N reals + N/2 complex) = 4 N reals
+    return 2 * n * 2 * sz if kind == "c2c" else 4 * n * sz
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md: 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.lines:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU implementation of the path on this box's host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    import numpy as np
+    from oracle import oracle as O  # the one place bench.py may execute oracle/
+
+    kind, dtype, n, batch = WORKLOADS[args.workload]
+    impl = "reference" if O.have_reference() else "port"
+    cores = os.cpu_count() or 1
+    rdt = np.float32 if dtype == "float32" else np.float64
+    # bounded sample: ~15 CPU-seconds of transforms per step, never more than the workload itself
+    probe = O.uniform(2 * n * 64 if kind == "c2c" else n * 64, SEED, rdt)
+    probe = probe.view(np.complex64 if dtype == "float32" else np.complex128).reshape(64, n) if kind == "c2c" \
+        else probe.reshape(64, n)
+    k_fwd = O.KIND_C2C_FWD if kind == "c2c" else O.KIND_R2C
+    t0 = time.perf_counter()
+    O.run(k_fwd, probe, n, 1, impl)
+    per = max((time.perf_counter() - t0) / 64, 1e-7)
+    sample = int(min(batch, max(cores * 8, 15.0 / per / max(args.steps + args.warmup, 1))))
+    x = O.uniform((2 if kind == "c2c" else 1) * n * sample, SEED, rdt)
+    x = x.view(np.complex64 if dtype == "float32" else np.complex128).reshape(sample, n) if kind == "c2c" \
+        else x.reshape(sample, n)
+
+    def step():
+        if kind == "c2c":
+            return O.run(O.KIND_C2C_FWD, x, n, cores, impl)[1]
+        y, s1 = O.run(O.KIND_R2C, x, n, cores, impl)
+        _, s2 = O.run(O.KIND_C2R, y, n, cores, impl)
+        return s1 + s2
+
+    for _ in range(args.warmup):
+        step()
+    secs = [step() for _ in range(args.steps)]
+    total = sum(secs)
+    value = sample * args.steps * flops_per_transform(kind, n) / total / 1e9
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "GFLOP/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32" if dtype == "float32" else "f64",
+        "data": "synthetic uniform[-0.5,0.5), counter-based generator, seed %d" % SEED,
+        "config": {"workload": f"{args.workload}: {kind} {dtype} N={n} x {batch} (CPU sample {sample} per step)"},
+        "cpu_baseline": {"value": value, "unit": "GFLOP/s", "cores": cores, "kind": impl,
+                         "sample": f"{sample} transforms of N={n} per step, batch split over {cores} host threads, "
+                                   "one FFT object per thread, plan build excluded"},
+        "e2e": {"value": value, "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=0, help="override transforms per GPU (tests only)")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import fft_b200
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    kind, dtype, n, batch = WORKLOADS[args.workload]
+    if args.batch:
+        batch = args.batch
+    tdt = torch.float32 if dtype == "float32" else torch.float64
+    cdt = torch.complex64 if dtype == "float32" else torch.complex128
+    esz = 4 if dtype == "float32" else 8
+
+    # ---- inputs resident in HBM (each rank its own slice of the global synthetic stream)
+    if kind == "c2c":
+        plan = fft_b200.FFT(n, dtype=dtype)
+        x = torch.empty((batch, n), dtype=cdt, device=dev)
+        y = torch.empty_like(x)
+        fft_b200.fill_uniform(x, SEED, first_idx=rank * batch * n * 2)
+
+        def step():
+            plan.fft(x, y)
+    else:
+        plan = fft_b200.RealFFT(n, dtype=dtype)
+        x = torch.empty((batch, n), dtype=tdt, device=dev)
+        y = torch.empty((batch, n // 2), dtype=cdt, device=dev)
+        z = torch.empty_like(x)
+        fft_b200.fill_uniform(x, SEED, first_idx=rank * batch * n)
+
+        def step():
+            plan.fft(x, y)
+            plan.ifft(y, z)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.25)
+    launches0 = fft_b200.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        step()
+    ev1.record()
+    barrier()
+    ms_total = ev0.elapsed_time(ev1)
+    launches = fft_b200.launch_count() - launches0
+    # keep the GPU busy a little longer so the clock sampler sees load even for short runs
+    if rank == 0:
+        t_end = time.time() + 0.6
+        while time.time() < t_end:
+            step()
+        torch.cuda.synchronize()
+    clocks = sampler.stop() if rank == 0 else None
+    if world > 1:
+        t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    ms_step = ms_total / args.steps
+    flops_step = world * batch * flops_per_transform(kind, n)
+    value = flops_step / (ms_step * 1e-3) / 1e9
+    bytes_step_gpu = batch * alg_bytes_per_transform(kind, n, dtype)
+    peak, peak_src = measured_peak()
+    achieved = bytes_step_gpu / (ms_step * 1e-3) / 1e9  # per GPU
+
+    # ---- end to end through the host-pointer API (pinned host memory, H2D + D2H inside the timed region)
+    e2e = None
+    if not args.no_e2e:
+        e2e_steps = max(1, min(args.steps, 8))
+        host_in = torch.empty(x.shape, dtype=x.dtype, pin_memory=True)
+        host_in.copy_(x)
+        host_out = torch.empty(y.shape if kind == "c2c" else x.shape, dtype=(cdt if kind == "c2c" else tdt), pin_memory=True)
+        host_mid = torch.empty(y.shape, dtype=cdt, pin_memory=True) if kind != "c2c" else None
+        torch.cuda.synchronize()
+        hin, hout = host_in.numpy(), host_out.numpy()
+        hmid = host_mid.numpy() if host_mid is not None else None
+
+        def e2e_step():
+            if kind == "c2c":
+                plan.fft(hin, hout)
+            else:
+                plan.fft(hin, hmid)
+                plan.ifft(hmid, hout)
+
+        e2e_step()  # warm the staging buffers
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            e2e_step()
+        torch.cuda.synchronize()
+        el = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([el], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            el = float(t.item())
+        io = batch * n * 2 * esz if kind == "c2c" else batch * n * esz
+        e2e = {"value": flops_step * e2e_steps / el / 1e9, "unit": "GFLOP/s",
+               "h2d_bytes_per_step": io if kind == "c2c" else 2 * io, "d2h_bytes_per_step": io if kind == "c2c" else 2 * io,
+               "ms_per_step": 1e3 * el / e2e_steps, "steps": e2e_steps,
+               "api": "fft_b200.FFT.fft(host_in, host_out) -> ssfft_exec_host (pinned buffers, sliced H2D/compute/D2H overlap)"}
+        # sanity: the e2e result equals the device-resident result
+        if kind == "c2c":
+            assert torch.equal(host_out[:4], y[:4].cpu()), "e2e output differs from device output"
+        del host_in, host_out
+
+    # ---- CPU baseline: the reference's own implementation on this box's host cores (rank 0, N=1 only)
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        from oracle import oracle as O  # checker / baseline only
+
+        impl = "reference" if O.have_reference() else "port"
+        cores = os.cpu_count() or 1
+        per_transform_s = 60e-6 * (n * math.log2(n)) / (4096 * 12) * (20 if any(n % p == 0 for p in (5, 7, 11, 13)) else 1)
+        sample = int(min(batch, max(cores * 4, 15.0 / per_transform_s)))
+        xs = x[:sample].cpu().numpy()
+        k = O.KIND_C2C_FWD if kind == "c2c" else O.KIND_R2C
+        O.run(k, xs[: max(cores, 1)], n, cores, impl)
+        best = None
+        for _ in range(2):
+            if kind == "c2c":
+                secs = O.run(k, xs, n, cores, impl)[1]
+            else:
+                ys, s1 = O.run(O.KIND_R2C, xs, n, cores, impl)
+                secs = s1 + O.run(O.KIND_C2R, ys, n, cores, impl)[1]
+            best = secs if best is None else min(best, secs)
+        cpu = {"value": sample * flops_per_transform(kind, n) / best / 1e9, "unit": "GFLOP/s", "cores": cores,
+               "kind": impl,
+               "sample": f"{sample} of the {batch} transforms (same synthetic inputs), batch split over {cores} host "
+                         f"threads, one {'FFT' if kind == 'c2c' else 'RealFFT'}<{dtype}> object per thread, plan "
+                         "build excluded, best of 2"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": "GFLOP/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32" if dtype == "float32" else "f64",
+            "data": f"synthetic uniform[-0.5,0.5), counter-based generator (device twin of the oracle's), seed {SEED}",
+            "config": {"workload": f"{args.workload}: {kind} {dtype} N={n} x {batch} transforms per GPU"
+                                   + (" (forward + inverse per step)" if kind != "c2c" else " (forward)"),
+                       "plan": plan.describe(), "parallelism": f"batch-sharded x{world}, no collective",
+                       "l2": f"working set {2 * batch * n * (2 if kind == 'c2c' else 1) * esz / 2**20:.0f} MiB per GPU "
+                             ">> 126 MB L2 (inputs larger than L2, no flush needed)"},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_step_per_gpu": bytes_step_gpu,
+                         "kernel_ms": ms_step},
+            "clocks": clocks, "gpu_launches": launches,
+        }
+        if e2e:
+            line["e2e"] = e2e
+        if cpu:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())
