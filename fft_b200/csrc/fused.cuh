@@ -29,10 +29,13 @@ namespace ssfft {
 enum { FUSED_C2C = 0, FUSED_R2C = 1, FUSED_C2R = 2 };
 enum { FUSED_CONTIG = 0 };
 
-template <typename T_, int N_, int R0_, int R1_, int R2_, int R3_, int TX_, int FPB_, int MINB_, int PADSHIFT_ = 4>
+template <typename T_, int N_, int R0_, int R1_, int R2_, int R3_, int TX_, int FPB_, int MINB_, int PADSHIFT_ = 4, int PF_ = 0>
 struct FusedCfg {
     using T = T_;
     static constexpr int N = N_, TX = TX_, FPB = FPB_, MINB = MINB_, PADSHIFT = PADSHIFT_;
+    // PF = 1: the next group of transforms is prefetched HBM -> shared staging buffer by one TMA bulk copy
+    // (cp.async.bulk + mbarrier) while the current group is being transformed.
+    static constexpr int PF = PF_;
     static constexpr int NP = (R3_ > 1) ? 4 : (R2_ > 1) ? 3 : (R1_ > 1) ? 2 : 1;
     static constexpr int E = N / TX;
     __host__ __device__ static constexpr int radix(int i) { return i == 0 ? R0_ : i == 1 ? R1_ : i == 2 ? R2_ : R3_; }
@@ -47,7 +50,11 @@ struct FusedCfg {
     static constexpr int tw_total = tw_off(NP - 1);
     __host__ __device__ static constexpr int pad(int e) { return e + (e >> PADSHIFT); }
     static constexpr int SM_STRIDE = pad(N) + 1;  // cx elements of shared memory per transform
-    static constexpr size_t smem_bytes = (size_t)SM_STRIDE * FPB * sizeof(cx<T>);
+    static constexpr size_t xchg_bytes = (((size_t)SM_STRIDE * FPB * sizeof(cx<T>)) + 127) / 128 * 128;
+    static constexpr size_t stage_bytes = PF ? (size_t)N * FPB * sizeof(cx<T>) : 0;
+    static constexpr size_t smem_bytes = xchg_bytes + stage_bytes;
+    static_assert(!PF || ((size_t)N * FPB * sizeof(cx<T>)) % 16 == 0, "bulk copies need 16-byte multiples: use an even FPB");
+    static_assert(!PF || (R1_ > 1), "prefetch variant needs at least two passes");
     static_assert(R0_ * R1_ * R2_ * R3_ == N_, "radices must multiply to N");
     static_assert(N_ % TX_ == 0, "TX must divide N");
     static_assert(E % R0_ == 0 && E % R1_ == 0 && E % R2_ == 0 && E % R3_ == 0, "E must be a multiple of every radix");
@@ -79,6 +86,31 @@ __device__ __forceinline__ cx<T> ld_table(const cx<T> *p) {
     return mk<T>(v.x, v.y);
 }
 
+// ---- TMA bulk copy + mbarrier (sm_90+/sm_100a PTX; SASS: UBLKCP / SYNCS)
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, unsigned bytes, unsigned long long *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
 template <typename Cfg>
 __global__ void __launch_bounds__(Cfg::TX *Cfg::FPB, Cfg::MINB)
 fused_fft_kernel(const cx<typename Cfg::T> *__restrict__ in, cx<typename Cfg::T> *__restrict__ out,
@@ -86,10 +118,38 @@ fused_fft_kernel(const cx<typename Cfg::T> *__restrict__ in, cx<typename Cfg::T>
                  long long batch, int inverse, int mode) {
     using T = typename Cfg::T;
     constexpr int N = Cfg::N, TX = Cfg::TX, FPB = Cfg::FPB, E = Cfg::E, NP = Cfg::NP;
-    extern __shared__ __align__(16) unsigned char ssfft_smem[];
+    constexpr bool PF = Cfg::PF != 0;
+    extern __shared__ __align__(128) unsigned char ssfft_smem[];
+    __shared__ __align__(8) unsigned long long mbar;
     const int t = threadIdx.x, f = threadIdx.y;
     cx<T> *sm = reinterpret_cast<cx<T> *>(ssfft_smem) + (size_t)f * Cfg::SM_STRIDE;
+    const cx<T> *stage_all = reinterpret_cast<const cx<T> *>(ssfft_smem + Cfg::xchg_bytes);
+    const cx<T> *stage = stage_all + (size_t)f * N;
     const long long groups = (batch + FPB - 1) / FPB;
+    const bool leader = (t == 0 && f == 0);
+    unsigned parity = 0;
+
+    // one thread asks the TMA engine for a whole group of transforms (contiguous in HBM).  Bulk copies
+    // move multiples of 16 bytes: a ragged last group of an odd-length size falls back to plain loads.
+    auto group_bytes = [&](long long g) -> unsigned {
+        const long long first_tr = g * FPB;
+        const long long cnt = (batch - first_tr < FPB) ? (batch - first_tr) : FPB;
+        return (unsigned)(cnt * N * sizeof(cx<T>));
+    };
+    auto prefetch = [&](long long g) {
+        if (leader && g < groups) {
+            const unsigned bytes = group_bytes(g);
+            if (bytes % 16 == 0) {
+                mbar_expect_tx(&mbar, bytes);
+                bulk_g2s(const_cast<cx<T> *>(stage_all), in + g * FPB * N, bytes, &mbar);
+            }
+        }
+    };
+    if constexpr (PF) {
+        if (leader) mbar_init(&mbar, 1);
+        __syncthreads();
+        prefetch(blockIdx.x);
+    }
 
     for (long long g = blockIdx.x; g < groups; g += gridDim.x) {
         const long long tr = g * FPB + f;
@@ -97,6 +157,22 @@ fused_fft_kernel(const cx<typename Cfg::T> *__restrict__ in, cx<typename Cfg::T>
         const cx<T> *gin = in + (active ? tr : 0) * N;
         cx<T> *gout = out + (active ? tr : 0) * N;
         cx<T> v[E];
+        if constexpr (PF) {
+            const unsigned bytes = group_bytes(g);
+            if (bytes % 16 == 0) {
+                mbar_wait(&mbar, parity);  // this group's input has landed in the staging buffer
+                parity ^= 1u;
+            } else {  // ragged tail: cooperative plain copy into the staging buffer
+                cx<T> *st = const_cast<cx<T> *>(stage_all);
+                const int n_el = (int)(bytes / sizeof(cx<T>));
+                for (int i = f * TX + t; i < n_el; i += TX * FPB) st[i] = ld_stream(in + g * FPB * N + i);
+                __syncthreads();
+            }
+        }
+        auto load_in = [&](int idx) -> cx<T> {
+            if constexpr (PF) return stage[idx];
+            else return ld_stream(gin + idx);
+        };
 
         // ---------------- C2R prologue: pre-twiddle pairs into shared memory (RealFFT::ifft :478-492)
         if (mode == FUSED_C2R) {
@@ -104,18 +180,19 @@ fused_fft_kernel(const cx<typename Cfg::T> *__restrict__ in, cx<typename Cfg::T>
                 constexpr int H2 = N / 2 + 1;
                 for (int i = t; i < H2; i += TX) {
                     if (i == 0) {
-                        cx<T> a = ld_stream(gin);
+                        cx<T> a = load_in(0);
                         sm[Cfg::pad(0)] = mk<T>(a.x + a.y, a.x - a.y);
                     } else {
                         const int ci = N - i;
                         cx<T> bi, bc;
-                        c2r_pair(ld_stream(gin + i), ld_stream(gin + ci), ld_table(rtw + i), bi, bc);
+                        c2r_pair(load_in(i), load_in(ci), ld_table(rtw + i), bi, bc);
                         sm[Cfg::pad(i)] = bi;
                         sm[Cfg::pad(ci)] = bc;
                     }
                 }
             }
             __syncthreads();
+            if constexpr (PF) prefetch(g + gridDim.x);  // staging buffer fully consumed
         }
 
         sfor<0, NP>([&](auto pc) {
@@ -130,17 +207,17 @@ fused_fft_kernel(const cx<typename Cfg::T> *__restrict__ in, cx<typename Cfg::T>
 #pragma unroll
                         for (int j = 0; j < R; ++j) v[u * R + j] = cswap(sm[Cfg::pad(t + TX * u + NR * j)]);
                     __syncthreads();
-                } else if (active) {
+                } else if (PF || active) {
                     if (inverse) {
 #pragma unroll
                         for (int u = 0; u < U; ++u)
 #pragma unroll
-                            for (int j = 0; j < R; ++j) v[u * R + j] = cswap(ld_stream(gin + t + TX * u + NR * j));
+                            for (int j = 0; j < R; ++j) v[u * R + j] = cswap(load_in(t + TX * u + NR * j));
                     } else {
 #pragma unroll
                         for (int u = 0; u < U; ++u)
 #pragma unroll
-                            for (int j = 0; j < R; ++j) v[u * R + j] = ld_stream(gin + t + TX * u + NR * j);
+                            for (int j = 0; j < R; ++j) v[u * R + j] = load_in(t + TX * u + NR * j);
                     }
                 }
             } else {
@@ -178,6 +255,9 @@ fused_fft_kernel(const cx<typename Cfg::T> *__restrict__ in, cx<typename Cfg::T>
                     for (int r = 0; r < R; ++r) sm[Cfg::pad(o + P * r)] = v[u * R + r];
                 }
                 __syncthreads();
+                if constexpr (PF && first) {
+                    if (mode != FUSED_C2R) prefetch(g + gridDim.x);  // every thread has consumed the staging buffer
+                }
             } else {
                 // last pass: P == N/R, m' == 0, racc == b  ->  natural-order index b + P*r
                 if (mode == FUSED_R2C) {

@@ -1,0 +1,219 @@
+// signalsmith-fft.h (B200 edition) -- header-only C++ front end over the C ABI in ssfft.h.
+//
+// Source-compatible with the reference header of the same name: namespace macro SIGNALSMITH_FFT_NAMESPACE,
+// classes FFT<V>, RealFFT<V, flags>, ModifiedRealFFT<V>, FFTOptions, and the methods setSize /
+// setSizeMinimum / setSizeMaximum / size / fft / ifft / static sizeMinimum / sizeMaximum with the same
+// argument meaning and return types (reference: signalsmith-fft.h:326-387, :389-391, :402-503, :505-508).
+// The transforms run on the GPU: every call forwards to libssfft.so (hand-written sm_100a kernels).
+// There is no CPU fallback; failures (no device, CUDA error, unsupported size) throw std::runtime_error,
+// the closest analogue of the std::bad_alloc the reference can throw from setSize.
+//
+// Two ways to call fft()/ifft():
+//   1. the reference's way -- host containers or iterators:   fft.fft(input, output);
+//      data is staged through the device (one transform), results are identical in layout and scaling;
+//   2. NEW batched device-pointer overloads:                   fft.fft(d_in, d_out, batch, stream);
+//      `batch` contiguous transforms, asynchronous on `stream` (a cudaStream_t passed as void*).
+//
+// Conventions kept from the reference: unnormalised in both directions (ifft(fft(x)) == N*x); RealFFT
+// packs DC into output[0].real() and Nyquist into output[0].imag() and writes only N/2 bins;
+// RealFFT::setSize() returns N/2 while size() returns N; odd real sizes truncate to 2*(N/2).
+#ifndef SIGNALSMITH_FFT_B200_V1
+#define SIGNALSMITH_FFT_B200_V1
+#ifndef SIGNALSMITH_FFT_NAMESPACE
+#define SIGNALSMITH_FFT_NAMESPACE signalsmith
+#endif
+
+#include <complex>
+#include <cstddef>
+#include <iterator>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <type_traits>
+#include <utility>
+#include <vector>
+
+#include "ssfft.h"
+
+namespace SIGNALSMITH_FFT_NAMESPACE {
+
+namespace b200_detail {
+template <typename V> struct Precision;
+template <> struct Precision<float> { static constexpr int value = SSFFT_F32; };
+template <> struct Precision<double> { static constexpr int value = SSFFT_F64; };
+
+inline void check(int status, const char *what) {
+    if (status != SSFFT_OK) {
+        std::string msg = std::string(what) + ": " + ssfft_error_string(status);
+        if (status == SSFFT_ERR_CUDA) msg += std::string(" [") + ssfft_last_cuda_error() + "]";
+        throw std::runtime_error(msg);
+    }
+}
+// Plans are immutable once built (tables live in HBM), so copies of an FFT object share one handle --
+// reference objects are copyable (they own std::vectors), and this keeps that property.
+inline std::shared_ptr<ssfft_plan> makePlan(int kind, int precision, std::size_t n) {
+    ssfft_plan *raw = nullptr;
+    check(ssfft_plan_create(&raw, kind, precision, n, -1), "ssfft_plan_create");
+    return std::shared_ptr<ssfft_plan>(raw, [](ssfft_plan *p) { ssfft_plan_destroy(p); });
+}
+
+// Accept containers (anything std::begin works on) or iterators/pointers, as the reference does (:56-67).
+template <typename T, typename = void>
+struct IteratorOf {
+    static T get(const T &t) { return t; }
+};
+template <typename T>
+struct IteratorOf<T, decltype((void)std::begin(std::declval<T &>()))> {
+    static auto get(T &t) -> decltype(std::begin(t)) { return std::begin(t); }
+};
+template <typename T>
+auto iteratorOf(T &&t) -> decltype(IteratorOf<typename std::remove_reference<T>::type>::get(t)) {
+    return IteratorOf<typename std::remove_reference<T>::type>::get(t);
+}
+}  // namespace b200_detail
+
+template <typename V>
+class FFT {
+    using complex = std::complex<V>;
+    std::size_t _size;
+    std::shared_ptr<ssfft_plan> plan;
+    std::vector<complex> hostIn, hostOut;  // staging for the host-iterator path
+
+    template <bool inverse, typename InputIterator, typename OutputIterator>
+    void runHost(InputIterator input, OutputIterator output) {
+        for (std::size_t i = 0; i < _size; ++i) hostIn[i] = input[i];  // the input is never modified
+        if (_size) b200_detail::check(ssfft_exec_host(plan.get(), inverse ? 1 : 0, hostIn.data(), hostOut.data(), 1), "ssfft_exec_host");
+        for (std::size_t i = 0; i < _size; ++i) output[i] = hostOut[i];
+    }
+
+public:
+    static std::size_t sizeMinimum(std::size_t size) { return ssfft_size_minimum(size); }
+    static std::size_t sizeMaximum(std::size_t size) { return ssfft_size_maximum(size); }
+
+    FFT(std::size_t size, int fastDirection = 0) : _size(0) {
+        if (fastDirection > 0) size = sizeMinimum(size);
+        if (fastDirection < 0) size = sizeMaximum(size);
+        this->setSize(size);
+    }
+
+    std::size_t setSize(std::size_t size) {
+        if (size != _size || !plan) {
+            _size = size;
+            hostIn.resize(size);
+            hostOut.resize(size);
+            plan = size ? b200_detail::makePlan(SSFFT_C2C, b200_detail::Precision<V>::value, size) : nullptr;
+        }
+        return _size;
+    }
+    std::size_t setSizeMinimum(std::size_t size) { return setSize(sizeMinimum(size)); }
+    std::size_t setSizeMaximum(std::size_t size) { return setSize(sizeMaximum(size)); }
+    const std::size_t &size() const { return _size; }
+
+    // ---- the reference's host API (containers or iterators of std::complex<V>)
+    template <typename Input, typename Output>
+    void fft(Input &&input, Output &&output) {
+        runHost<false>(b200_detail::iteratorOf(input), b200_detail::iteratorOf(output));
+    }
+    template <typename Input, typename Output>
+    void ifft(Input &&input, Output &&output) {
+        runHost<true>(b200_detail::iteratorOf(input), b200_detail::iteratorOf(output));
+    }
+
+    // ---- batched device-pointer overloads (new): `batch` contiguous transforms, async on `stream`
+    void fft(const complex *d_in, complex *d_out, std::size_t batch, void *stream = nullptr) {
+        if (_size) b200_detail::check(ssfft_exec_c2c(plan.get(), d_in, d_out, batch, SSFFT_FORWARD, stream), "ssfft_exec_c2c");
+    }
+    void ifft(const complex *d_in, complex *d_out, std::size_t batch, void *stream = nullptr) {
+        if (_size) b200_detail::check(ssfft_exec_c2c(plan.get(), d_in, d_out, batch, SSFFT_INVERSE, stream), "ssfft_exec_c2c");
+    }
+    // batched HOST buffers in one call (H2D, kernels and D2H overlap inside the library)
+    void fftHostBatch(const complex *h_in, complex *h_out, std::size_t batch) {
+        if (_size) b200_detail::check(ssfft_exec_host(plan.get(), 0, h_in, h_out, batch), "ssfft_exec_host");
+    }
+    void ifftHostBatch(const complex *h_in, complex *h_out, std::size_t batch) {
+        if (_size) b200_detail::check(ssfft_exec_host(plan.get(), 1, h_in, h_out, batch), "ssfft_exec_host");
+    }
+    std::string describe() const {
+        char buf[1024] = "empty";
+        if (plan) ssfft_plan_describe(plan.get(), buf, sizeof(buf));
+        return buf;
+    }
+};
+
+struct FFTOptions {
+    static constexpr int halfFreqShift = 1;
+};
+
+template <typename V, int optionFlags = 0>
+class RealFFT {
+    static constexpr bool modified = (optionFlags & FFTOptions::halfFreqShift);
+    using complex = std::complex<V>;
+    std::size_t halfSize;
+    std::shared_ptr<ssfft_plan> plan;
+    std::vector<V> hostReal;
+    std::vector<complex> hostComplex;
+
+public:
+    // quirks of the reference reproduced on purpose (signalsmith-fft.h:403-408)
+    static std::size_t sizeMinimum(std::size_t size) { return ssfft_real_size_minimum(size); }
+    static std::size_t sizeMaximum(std::size_t size) { return ssfft_real_size_maximum(size); }
+
+    RealFFT(std::size_t size, int fastDirection = 0) : halfSize(0) {
+        if (fastDirection > 0) size = sizeMinimum(size);
+        if (fastDirection < 0) size = sizeMaximum(size);
+        this->setSize(size);
+    }
+
+    std::size_t setSize(std::size_t size) {
+        halfSize = size / 2;
+        hostReal.resize(halfSize * 2);
+        hostComplex.resize(halfSize);
+        plan = halfSize ? b200_detail::makePlan(modified ? SSFFT_REAL_MODIFIED : SSFFT_REAL,
+                                                b200_detail::Precision<V>::value, halfSize * 2)
+                        : nullptr;
+        return halfSize;  // the reference returns the COMPLEX size here (:434)
+    }
+    std::size_t setSizeMinimum(std::size_t size) { return setSize(sizeMinimum(size)); }
+    std::size_t setSizeMaximum(std::size_t size) { return setSize(sizeMaximum(size)); }
+    std::size_t size() const { return halfSize * 2; }
+
+    template <typename Input, typename Output>
+    void fft(Input &&input, Output &&output) {
+        auto in = b200_detail::iteratorOf(input);
+        auto out = b200_detail::iteratorOf(output);
+        for (std::size_t i = 0; i < halfSize * 2; ++i) hostReal[i] = in[i];
+        if (halfSize) b200_detail::check(ssfft_exec_host(plan.get(), 2, hostReal.data(), hostComplex.data(), 1), "ssfft_exec_host");
+        for (std::size_t i = 0; i < halfSize; ++i) out[i] = hostComplex[i];  // bins [N/2, N) stay untouched
+    }
+    template <typename Input, typename Output>
+    void ifft(Input &&input, Output &&output) {
+        auto in = b200_detail::iteratorOf(input);
+        auto out = b200_detail::iteratorOf(output);
+        for (std::size_t i = 0; i < halfSize; ++i) hostComplex[i] = in[i];
+        if (halfSize) b200_detail::check(ssfft_exec_host(plan.get(), 3, hostComplex.data(), hostReal.data(), 1), "ssfft_exec_host");
+        for (std::size_t i = 0; i < halfSize * 2; ++i) out[i] = hostReal[i];
+    }
+
+    // batched device-pointer overloads: N reals per transform <-> N/2 complex per transform
+    void fft(const V *d_in, complex *d_out, std::size_t batch, void *stream = nullptr) {
+        if (halfSize) b200_detail::check(ssfft_exec_r2c(plan.get(), d_in, d_out, batch, stream), "ssfft_exec_r2c");
+    }
+    void ifft(const complex *d_in, V *d_out, std::size_t batch, void *stream = nullptr) {
+        if (halfSize) b200_detail::check(ssfft_exec_c2r(plan.get(), d_in, d_out, batch, stream), "ssfft_exec_c2r");
+    }
+    std::string describe() const {
+        char buf[1024] = "empty";
+        if (plan) ssfft_plan_describe(plan.get(), buf, sizeof(buf));
+        return buf;
+    }
+};
+
+template <typename V>
+struct ModifiedRealFFT : public RealFFT<V, FFTOptions::halfFreqShift> {
+    using RealFFT<V, FFTOptions::halfFreqShift>::RealFFT;
+};
+
+}  // namespace SIGNALSMITH_FFT_NAMESPACE
+
+#undef SIGNALSMITH_FFT_NAMESPACE
+#endif  // SIGNALSMITH_FFT_B200_V1
