@@ -55,5 +55,8 @@ FusedEntry make_entry(const char *name) {
 
 #define SSFFT_FUSED(T, N, R0, R1, R2, R3, TX, FPB, MINB) \
     make_entry<FusedCfg<T, N, R0, R1, R2, R3, TX, FPB, MINB>>(#T "_" #N "_" #R0 "x" #R1 "x" #R2 "x" #R3)
+// same, with the TMA bulk-copy prefetch of the next transform group (cp.async.bulk + mbarrier)
+#define SSFFT_FUSED_PF(T, N, R0, R1, R2, R3, TX, FPB, MINB) \
+    make_entry<FusedCfg<T, N, R0, R1, R2, R3, TX, FPB, MINB, 4, 1>>(#T "_" #N "_" #R0 "x" #R1 "x" #R2 "x" #R3 "_tma")
 
 }  // namespace ssfft

@@ -91,6 +91,7 @@ void bench(const char *name, const void *in, void *out, long long batch, int wav
 static long long batch_for(int n, size_t sz) { return (long long)((2ull << 30) / (2 * sz * n)); }  // 2 GiB of input
 
 int main(int argc, char **argv) {
+    setvbuf(stdout, nullptr, _IOLBF, 0);
     const char *which = argc > 1 ? argv[1] : "4096";
     void *in, *out;
     size_t bytes = (size_t)2200 << 20;
