@@ -2,6 +2,7 @@
 #include <cstdlib>
 
 #include "fused.cuh"
+#include "tiled.cuh"
 namespace ssfft {
 void register_fused_f32_a(std::vector<FusedEntry> &);
 void register_fused_f32_b(std::vector<FusedEntry> &);
@@ -21,6 +22,23 @@ const std::vector<FusedEntry> &fused_registry() {
         register_fused_f32_c(v);
         register_fused_f64_a(v);
         register_fused_f64_b(v);
+        return v;
+    }();
+    return reg;
+}
+
+void register_tile_f32_a(std::vector<TileEntry> &);
+void register_tile_f32_b(std::vector<TileEntry> &);
+void register_tile_f64_a(std::vector<TileEntry> &);
+
+const std::vector<TileEntry> &tile_registry() {
+    static const std::vector<TileEntry> reg = [] {
+        std::vector<TileEntry> v;
+        const char *off = getenv("SSFFT_DISABLE_TILED");  // parity tests: force the generic four-step
+        if (off && off[0] == '1') return v;
+        register_tile_f32_a(v);
+        register_tile_f32_b(v);
+        register_tile_f64_a(v);
         return v;
     }();
     return reg;

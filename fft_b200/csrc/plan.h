@@ -41,6 +41,12 @@ struct ssfft_plan {
     ssfft::GenericStage direct, col, row;  // direct: !four_step;  col (n1, strided) / row (n2) otherwise
     ssfft::FusedChoice fused;              // contiguous single-pass kernel for n, when registered
     ssfft::FusedChoice fused_col, fused_row;
+    // fast four-step through the tile kernels (tiled.cuh): ids into tile_registry(), -1 = not used
+    bool tiled = false;
+    int tile_a = -1, tile_b = -1;          // length-n1 (column) and length-n2 (row) kernels
+    void *d_tile_tw_a = nullptr, *d_tile_tw_b = nullptr;
+    void *d_tw4 = nullptr;                 // W_N^(n2*k1) laid out [k1][n2]
+    size_t scratch_per = 0;                // scratch elements (cx) per transform
     void *d_ep_lo = nullptr, *d_ep_hi = nullptr;
     int ep_shift = 0;
     void *d_scratch = nullptr;  // four-step intermediate, chunk transforms

@@ -9,6 +9,7 @@
 
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -19,6 +20,7 @@
 #include "plan.h"
 #include "planner.h"
 #include "real_kernels.cuh"
+#include "tiled.cuh"
 
 using namespace ssfft;
 
@@ -136,11 +138,107 @@ int launch_generic(const ssfft_plan *pl, const GenericStage &st, const void *in,
     return SSFFT_OK;
 }
 
+int env_int(const char *name, int dflt) {
+    const char *e = getenv(name);
+    return e ? atoi(e) : dflt;
+}
+
+template <typename T>
+int launch_tile_flavor(int id, int flavor, const cx<T> *in, cx<T> *out, const void *tw, const void *tw4, int n1, int n2,
+                       long long batch, long long in_stride, long long out_stride, int inverse, cudaStream_t s) {
+    TileParams<T> p;
+    p.in = in; p.out = out;
+    p.tw = (const cx<T> *)tw; p.tw4 = (const cx<T> *)tw4;
+    p.n1 = n1; p.n2 = n2; p.batch = batch;
+    p.in_stride = in_stride; p.out_stride = out_stride; p.inverse = inverse;
+    int rc = tile_registry()[id].launch[flavor](&p, s);
+    ++g_launches;
+    return rc ? SSFFT_ERR_CUDA : SSFFT_OK;
+}
+
+// Try to set up the tile-kernel four-step for total length `total` (complex n, or the REAL length for real
+// plans).  Returns true when both factors have a tile kernel.
+template <typename T>
+int setup_tiled(ssfft_plan *pl, size_t total, bool real, bool *ok) {
+    *ok = false;
+    if (total == 0 || (total & (total - 1))) return SSFFT_OK;  // power-of-two only
+    int lg = 0;
+    while (((size_t)1 << lg) < total) ++lg;
+    const int min_lg = real ? env_int("SSFFT_TILE_MIN_LOG2_REAL", 15) : env_int("SSFFT_TILE_MIN_LOG2", 14);
+    if (lg < min_lg) return SSFFT_OK;
+    size_t n1 = (size_t)1 << (lg / 2), n2 = total / n1;
+    int ia = find_tile<T>(n1), ib = find_tile<T>(n2);
+    if (ia < 0 || ib < 0) return SSFFT_OK;
+    pl->tile_a = ia; pl->tile_b = ib; pl->n1 = n1; pl->n2 = n2;
+    int rc = build_tile_twiddles<T>(ia, &pl->d_tile_tw_a);
+    if (rc) return rc;
+    rc = build_tile_twiddles<T>(ib, &pl->d_tile_tw_b);
+    if (rc) return rc;
+    const size_t rows = real ? n1 / 2 + 1 : n1;
+    std::vector<T> h(2 * rows * n2);
+    for (size_t k1 = 0; k1 < rows; ++k1)
+        for (size_t c = 0; c < n2; ++c) {
+            unsigned long long q = (unsigned long long)k1 * c % total;
+            long double a = 2.0L * 3.14159265358979323846264338327950288L * (long double)q / (long double)total;
+            h[2 * (k1 * n2 + c)] = (T)cosl(a);
+            h[2 * (k1 * n2 + c) + 1] = (T)(-sinl(a));
+        }
+    CU(cudaMalloc(&pl->d_tw4, h.size() * sizeof(T)));
+    CU(cudaMemcpy(pl->d_tw4, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+    pl->scratch_per = rows * n2;
+    const size_t per = pl->scratch_per * sizeof(cx<T>);
+    pl->chunk = ((size_t)env_int("SSFFT_SCRATCH_MB", 32) << 20) / per;
+    if (pl->chunk < 1) pl->chunk = 1;
+    CU(cudaMalloc(&pl->d_scratch, pl->chunk * per));
+    pl->tiled = true;
+    *ok = true;
+    return SSFFT_OK;
+}
+
+// kind: 0 = C2C (dir by `inverse`), 1 = R2C, 2 = C2R.  in/out are user buffers of `batch` transforms.
+template <typename T>
+int exec_tiled(ssfft_plan *pl, int kind, const void *in, void *out, long long batch, int inverse, cudaStream_t s) {
+    const int n1 = (int)pl->n1, n2 = (int)pl->n2;
+    const long long total = (long long)n1 * n2;
+    const long long user_stride = kind == 0 ? total : total / 2;  // cx elements per transform on the user side
+    const long long sp = (long long)pl->scratch_per;
+    cx<T> *scratch = (cx<T> *)pl->d_scratch;
+    for (long long b0 = 0; b0 < batch; b0 += (long long)pl->chunk) {
+        const long long nb = (batch - b0 < (long long)pl->chunk) ? batch - b0 : (long long)pl->chunk;
+        const cx<T> *cin = (const cx<T> *)in + b0 * user_stride;
+        cx<T> *cout = (cx<T> *)out + b0 * user_stride;
+        int rc;
+        if (kind == 0) {
+            rc = launch_tile_flavor<T>(pl->tile_a, TILE_A_C2C, cin, scratch, pl->d_tile_tw_a, pl->d_tw4, n1, n2, nb,
+                                       user_stride, sp, inverse, s);
+            if (rc) return rc;
+            rc = launch_tile_flavor<T>(pl->tile_b, TILE_B_C2C, scratch, cout, pl->d_tile_tw_b, pl->d_tw4, n1, n2, nb, sp,
+                                       user_stride, inverse, s);
+        } else if (kind == 1) {
+            rc = launch_tile_flavor<T>(pl->tile_a, TILE_A_R2C, cin, scratch, pl->d_tile_tw_a, pl->d_tw4, n1, n2, nb,
+                                       user_stride, sp, 0, s);
+            if (rc) return rc;
+            rc = launch_tile_flavor<T>(pl->tile_b, TILE_B_R2C, scratch, cout, pl->d_tile_tw_b, pl->d_tw4, n1, n2, nb, sp,
+                                       user_stride, 0, s);
+        } else {
+            rc = launch_tile_flavor<T>(pl->tile_b, TILE_B_C2R, cin, scratch, pl->d_tile_tw_b, pl->d_tw4, n1, n2, nb,
+                                       user_stride, sp, 1, s);
+            if (rc) return rc;
+            rc = launch_tile_flavor<T>(pl->tile_a, TILE_A_C2R, scratch, cout, pl->d_tile_tw_a, pl->d_tw4, n1, n2, nb, sp,
+                                       user_stride, 1, s);
+        }
+        if (rc) return rc;
+    }
+    CU(cudaGetLastError());
+    return SSFFT_OK;
+}
+
 // Complex core: batch contiguous transforms of length pl->n, in -> out (in == out allowed).
 template <typename T>
 int exec_complex(ssfft_plan *pl, const void *in, void *out, long long batch, int inverse, cudaStream_t s) {
     const long long n = (long long)pl->n;
     if (batch <= 0 || n == 0) return SSFFT_OK;
+    if (pl->tiled && pl->kind == SSFFT_C2C) return exec_tiled<T>(pl, 0, in, out, batch, inverse, s);
     if (!pl->four_step) {
         if (pl->fused.id >= 0)
             return launch_fused<T>(pl->fused.id, pl->fused.d_twiddles, in, out, batch, inverse, FUSED_C2C, nullptr, s,
@@ -175,7 +273,20 @@ int build_plan_typed(ssfft_plan *pl) {
     char buf[512];
     if (n == 0) { pl->desc = "empty"; return SSFFT_OK; }
     const size_t limit = generic_limit(sizeof(cx<T>), smem_max);
-    if (n <= limit) {
+    bool tiled_ok = false;
+    if (pl->kind == SSFFT_C2C) {
+        int rc = setup_tiled<T>(pl, n, false, &tiled_ok);
+        if (rc) return rc;
+    } else if (pl->kind == SSFFT_REAL) {
+        int rc = setup_tiled<T>(pl, pl->n_real, true, &tiled_ok);
+        if (rc) return rc;
+    }
+    if (tiled_ok) {
+        snprintf(buf, sizeof(buf), "%s N=%zu four-step tiles n1=%zu (%s) x n2=%zu (%s) chunk=%zu L2-resident scratch",
+                 pl->kind == SSFFT_C2C ? "complex" : "real", pl->kind == SSFFT_C2C ? n : pl->n_real, pl->n1,
+                 tile_registry()[pl->tile_a].name, pl->n2, tile_registry()[pl->tile_b].name, pl->chunk);
+        pl->desc = buf;
+    } else if (n <= limit) {
         pl->four_step = false;
         int rc = build_generic_stage<T>(pl->direct, n, smem_max);
         if (rc) return rc;
@@ -216,7 +327,7 @@ int build_plan_typed(ssfft_plan *pl) {
         snprintf(buf, sizeof(buf), "n=%zu four-step n1=%zu n2=%zu chunk=%zu (generic x generic)", n, n1, n2, pl->chunk);
         pl->desc = buf;
     }
-    if (pl->kind != SSFFT_C2C) {
+    if (pl->kind != SSFFT_C2C && !pl->tiled) {
         const bool modified = pl->kind == SSFFT_REAL_MODIFIED;
         std::vector<T> h(2 * (pl->n_real / 4 + 1));
         fill_real_twiddles<T>(h.data(), pl->n_real, modified);
@@ -240,6 +351,7 @@ int exec_r2c_typed(ssfft_plan *pl, const void *in, void *out, long long batch, c
     const long long h = (long long)pl->n;
     if (h == 0 || batch <= 0) return SSFFT_OK;
     const bool modified = pl->kind == SSFFT_REAL_MODIFIED;
+    if (pl->tiled) return exec_tiled<T>(pl, 1, in, out, batch, 0, s);
     if (!modified && !pl->four_step && pl->fused.id >= 0)
         return launch_fused<T>(pl->fused.id, pl->fused.d_twiddles, in, out, batch, 0, FUSED_R2C, pl->d_rtw, s,
                                &g_launches);
@@ -265,6 +377,7 @@ int exec_c2r_typed(ssfft_plan *pl, const void *in, void *out, long long batch, c
     const long long h = (long long)pl->n;
     if (h == 0 || batch <= 0) return SSFFT_OK;
     const bool modified = pl->kind == SSFFT_REAL_MODIFIED;
+    if (pl->tiled) return exec_tiled<T>(pl, 2, in, out, batch, 1, s);
     if (!modified && !pl->four_step && pl->fused.id >= 0)
         return launch_fused<T>(pl->fused.id, pl->fused.d_twiddles, in, out, batch, 1, FUSED_C2R, pl->d_rtw, s,
                                &g_launches);
@@ -339,7 +452,8 @@ int ssfft_plan_destroy(ssfft_plan *pl) {
     DeviceGuard guard(pl->device);
     free_stage(pl->direct); free_stage(pl->col); free_stage(pl->row);
     void *ptrs[] = {pl->fused.d_twiddles, pl->fused_col.d_twiddles, pl->fused_row.d_twiddles, pl->d_ep_lo, pl->d_ep_hi,
-                    pl->d_scratch, pl->d_rtw, pl->d_rot, pl->d_stage_in, pl->d_stage_out};
+                    pl->d_scratch, pl->d_rtw, pl->d_rot, pl->d_stage_in, pl->d_stage_out, pl->d_tile_tw_a, pl->d_tile_tw_b,
+                    pl->d_tw4};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     if (pl->host_stream) cudaStreamDestroy(pl->host_stream);

@@ -1,0 +1,328 @@
+// tiled.cuh -- four-step (N = N1 * N2) tile kernels for transforms too large for one CTA.
+//
+// GPU analogue of the reference's cache-blocking branch (addPlanSteps, signalsmith-fft.h:130-133): when a
+// transform does not fit on chip it is split into N2 column FFTs of length N1, a twiddle W_N^(n2*k1), and
+// N1 row FFTs of length N2 whose output is stored transposed, X[k1 + N1*k2].  The intermediate lives in a
+// scratch buffer small enough to stay in the 126 MB L2, so HBM sees each input and output byte once.
+//
+// A CTA owns a TILE of CT adjacent columns (or rows): threadIdx.x = lane within the tile (so every global
+// access is a 128-byte segment and every shared-memory access is conflict-free), threadIdx.y = butterfly
+// thread.  Shared layout [idx][lane] with pitch CT+1 (lets the row kernels transpose on the way in/out).
+//
+// Real transforms (RealFFT<V>::fft/ifft, :446-502) use a REAL four-step instead of the reference's
+// "N/2 complex + post-twiddle" trick, because that trick pairs bin k with bin N/2-k which live in different
+// CTAs here.  Two adjacent real columns are packed into one complex column FFT and separated in shared
+// memory; only rows k1 <= N1/2 are kept, and each row FFT emits its own bins (k2 < N2/2) plus, conjugated,
+// the bins of row N1-k1 (k2 >= N2/2).  Same outputs (bins 0..N/2-1, (DC, Nyquist) packed in bin 0), no
+// cross-CTA exchange, half the traffic of a complex transform.
+//
+//   flavor      FFT length  tile over              reads                      writes
+//   A_C2C       N1          n2 (columns)           x[n1][n2]                  Y[k1][n2] * W_N^(n2 k1)   (scratch)
+//   B_C2C       N2          k1 (rows)              Y[k1][n2]   (transposing)  X[k1 + N1 k2]
+//   A_R2C       N1          n2/2 (column pairs)    real x as complex pairs    Y[k1<=N1/2][n2] * W       (scratch)
+//   B_R2C       N2          k1 <= N1/2             Y[k1][n2]   (transposing)  packed half spectrum
+//   B_C2R       N2          k1 <= N1/2             packed half spectrum       U[k1][n2] * conj W  (scratch, transposing)
+//   A_C2R       N1          n2/2 (column pairs)    U (Hermitian-extended)     real x as complex pairs
+#pragma once
+#include <cuda_runtime.h>
+
+#include "codelets.cuh"
+#include "fused.cuh"
+
+namespace ssfft {
+
+enum { TILE_A_C2C = 0, TILE_B_C2C = 1, TILE_A_R2C = 2, TILE_B_R2C = 3, TILE_B_C2R = 4, TILE_A_C2R = 5 };
+
+template <typename T_, int L_, int R0_, int R1_, int R2_, int TX_, int CT_, int MINB_>
+struct TileCfg {
+    using T = T_;
+    static constexpr int L = L_, TX = TX_, CT = CT_, MINB = MINB_;
+    static constexpr int NP = (R2_ > 1) ? 3 : (R1_ > 1) ? 2 : 1;
+    static constexpr int E = L / TX;
+    static constexpr int PITCH = CT + 1;
+    static constexpr int THREADS = TX * CT;
+    __host__ __device__ static constexpr int radix(int i) { return i == 0 ? R0_ : i == 1 ? R1_ : R2_; }
+    __host__ __device__ static constexpr int prod(int i) { return i == 0 ? 1 : i == 1 ? R0_ : R0_ * R1_; }
+    __host__ __device__ static constexpr int mnext(int i) { return L / (prod(i) * radix(i)); }
+    __host__ __device__ static constexpr int tw_off(int i) {
+        int o = 0;
+        for (int k = 0; k < i; ++k) o += (radix(k) - 1) * mnext(k);
+        return o;
+    }
+    static constexpr int tw_total = tw_off(NP - 1);
+    static constexpr size_t smem_bytes = (size_t)L * PITCH * sizeof(cx<T>);
+    static_assert(R0_ * R1_ * R2_ == L_, "radices must multiply to L");
+    static_assert(E % R0_ == 0 && E % R1_ == 0 && E % R2_ == 0, "E must be a multiple of every radix");
+    static_assert((L_ & (L_ - 1)) == 0, "tile kernels are power-of-two only");
+};
+
+template <typename T>
+struct TileParams {
+    const cx<T> *in;
+    cx<T> *out;
+    const cx<T> *tw;   // per-pass twiddles of the length-L transform ([r][m'] per pass, as fused.cuh)
+    const cx<T> *tw4;  // four-step twiddles W_N^(n2*k1) laid out [k1][n2]
+    int n1, n2;        // N = n1 * n2 (REAL length for the real flavors)
+    long long batch;
+    long long in_stride, out_stride;  // cx elements between consecutive transforms
+    int inverse;       // C2C only: swap re/im on the way in (A) and out (B)
+};
+
+#ifdef __CUDACC__
+
+template <typename T>
+__device__ __forceinline__ cx<T> ld_plain(const cx<T> *p) {
+    using V = typename vec2<T>::type;
+    V v = *reinterpret_cast<const V *>(p);
+    return mk<T>(v.x, v.y);
+}
+template <typename T>
+__device__ __forceinline__ void st_plain(cx<T> *p, cx<T> v) {
+    using V = typename vec2<T>::type;
+    V w; w.x = v.x; w.y = v.y;
+    *reinterpret_cast<V *>(p) = w;
+}
+
+template <typename Cfg, int FLAVOR>
+__global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINB) tile_fft_kernel(TileParams<typename Cfg::T> p) {
+    using T = typename Cfg::T;
+    constexpr int L = Cfg::L, TX = Cfg::TX, CT = Cfg::CT, E = Cfg::E, NP = Cfg::NP, PITCH = Cfg::PITCH;
+    constexpr int THREADS = Cfg::THREADS;
+    constexpr bool kFirstFromSmem = (FLAVOR == TILE_B_C2C || FLAVOR == TILE_B_R2C || FLAVOR == TILE_A_C2R);
+    constexpr bool kLastToSmem = (FLAVOR == TILE_A_R2C || FLAVOR == TILE_B_C2R);
+    extern __shared__ __align__(16) unsigned char ssfft_smem[];
+    cx<T> *sm = reinterpret_cast<cx<T> *>(ssfft_smem);
+    const int c = threadIdx.x, t = threadIdx.y;
+    const int tid = t * CT + c;
+    const int n1 = p.n1, n2 = p.n2;
+    // how many lanes (columns / rows) exist along the tiled dimension
+    const int width = (FLAVOR == TILE_A_C2C)   ? n2
+                      : (FLAVOR == TILE_B_C2C) ? n1
+                      : (FLAVOR == TILE_A_R2C || FLAVOR == TILE_A_C2R) ? n2 / 2
+                                               : n1 / 2 + 1;
+    const int tiles = (width + CT - 1) / CT;
+    const long long items = p.batch * tiles;
+
+    for (long long item = blockIdx.x; item < items; item += gridDim.x) {
+        const long long B = item / tiles;
+        const int lane0 = (int)(item - B * tiles) * CT;
+        const int lane = lane0 + c;  // column (A flavors) or row k1 (B flavors)
+        const bool live = lane < width;
+        const cx<T> *gin = p.in + B * p.in_stride;
+        cx<T> *gout = p.out + B * p.out_stride;
+        cx<T> v[E];
+
+        // ------------------------------------------------------------------ stage-in for the smem-first flavors
+        if constexpr (FLAVOR == TILE_B_C2C || FLAVOR == TILE_B_R2C) {
+            // rows are contiguous in the scratch: read them coalesced along n2, store transposed [n2][row]
+            for (int e = tid; e < CT * L; e += THREADS) {
+                const int rr = e / L, i = e - rr * L;
+                if (lane0 + rr < width) sm[i * PITCH + rr] = ld_plain(gin + (long long)(lane0 + rr) * n2 + i);
+            }
+            __syncthreads();
+        }
+        if constexpr (FLAVOR == TILE_A_C2R) {
+            // G[k1] = U[k1][2c'] + i U[k1][2c'+1], Hermitian-extended to k1 > N1/2; scratch holds swap(U)
+            if (live) {
+                for (int k1 = t; k1 <= L / 2; k1 += TX) {
+                    const cx<T> *src = gin + (long long)k1 * n2 + 2 * lane;
+                    const cx<T> a = cswap(ld_plain(src)), b = cswap(ld_plain(src + 1));
+                    sm[k1 * PITCH + c] = cswap(mk<T>(a.x - b.y, a.y + b.x));
+                    if (k1 > 0 && k1 < L / 2) sm[(L - k1) * PITCH + c] = cswap(mk<T>(a.x + b.y, b.x - a.y));
+                }
+            }
+            __syncthreads();
+        }
+
+        sfor<0, NP>([&](auto pc) {
+            constexpr int ps = decltype(pc)::value;
+            constexpr int R = Cfg::radix(ps), P = Cfg::prod(ps), MN = Cfg::mnext(ps), NR = L / R, U = E / R;
+            constexpr bool first = (ps == 0), last = (ps == NP - 1);
+            // ---- gather
+            if constexpr (first && !kFirstFromSmem) {
+                if (live) {
+#pragma unroll
+                    for (int u = 0; u < U; ++u)
+#pragma unroll
+                        for (int j = 0; j < R; ++j) {
+                            const int idx = t + TX * u + NR * j;
+                            cx<T> x;
+                            if constexpr (FLAVOR == TILE_A_C2C) {
+                                x = ld_stream(gin + (long long)idx * n2 + lane);
+                                if (p.inverse) x = cswap(x);
+                            } else if constexpr (FLAVOR == TILE_A_R2C) {
+                                x = ld_stream(gin + (long long)idx * (n2 / 2) + lane);
+                            } else {  // TILE_B_C2R: row k1 = lane, element k2 = idx, Hermitian-extended packed spectrum
+                                const int k1 = lane, k2 = idx;
+                                if (k2 < L / 2) {
+                                    x = ld_stream(gin + k1 + (long long)n1 * k2);
+                                    if (k1 == 0 && k2 == 0) x.y = (T)0;  // bin 0 packs (DC, Nyquist)
+                                } else if (k1 == 0) {
+                                    if (k2 == L / 2) {
+                                        x = ld_stream(gin);
+                                        x = mk<T>(x.y, (T)0);
+                                    } else {
+                                        x = cconj(ld_stream(gin + (long long)n1 * (L - k2)));
+                                    }
+                                } else {
+                                    x = cconj(ld_stream(gin + (n1 - k1) + (long long)n1 * (L - 1 - k2)));
+                                }
+                                x = cswap(x);  // inverse transform via the swap trick
+                            }
+                            v[u * R + j] = x;
+                        }
+                }
+            } else {
+#pragma unroll
+                for (int u = 0; u < U; ++u)
+#pragma unroll
+                    for (int j = 0; j < R; ++j) v[u * R + j] = sm[(t + TX * u + NR * j) * PITCH + c];
+                __syncthreads();
+            }
+            // ---- butterflies + inter-pass twiddles (identical for every lane: broadcast loads)
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                cx<T> w[R];
+#pragma unroll
+                for (int j = 0; j < R; ++j) w[j] = v[u * R + j];
+                Dft<R>::run(w);
+                if constexpr (!last) {
+                    const int b = t + TX * u;
+                    const int mp = b / P;
+                    const cx<T> *twp = p.tw + Cfg::tw_off(ps) + mp;
+#pragma unroll
+                    for (int r = 1; r < R; ++r) w[r] = cmul(w[r], ld_table(twp + (r - 1) * MN));
+                }
+#pragma unroll
+                for (int j = 0; j < R; ++j) v[u * R + j] = w[j];
+            }
+            // ---- scatter
+            if constexpr (!last) {
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int b = t + TX * u;
+                    const int mp = b / P, racc = b - mp * P;
+                    const int o = racc + P * R * mp;
+#pragma unroll
+                    for (int r = 0; r < R; ++r) sm[(o + P * r) * PITCH + c] = v[u * R + r];
+                }
+                __syncthreads();
+            } else if constexpr (kLastToSmem) {
+#pragma unroll
+                for (int u = 0; u < U; ++u)
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {
+                        const int k = t + TX * u + P * r;  // natural-order output index
+                        cx<T> x = v[u * R + r];
+                        if constexpr (FLAVOR == TILE_B_C2R) {
+                            if (live) x = cmul(x, ld_table(p.tw4 + (long long)lane * n2 + k));  // swapped domain: plain W
+                        }
+                        sm[k * PITCH + c] = x;
+                    }
+                __syncthreads();
+            } else if (live) {
+#pragma unroll
+                for (int u = 0; u < U; ++u)
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {
+                        const int k = t + TX * u + P * r;
+                        cx<T> x = v[u * R + r];
+                        if constexpr (FLAVOR == TILE_A_C2C) {
+                            x = cmul(x, ld_table(p.tw4 + (long long)k * n2 + lane));
+                            st_plain(gout + (long long)k * n2 + lane, x);  // scratch: keep it in L2
+                        } else if constexpr (FLAVOR == TILE_B_C2C) {
+                            if (p.inverse) x = cswap(x);
+                            st_stream(gout + lane + (long long)n1 * k, x);
+                        } else if constexpr (FLAVOR == TILE_A_C2R) {
+                            st_stream(gout + (long long)k * (n2 / 2) + lane, cswap(x));
+                        } else {  // TILE_B_R2C: row k1 = lane, bin k2 = k
+                            const int k1 = lane, k2 = k;
+                            if (k2 < L / 2) {
+                                if (k1 == 0 && k2 == 0) reinterpret_cast<T *>(gout)[0] = x.x;  // DC
+                                else st_stream(gout + k1 + (long long)n1 * k2, x);
+                            } else if (k1 == 0) {
+                                if (k2 == L / 2) reinterpret_cast<T *>(gout)[1] = x.x;  // Nyquist
+                            } else if (k1 < n1 / 2) {
+                                st_stream(gout + (n1 - k1) + (long long)n1 * (L - 1 - k2), cconj(x));
+                            }
+                        }
+                    }
+            }
+        });
+
+        // ------------------------------------------------------------------ epilogues of the smem-last flavors
+        if constexpr (FLAVOR == TILE_A_R2C) {
+            // separate the two real columns packed in Z, twiddle, store rows k1 <= N1/2 of the scratch
+            if (live) {
+                for (int k1 = t; k1 <= L / 2; k1 += TX) {
+                    const cx<T> z = sm[k1 * PITCH + c], zc = sm[((L - k1) & (L - 1)) * PITCH + c];
+                    const T half = (T)0.5;
+                    const cx<T> xe = mk<T>((z.x + zc.x) * half, (z.y - zc.y) * half);
+                    const cx<T> xo = mk<T>((z.y + zc.y) * half, (zc.x - z.x) * half);
+                    const cx<T> *w = p.tw4 + (long long)k1 * n2 + 2 * lane;
+                    cx<T> *dst = gout + (long long)k1 * n2 + 2 * lane;
+                    st_plain(dst, cmul(xe, ld_table(w)));
+                    st_plain(dst + 1, cmul(xo, ld_table(w + 1)));
+                }
+            }
+            __syncthreads();
+        }
+        if constexpr (FLAVOR == TILE_B_C2R) {
+            for (int e = tid; e < CT * L; e += THREADS) {
+                const int rr = e / L, i = e - rr * L;
+                if (lane0 + rr < width) st_plain(gout + (long long)(lane0 + rr) * n2 + i, sm[i * PITCH + rr]);
+            }
+            __syncthreads();
+        }
+        if constexpr (FLAVOR == TILE_A_C2C || FLAVOR == TILE_B_C2C || FLAVOR == TILE_B_R2C || FLAVOR == TILE_A_C2R) {
+            if constexpr (NP == 1) __syncthreads();  // (multi-pass kernels end on a post-gather barrier already)
+        }
+    }
+}
+
+#endif  // __CUDACC__
+
+// ---------------------------------------------------------------------------------------------
+// registry of tile kernels: one entry per (precision, L), six flavor launchers each
+// ---------------------------------------------------------------------------------------------
+struct TileEntry {
+    int prec, len;
+    const char *name;
+    int tw_total, np, radix[3];
+    int (*launch[6])(const void *params, cudaStream_t s);  // params: TileParams<T>
+};
+const std::vector<TileEntry> &tile_registry();
+
+template <typename T>
+inline int find_tile(size_t len) {
+    const int prec = sizeof(T) == 4 ? 0 : 1;
+    const auto &reg = tile_registry();
+    for (size_t i = 0; i < reg.size(); ++i)
+        if (reg[i].prec == prec && (size_t)reg[i].len == len) return (int)i;
+    return -1;
+}
+
+template <typename T>
+inline int build_tile_twiddles(int id, void **d_out) {
+    const TileEntry &e = tile_registry()[id];
+    std::vector<T> h(2 * (size_t)(e.tw_total > 0 ? e.tw_total : 1));
+    size_t o = 0;
+    int P = 1;
+    for (int p = 0; p + 1 < e.np; ++p) {
+        const int R = e.radix[p], MN = e.len / (P * R);
+        for (int r = 1; r < R; ++r)
+            for (int m = 0; m < MN; ++m) {
+                unsigned long long q = (unsigned long long)P * m * r % (unsigned long long)e.len;
+                long double a = 2.0L * 3.14159265358979323846264338327950288L * (long double)q / (long double)e.len;
+                h[2 * o] = (T)cosl(a);
+                h[2 * o + 1] = (T)(-sinl(a));
+                ++o;
+            }
+        P *= R;
+    }
+    if (cudaMalloc(d_out, h.size() * sizeof(T)) != cudaSuccess) return 5;
+    if (cudaMemcpy(*d_out, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice) != cudaSuccess) return 2;
+    return 0;
+}
+
+}  // namespace ssfft

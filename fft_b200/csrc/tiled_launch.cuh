@@ -1,0 +1,63 @@
+// tiled_launch.cuh -- host launchers for the four-step tile kernels (tiled.cuh).
+#pragma once
+#include "tiled.cuh"
+
+namespace ssfft {
+
+template <typename Cfg, int FLAVOR>
+int launch_tile(const void *params, cudaStream_t s) {
+    using T = typename Cfg::T;
+    const TileParams<T> &p = *reinterpret_cast<const TileParams<T> *>(params);
+    static int ready_mask = 0;
+    static int resident[32] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 2;
+    if (dev < 0 || dev >= 32) return 1;
+    if (!(ready_mask & (1 << dev))) {
+        if (Cfg::smem_bytes > 48 * 1024 &&
+            cudaFuncSetAttribute(tile_fft_kernel<Cfg, FLAVOR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)Cfg::smem_bytes) != cudaSuccess)
+            return 2;
+        int per_sm = 0, sms = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tile_fft_kernel<Cfg, FLAVOR>, Cfg::THREADS,
+                                                          Cfg::smem_bytes) != cudaSuccess)
+            return 2;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        resident[dev] = (per_sm < 1 ? 1 : per_sm) * sms;
+        ready_mask |= 1 << dev;
+    }
+    const int width = (FLAVOR == TILE_A_C2C)   ? p.n2
+                      : (FLAVOR == TILE_B_C2C) ? p.n1
+                      : (FLAVOR == TILE_A_R2C || FLAVOR == TILE_A_C2R) ? p.n2 / 2
+                                               : p.n1 / 2 + 1;
+    const long long items = p.batch * ((width + Cfg::CT - 1) / Cfg::CT);
+    if (items <= 0) return 0;
+    long long grid = items;
+    const long long cap = (long long)resident[dev] * fused_waves();
+    if (cap > 0 && grid > cap) grid = cap;
+    tile_fft_kernel<Cfg, FLAVOR><<<(unsigned)grid, dim3(Cfg::CT, Cfg::TX), Cfg::smem_bytes, s>>>(p);
+    return cudaGetLastError() == cudaSuccess ? 0 : 2;
+}
+
+template <typename Cfg>
+TileEntry make_tile_entry(const char *name) {
+    TileEntry e;
+    e.prec = sizeof(typename Cfg::T) == 4 ? 0 : 1;
+    e.len = Cfg::L;
+    e.name = name;
+    e.tw_total = Cfg::tw_total;
+    e.np = Cfg::NP;
+    for (int i = 0; i < 3; ++i) e.radix[i] = Cfg::radix(i);
+    e.launch[TILE_A_C2C] = &launch_tile<Cfg, TILE_A_C2C>;
+    e.launch[TILE_B_C2C] = &launch_tile<Cfg, TILE_B_C2C>;
+    e.launch[TILE_A_R2C] = &launch_tile<Cfg, TILE_A_R2C>;
+    e.launch[TILE_B_R2C] = &launch_tile<Cfg, TILE_B_R2C>;
+    e.launch[TILE_B_C2R] = &launch_tile<Cfg, TILE_B_C2R>;
+    e.launch[TILE_A_C2R] = &launch_tile<Cfg, TILE_A_C2R>;
+    return e;
+}
+
+#define SSFFT_TILE(T, L, R0, R1, R2, TX, CT, MINB) \
+    make_tile_entry<TileCfg<T, L, R0, R1, R2, TX, CT, MINB>>(#T "_tile" #L "_" #R0 "x" #R1 "x" #R2 "_ct" #CT)
+
+}  // namespace ssfft

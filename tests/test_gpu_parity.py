@@ -21,7 +21,7 @@ SEED = 7
 REF_TEST_SIZES = [1, 2, 4, 8, 16, 32, 64, 128, 256, 3, 6, 9, 12, 18, 24, 5, 10, 15, 20, 25, 7, 14, 21, 28, 49,
                   11, 13, 17, 19, 22, 23]
 CONFIG_SIZES = [512, 1000, 1024, 2048, 2187, 3125, 4096, 6000, 8192, 16384]
-LARGE_SIZES = [32768, 65536, 3 * 2 ** 15, 100000, 2 ** 18, 2 ** 20]
+LARGE_SIZES = [16384, 32768, 65536, 3 * 2 ** 15, 100000, 2 ** 17, 2 ** 18, 2 ** 19, 2 ** 20]
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_vectors.npz")
 
 
@@ -149,7 +149,7 @@ def test_real_vs_oracle(oracle, cuda_device, prec, cls_name):
     _, tcdt = cdt_of(prec)
     modified = cls_name == "ModifiedRealFFT"
     cls = getattr(fft_b200, cls_name)
-    for n in list(range(2, 100, 2)) + [128, 256, 1000, 2048, 4096, 8192, 6000, 65536, 2 ** 17]:
+    for n in list(range(2, 100, 2)) + [128, 256, 1000, 2048, 4096, 8192, 6000, 32768, 65536, 2 ** 17, 2 ** 18, 2 ** 20]:
         batch = 5
         x = oracle.uniform(batch * n, SEED, npdt).reshape(batch, n)
         r = cls(n, dtype=prec)
@@ -180,12 +180,13 @@ def test_generic_path_matches_too(oracle, cuda_device):
     code = r"""
 import os, sys, math
 os.environ["SSFFT_DISABLE_FUSED"] = "1"
+os.environ["SSFFT_DISABLE_TILED"] = "1"
 sys.path.insert(0, os.getcwd())
 import numpy as np, torch, fft_b200
 from oracle import oracle as O
 for prec, npdt in (("float32", np.complex64), ("float64", np.complex128)):
-    for n in [64, 256, 1000, 1024, 2187, 3125, 4096, 6000]:
-        x = O.uniform_complex((9, n), 7, npdt)
+    for n in [64, 256, 1000, 1024, 2187, 3125, 4096, 6000, 65536]:
+        x = O.uniform_complex((9 if n < 60000 else 2, n), 7, npdt)
         f = fft_b200.FFT(n, dtype=prec)
         assert "generic" in f.describe(), f.describe()
         xd = torch.from_numpy(x).cuda(); out = torch.empty_like(xd)
