@@ -1,0 +1,7 @@
+// cluster four-step kernels (both stages in one persistent launch), fp32
+#include "tiled_launch.cuh"
+namespace ssfft {
+void register_fourstep_f32_b(std::vector<FourStepEntry> &v) {
+    v.push_back(make_fourstep_entry<TileCfg<float, 256, 16, 16, 1, 16, 16, 3>, TileCfg<float, 256, 16, 16, 1, 16, 16, 3>>("float_cluster_256x256"));
+}
+}  // namespace ssfft

@@ -44,6 +44,33 @@ const std::vector<TileEntry> &tile_registry() {
     return reg;
 }
 
+void register_fourstep_f32_a(std::vector<FourStepEntry> &);
+void register_fourstep_f32_b(std::vector<FourStepEntry> &);
+void register_fourstep_f32_c(std::vector<FourStepEntry> &);
+void register_fourstep_f32_d(std::vector<FourStepEntry> &);
+
+const std::vector<FourStepEntry> &fourstep_registry() {
+    static const std::vector<FourStepEntry> reg = [] {
+        std::vector<FourStepEntry> v;
+        const char *off = getenv("SSFFT_DISABLE_CLUSTER");  // fall back to two launches per chunk
+        if (off && off[0] == '1') return v;
+        register_fourstep_f32_a(v);
+        register_fourstep_f32_b(v);
+        register_fourstep_f32_c(v);
+        register_fourstep_f32_d(v);
+        return v;
+    }();
+    return reg;
+}
+int fourstep_cluster_size() {
+    static const int c = [] {
+        const char *e = getenv("SSFFT_CLUSTER");
+        int v = e ? atoi(e) : 4;
+        return (v < 1 || v > 16) ? 4 : v;
+    }();
+    return c;
+}
+
 // how many resident "waves" of CTAs a fused launch may create before CTAs start looping
 int fused_waves() {
     static const int w = [] {

@@ -187,9 +187,28 @@ int setup_tiled(ssfft_plan *pl, size_t total, bool real, bool *ok) {
     CU(cudaMemcpy(pl->d_tw4, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
     pl->scratch_per = rows * n2;
     const size_t per = pl->scratch_per * sizeof(cx<T>);
-    pl->chunk = ((size_t)env_int("SSFFT_SCRATCH_MB", 32) << 20) / per;
-    if (pl->chunk < 1) pl->chunk = 1;
-    CU(cudaMalloc(&pl->d_scratch, pl->chunk * per));
+    // preferred: one persistent cluster launch per call, two scratch slots per co-resident cluster
+    pl->fs_id = find_fourstep<T>(n1, n2);
+    if (pl->fs_id >= 0) {
+        const FourStepEntry &fe = fourstep_registry()[pl->fs_id];
+        const int cs = fourstep_cluster_size();
+        int clusters = 1 << 30;
+        for (int kind = real ? 1 : 0; kind <= (real ? 2 : 0); ++kind) {
+            int m = fe.max_clusters[kind](cs);
+            if (m < clusters) clusters = m;
+        }
+        if (clusters >= 1) {
+            pl->fs_clusters = clusters;
+            CU(cudaMalloc(&pl->d_scratch, (size_t)2 * clusters * per));
+        } else {
+            pl->fs_id = -1;  // clusters of this size cannot be scheduled here
+        }
+    }
+    if (pl->fs_id < 0) {
+        pl->chunk = ((size_t)env_int("SSFFT_SCRATCH_MB", 32) << 20) / per;
+        if (pl->chunk < 1) pl->chunk = 1;
+        CU(cudaMalloc(&pl->d_scratch, pl->chunk * per));
+    }
     pl->tiled = true;
     *ok = true;
     return SSFFT_OK;
@@ -203,6 +222,16 @@ int exec_tiled(ssfft_plan *pl, int kind, const void *in, void *out, long long ba
     const long long user_stride = kind == 0 ? total : total / 2;  // cx elements per transform on the user side
     const long long sp = (long long)pl->scratch_per;
     cx<T> *scratch = (cx<T> *)pl->d_scratch;
+    if (pl->fs_id >= 0) {
+        FourStepParams<T> q;
+        q.in = (const cx<T> *)in; q.out = (cx<T> *)out; q.scratch = scratch;
+        q.tw_a = (const cx<T> *)pl->d_tile_tw_a; q.tw_b = (const cx<T> *)pl->d_tile_tw_b; q.tw4 = (const cx<T> *)pl->d_tw4;
+        q.n1 = n1; q.n2 = n2; q.batch = batch; q.user_stride = user_stride; q.scratch_per = sp; q.inverse = inverse;
+        int rc = fourstep_registry()[pl->fs_id].launch[kind](&q, pl->fs_clusters, s);
+        ++g_launches;
+        if (rc) return cuda_fail(cudaGetLastError(), "fourstep_cluster_kernel launch");
+        return SSFFT_OK;
+    }
     for (long long b0 = 0; b0 < batch; b0 += (long long)pl->chunk) {
         const long long nb = (batch - b0 < (long long)pl->chunk) ? batch - b0 : (long long)pl->chunk;
         const cx<T> *cin = (const cx<T> *)in + b0 * user_stride;
@@ -282,9 +311,16 @@ int build_plan_typed(ssfft_plan *pl) {
         if (rc) return rc;
     }
     if (tiled_ok) {
-        snprintf(buf, sizeof(buf), "%s N=%zu four-step tiles n1=%zu (%s) x n2=%zu (%s) chunk=%zu L2-resident scratch",
-                 pl->kind == SSFFT_C2C ? "complex" : "real", pl->kind == SSFFT_C2C ? n : pl->n_real, pl->n1,
-                 tile_registry()[pl->tile_a].name, pl->n2, tile_registry()[pl->tile_b].name, pl->chunk);
+        if (pl->fs_id >= 0)
+            snprintf(buf, sizeof(buf), "%s N=%zu four-step n1=%zu x n2=%zu, one persistent launch %s, clusters of %d CTAs x %d, "
+                     "L2-resident scratch %.1f MiB", pl->kind == SSFFT_C2C ? "complex" : "real",
+                     pl->kind == SSFFT_C2C ? n : pl->n_real, pl->n1, pl->n2, fourstep_registry()[pl->fs_id].name,
+                     fourstep_cluster_size(), pl->fs_clusters,
+                     2.0 * pl->fs_clusters * pl->scratch_per * sizeof(cx<T>) / 1048576.0);
+        else
+            snprintf(buf, sizeof(buf), "%s N=%zu four-step tiles n1=%zu (%s) x n2=%zu (%s) chunk=%zu L2-resident scratch",
+                     pl->kind == SSFFT_C2C ? "complex" : "real", pl->kind == SSFFT_C2C ? n : pl->n_real, pl->n1,
+                     tile_registry()[pl->tile_a].name, pl->n2, tile_registry()[pl->tile_b].name, pl->chunk);
         pl->desc = buf;
     } else if (n <= limit) {
         pl->four_step = false;

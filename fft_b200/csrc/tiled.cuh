@@ -26,6 +26,8 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <type_traits>
+
 #include "codelets.cuh"
 #include "fused.cuh"
 
@@ -83,33 +85,41 @@ __device__ __forceinline__ void st_plain(cx<T> *p, cx<T> v) {
     *reinterpret_cast<V *>(p) = w;
 }
 
+// scratch is rewritten by other SMs between uses: read it through L2 (L1 is not coherent)
+template <typename T>
+__device__ __forceinline__ cx<T> ld_l2(const cx<T> *p) {
+    using V = typename vec2<T>::type;
+    V v = __ldcg(reinterpret_cast<const V *>(p));
+    return mk<T>(v.x, v.y);
+}
+
+template <int FLAVOR>
+__host__ __device__ constexpr int tile_width(int n1, int n2) {
+    return (FLAVOR == TILE_A_C2C)   ? n2
+           : (FLAVOR == TILE_B_C2C) ? n1
+           : (FLAVOR == TILE_A_R2C || FLAVOR == TILE_A_C2R) ? n2 / 2
+                                    : n1 / 2 + 1;
+}
+
+// One tile of one transform: lanes lane0 .. lane0+CT-1 of the tiled dimension.  gin/gout point at the
+// transform (user buffer or scratch, depending on the flavor).  Every thread of the CTA must call this.
 template <typename Cfg, int FLAVOR>
-__global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINB) tile_fft_kernel(TileParams<typename Cfg::T> p) {
+__device__ __forceinline__ void tile_body(const TileParams<typename Cfg::T> &p, const cx<typename Cfg::T> *gin,
+                                          cx<typename Cfg::T> *gout, int lane0, cx<typename Cfg::T> *sm) {
     using T = typename Cfg::T;
     constexpr int L = Cfg::L, TX = Cfg::TX, CT = Cfg::CT, E = Cfg::E, NP = Cfg::NP, PITCH = Cfg::PITCH;
     constexpr int THREADS = Cfg::THREADS;
     constexpr bool kFirstFromSmem = (FLAVOR == TILE_B_C2C || FLAVOR == TILE_B_R2C || FLAVOR == TILE_A_C2R);
     constexpr bool kLastToSmem = (FLAVOR == TILE_A_R2C || FLAVOR == TILE_B_C2R);
-    extern __shared__ __align__(16) unsigned char ssfft_smem[];
-    cx<T> *sm = reinterpret_cast<cx<T> *>(ssfft_smem);
-    const int c = threadIdx.x, t = threadIdx.y;
-    const int tid = t * CT + c;
+    // lane / butterfly-thread split from the flat thread id, so stages with different tile shapes (same
+    // thread count) can share one CTA in the cluster kernel
+    const int tid = threadIdx.x + threadIdx.y * blockDim.x;
+    const int c = tid % CT, t = tid / CT;
     const int n1 = p.n1, n2 = p.n2;
-    // how many lanes (columns / rows) exist along the tiled dimension
-    const int width = (FLAVOR == TILE_A_C2C)   ? n2
-                      : (FLAVOR == TILE_B_C2C) ? n1
-                      : (FLAVOR == TILE_A_R2C || FLAVOR == TILE_A_C2R) ? n2 / 2
-                                               : n1 / 2 + 1;
-    const int tiles = (width + CT - 1) / CT;
-    const long long items = p.batch * tiles;
-
-    for (long long item = blockIdx.x; item < items; item += gridDim.x) {
-        const long long B = item / tiles;
-        const int lane0 = (int)(item - B * tiles) * CT;
+    const int width = tile_width<FLAVOR>(n1, n2);
+    {
         const int lane = lane0 + c;  // column (A flavors) or row k1 (B flavors)
         const bool live = lane < width;
-        const cx<T> *gin = p.in + B * p.in_stride;
-        cx<T> *gout = p.out + B * p.out_stride;
         cx<T> v[E];
 
         // ------------------------------------------------------------------ stage-in for the smem-first flavors
@@ -117,7 +127,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINB) tile_fft_kernel(TileP
             // rows are contiguous in the scratch: read them coalesced along n2, store transposed [n2][row]
             for (int e = tid; e < CT * L; e += THREADS) {
                 const int rr = e / L, i = e - rr * L;
-                if (lane0 + rr < width) sm[i * PITCH + rr] = ld_plain(gin + (long long)(lane0 + rr) * n2 + i);
+                if (lane0 + rr < width) sm[i * PITCH + rr] = ld_l2(gin + (long long)(lane0 + rr) * n2 + i);
             }
             __syncthreads();
         }
@@ -126,7 +136,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINB) tile_fft_kernel(TileP
             if (live) {
                 for (int k1 = t; k1 <= L / 2; k1 += TX) {
                     const cx<T> *src = gin + (long long)k1 * n2 + 2 * lane;
-                    const cx<T> a = cswap(ld_plain(src)), b = cswap(ld_plain(src + 1));
+                    const cx<T> a = cswap(ld_l2(src)), b = cswap(ld_l2(src + 1));
                     sm[k1 * PITCH + c] = cswap(mk<T>(a.x - b.y, a.y + b.x));
                     if (k1 > 0 && k1 < L / 2) sm[(L - k1) * PITCH + c] = cswap(mk<T>(a.x + b.y, b.x - a.y));
                 }
@@ -280,6 +290,91 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINB) tile_fft_kernel(TileP
     }
 }
 
+// stand-alone launch of one stage over a whole batch (two launches per chunk; used for fp64 and as fallback)
+template <typename Cfg, int FLAVOR>
+__global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINB) tile_fft_kernel(TileParams<typename Cfg::T> p) {
+    using T = typename Cfg::T;
+    extern __shared__ __align__(16) unsigned char ssfft_smem[];
+    cx<T> *sm = reinterpret_cast<cx<T> *>(ssfft_smem);
+    const int width = tile_width<FLAVOR>(p.n1, p.n2);
+    const int tiles = (width + Cfg::CT - 1) / Cfg::CT;
+    const long long items = p.batch * tiles;
+    for (long long item = blockIdx.x; item < items; item += gridDim.x) {
+        const long long B = item / tiles;
+        const int lane0 = (int)(item - B * tiles) * Cfg::CT;
+        tile_body<Cfg, FLAVOR>(p, p.in + B * p.in_stride, p.out + B * p.out_stride, lane0, sm);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Both stages in ONE persistent launch: a thread-block cluster owns a transform.  Stage 1 tiles are
+// spread over the cluster's CTAs, a hardware cluster barrier (release/acquire) publishes the scratch,
+// stage 2 tiles follow.  The scratch (two slots per cluster, alternating) is a few MB in total and
+// clusters are placed on one die, so the intermediate never leaves that die's L2.
+//   KIND 0: C2C  (A_C2C on CfgA, then B_C2C on CfgB)
+//   KIND 1: R2C  (A_R2C on CfgA, then B_R2C on CfgB)
+//   KIND 2: C2R  (B_C2R on CfgB, then A_C2R on CfgA)
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+struct FourStepParams {
+    const cx<T> *in;
+    cx<T> *out;
+    cx<T> *scratch;          // 2 * clusters * scratch_per elements
+    const cx<T> *tw_a, *tw_b, *tw4;
+    int n1, n2;
+    long long batch, user_stride, scratch_per;
+    int inverse;
+};
+
+__device__ __forceinline__ unsigned cluster_ctarank() {
+    unsigned r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ unsigned cluster_nctarank() {
+    unsigned r;
+    asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_barrier() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+template <typename CfgA, typename CfgB, int KIND>
+__global__ void __launch_bounds__(CfgA::THREADS, (CfgA::MINB < CfgB::MINB ? CfgA::MINB : CfgB::MINB))
+fourstep_cluster_kernel(FourStepParams<typename CfgA::T> q) {
+    using T = typename CfgA::T;
+    static_assert(CfgA::THREADS == CfgB::THREADS, "both stages must use the same CTA size");
+    extern __shared__ __align__(16) unsigned char ssfft_smem[];
+    cx<T> *sm = reinterpret_cast<cx<T> *>(ssfft_smem);
+    const int rank = (int)cluster_ctarank(), csize = (int)cluster_nctarank();
+    const long long cid = blockIdx.x / csize, nclusters = gridDim.x / csize;
+    constexpr int F1 = KIND == 0 ? TILE_A_C2C : KIND == 1 ? TILE_A_R2C : TILE_B_C2R;
+    constexpr int F2 = KIND == 0 ? TILE_B_C2C : KIND == 1 ? TILE_B_R2C : TILE_A_C2R;
+    using Cfg1 = typename std::conditional<KIND == 2, CfgB, CfgA>::type;
+    using Cfg2 = typename std::conditional<KIND == 2, CfgA, CfgB>::type;
+    TileParams<T> p1, p2;
+    p1.in = nullptr; p1.out = nullptr; p1.tw = KIND == 2 ? q.tw_b : q.tw_a; p1.tw4 = q.tw4;
+    p1.n1 = q.n1; p1.n2 = q.n2; p1.batch = 1; p1.in_stride = 0; p1.out_stride = 0; p1.inverse = q.inverse;
+    p2 = p1;
+    p2.tw = KIND == 2 ? q.tw_a : q.tw_b;
+    const int tiles1 = (tile_width<F1>(q.n1, q.n2) + Cfg1::CT - 1) / Cfg1::CT;
+    const int tiles2 = (tile_width<F2>(q.n1, q.n2) + Cfg2::CT - 1) / Cfg2::CT;
+    int slot = 0;
+    for (long long B = cid; B < q.batch; B += nclusters, slot ^= 1) {
+        cx<T> *scr = q.scratch + (cid * 2 + slot) * q.scratch_per;
+        const cx<T> *uin = q.in + B * q.user_stride;
+        cx<T> *uout = q.out + B * q.user_stride;
+        for (int tile = rank; tile < tiles1; tile += csize) tile_body<Cfg1, F1>(p1, uin, scr, tile * Cfg1::CT, sm);
+        cluster_barrier();  // stage-1 stores of every CTA in the cluster are visible; L1 is invalidated
+        // rotate the start so the CTA that gets an extra (ragged) tile changes from transform to transform
+        for (int i = rank; i < tiles2; i += csize) {
+            const int tile = (int)((i + B) % tiles2);
+            tile_body<Cfg2, F2>(p2, scr, uout, tile * Cfg2::CT, sm);
+        }
+    }
+}
+
 #endif  // __CUDACC__
 
 // ---------------------------------------------------------------------------------------------
@@ -292,6 +387,28 @@ struct TileEntry {
     int (*launch[6])(const void *params, cudaStream_t s);  // params: TileParams<T>
 };
 const std::vector<TileEntry> &tile_registry();
+
+// cluster four-step kernels: one entry per (precision, n1, n2), launchers for C2C / R2C / C2R
+struct FourStepEntry {
+    int prec, n1, n2;
+    const char *name;
+    int threads;
+    size_t smem_bytes;
+    // returns 0 on success; *clusters_out (may be null) reports how many clusters the launch used
+    int (*launch[3])(const void *params, int max_clusters, cudaStream_t s);
+    int (*max_clusters[3])(int cluster_size);  // co-resident clusters on the current device
+};
+const std::vector<FourStepEntry> &fourstep_registry();
+int fourstep_cluster_size();  // env SSFFT_CLUSTER (default 4)
+
+template <typename T>
+inline int find_fourstep(size_t n1, size_t n2) {
+    const int prec = sizeof(T) == 4 ? 0 : 1;
+    const auto &reg = fourstep_registry();
+    for (size_t i = 0; i < reg.size(); ++i)
+        if (reg[i].prec == prec && (size_t)reg[i].n1 == n1 && (size_t)reg[i].n2 == n2) return (int)i;
+    return -1;
+}
 
 template <typename T>
 inline int find_tile(size_t len) {

@@ -57,6 +57,65 @@ TileEntry make_tile_entry(const char *name) {
     return e;
 }
 
+template <typename CfgA, typename CfgB, int KIND>
+int fourstep_max_clusters(int cluster_size) {
+    constexpr size_t smem = CfgA::smem_bytes > CfgB::smem_bytes ? CfgA::smem_bytes : CfgB::smem_bytes;
+    auto kern = fourstep_cluster_kernel<CfgA, CfgB, KIND>;
+    if (smem > 48 * 1024 &&
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+        return -1;
+    if (cluster_size > 8 &&
+        cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess)
+        return -1;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(cluster_size * 1024);
+    cfg.blockDim = dim3(CfgA::THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = cluster_size; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess) { cudaGetLastError(); return -1; }
+    return n;
+}
+
+template <typename CfgA, typename CfgB, int KIND>
+int launch_fourstep(const void *params, int max_clusters, cudaStream_t s) {
+    using T = typename CfgA::T;
+    const FourStepParams<T> &q = *reinterpret_cast<const FourStepParams<T> *>(params);
+    constexpr size_t smem = CfgA::smem_bytes > CfgB::smem_bytes ? CfgA::smem_bytes : CfgB::smem_bytes;
+    const int csize = fourstep_cluster_size();
+    long long clusters = q.batch < max_clusters ? q.batch : max_clusters;
+    if (clusters <= 0) return 0;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(clusters * csize));
+    cfg.blockDim = dim3(CfgA::THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = csize; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, fourstep_cluster_kernel<CfgA, CfgB, KIND>, q) == cudaSuccess ? 0 : 2;
+}
+
+template <typename CfgA, typename CfgB>
+FourStepEntry make_fourstep_entry(const char *name) {
+    FourStepEntry e;
+    e.prec = sizeof(typename CfgA::T) == 4 ? 0 : 1;
+    e.n1 = CfgA::L; e.n2 = CfgB::L; e.name = name;
+    e.threads = CfgA::THREADS;
+    e.smem_bytes = CfgA::smem_bytes > CfgB::smem_bytes ? CfgA::smem_bytes : CfgB::smem_bytes;
+    e.launch[0] = &launch_fourstep<CfgA, CfgB, 0>;
+    e.launch[1] = &launch_fourstep<CfgA, CfgB, 1>;
+    e.launch[2] = &launch_fourstep<CfgA, CfgB, 2>;
+    e.max_clusters[0] = &fourstep_max_clusters<CfgA, CfgB, 0>;
+    e.max_clusters[1] = &fourstep_max_clusters<CfgA, CfgB, 1>;
+    e.max_clusters[2] = &fourstep_max_clusters<CfgA, CfgB, 2>;
+    return e;
+}
+
 #define SSFFT_TILE(T, L, R0, R1, R2, TX, CT, MINB) \
     make_tile_entry<TileCfg<T, L, R0, R1, R2, TX, CT, MINB>>(#T "_tile" #L "_" #R0 "x" #R1 "x" #R2 "_ct" #CT)
 
