@@ -43,6 +43,9 @@ WORKLOADS = {
     "c4-3125-f64": ("c2c", "float64", 3125, 65536),
     "c4-6000-f64": ("c2c", "float64", 6000, 65536),
     "c1": ("c2c", "float64", 1024, 1),
+    # one transform of 2^30 points sharded over all ranks (distributed four-step, strong scaling)
+    "c5": ("dist", "float32", 1 << 30, 1),
+    "c5-small": ("dist", "float32", 1 << 24, 1),
 }
 
 
@@ -171,6 +174,110 @@ def run_reference(args):
     return 0
 
 
+def run_dist(args, n, rank, world, dev, dist):
+    """BASELINE config 5: ONE length-n complex transform sharded over all ranks (fft_b200/dist.py)."""
+    import torch
+
+    import fft_b200
+    from fft_b200.dist import DistFFT1D
+
+    per = n // world
+    plan = DistFFT1D(n, world, rank, dtype=torch.complex64)
+    x = torch.empty(per, dtype=torch.complex64, device=dev)
+    y = torch.empty_like(x)
+    fft_b200.fill_uniform(x, SEED, first_idx=rank * per * 2)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    if world == 1:
+        plan._all_to_all = lambda send, recv: recv.copy_(send.reshape(-1))  # P = 1: the exchange is the identity
+    for _ in range(args.warmup):
+        plan.fft(x, y)
+    barrier()
+    sampler = ClockSampler(int(os.environ.get("LOCAL_RANK", "0")))
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.25)
+    launches0 = fft_b200.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        plan.fft(x, y)
+    ev1.record()
+    barrier()
+    ms_total = ev0.elapsed_time(ev1)
+    launches = fft_b200.launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    if world > 1:
+        t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    ms_step = ms_total / args.steps
+    flops = 5.0 * n * math.log2(n)
+    peak, peak_src = measured_peak()
+    alg_bytes_gpu = 2 * per * 8
+    exch_bytes_gpu = 3 * per * 8 * (world - 1) / max(world, 1)  # sent per GPU per step over NVLink
+    # size-independent checks (the oracle cannot run 2^30 casually; SURVEY.md 8c): single tone -> N delta,
+    # Parseval, and ifft(fft(x)) = N x on the random input
+    checks = None
+    if args.verify:
+        def allsum(v):
+            t = torch.tensor([float(v)], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(t)
+            return float(t.item())
+        f0 = 123456789 % n
+        idx = torch.arange(per, device=dev, dtype=torch.int64) + rank * per
+        ph = ((idx * f0) % n).double() * (2.0 * math.pi / n)
+        tone = torch.complex(torch.cos(ph), torch.sin(ph)).to(torch.complex64)
+        del idx, ph
+        yt = torch.empty_like(tone)
+        plan.fft(tone, yt)
+        e_all = allsum((yt.real.double() ** 2 + yt.imag.double() ** 2).sum().item())
+        own = f0 // per
+        peak_v = yt[f0 - own * per].item() if rank == own else 0j
+        pr, pi = allsum(peak_v.real), allsum(peak_v.imag)
+        tone_err = math.sqrt(max(e_all - (pr * pr + pi * pi), 0.0) + (pr - n) ** 2 + pi ** 2) / n
+        del tone, yt
+        ex = allsum((x.real.double() ** 2 + x.imag.double() ** 2).sum().item())
+        ey = allsum((y.real.double() ** 2 + y.imag.double() ** 2).sum().item())
+        back = torch.empty_like(x)
+        plan.ifft(y, back)
+        num = allsum(((back.real.double() - n * x.real.double()) ** 2 + (back.imag.double() - n * x.imag.double()) ** 2).sum().item())
+        rt_err = math.sqrt(num / (n * n * ex))
+        lim = 1e-6 * math.log2(n)
+        checks = {"tone_rel_err": tone_err, "parseval_rel_err": abs(ey / (n * ex) - 1.0), "roundtrip_rel_l2": rt_err,
+                  "tolerance": lim, "ok": bool(tone_err <= lim and rt_err <= 2 * lim and abs(ey / (n * ex) - 1.0) < 1e-4)}
+        del back
+    if rank == 0:
+        line = {
+            "metric": "Distributed fp32 C2C FFT GFLOP/s (5N·log2N), single transform N=%d" % n,
+            "value": flops / (ms_step * 1e-3) / 1e9, "unit": "GFLOP/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32",
+            "data": f"synthetic uniform[-0.5,0.5), counter-based generator, seed {SEED}",
+            "config": {"workload": f"{args.workload}: one c2c float32 transform of N={n} = {plan.n1} x {plan.n2}, "
+                                   f"block-sharded over {world} GPUs, natural order in and out",
+                       "parallelism": f"four-step, 3 all-to-all exchanges (all_to_all_single over NCCL) x{world}"},
+            "roofline": {"bound": "hbm", "achieved": alg_bytes_gpu / (ms_step * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                         "frac": alg_bytes_gpu / (ms_step * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
+                         "nvlink_bytes_per_gpu_per_step": exch_bytes_gpu,
+                         "nvlink_GBps_per_gpu_if_exchange_only": exch_bytes_gpu / (ms_step * 1e-3) / 1e9},
+            "clocks": clocks, "gpu_launches": launches,
+        }
+        if checks:
+            line["checks"] = checks
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -181,6 +288,7 @@ def main():
     ap.add_argument("--batch", type=int, default=0, help="override transforms per GPU (tests only)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--verify", action="store_true", help="c5: tone / Parseval / round-trip checks at full size")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
@@ -211,6 +319,8 @@ def main():
     esz = 4 if dtype == "float32" else 8
 
     # ---- inputs resident in HBM (each rank its own slice of the global synthetic stream)
+    if kind == "dist":
+        return run_dist(args, n, rank, world, dev, dist)
     if kind == "c2c":
         plan = fft_b200.FFT(n, dtype=dtype)
         x = torch.empty((batch, n), dtype=cdt, device=dev)

@@ -73,6 +73,8 @@ def load():
         "ssfft_memcpy_d2h": (i32, [vp, vp, sz, vp]),
         "ssfft_stream_synchronize": (i32, [vp]),
         "ssfft_fill_uniform": (i32, [vp, sz, i32, u64, u64, vp]),
+        "ssfft_transpose_twiddle": (i32, [vp, vp, sz, sz, sz, sz, u64, i32, i32, vp]),
+        "ssfft_permute102": (i32, [vp, vp, sz, sz, sz, i32, vp]),
         "ssfft_error_string": (c.c_char_p, [i32]),
         "ssfft_last_cuda_error": (c.c_char_p, []),
         "ssfft_launch_count": (u64, []),

@@ -102,6 +102,53 @@ __global__ void rotate_kernel(cx<T> *__restrict__ dst, const cx<T> *__restrict__
     dst[idx] = conj_rot ? cmulc(v, r) : cmul(v, r);
 }
 
+// ---- local building blocks of the distributed four-step (fft_b200/dist.py) ----
+// out[b][c][r] = in[b][r][c] * W_N^((row0 + r) * c)^(+-1)   (twiddle optional: n_total == 0 -> plain transpose)
+// 32x32 tiles through shared memory, both sides coalesced.  The twiddle phase is evaluated in double
+// (sincospi) from the exact integer (row*col) mod N, so it is correct for N up to 2^40 in both precisions.
+template <typename T>
+__global__ void transpose_twiddle_kernel(const cx<T> *__restrict__ in, cx<T> *__restrict__ out, long long rows,
+                                         long long cols, long long row0, unsigned long long n_total, int conj_tw) {
+    __shared__ cx<T> tile[32][33];
+    const long long b = blockIdx.z;
+    const long long r0 = (long long)blockIdx.y * 32, c0 = (long long)blockIdx.x * 32;
+    const cx<T> *src = in + b * rows * cols;
+    cx<T> *dst = out + b * rows * cols;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const long long r = r0 + i, c = c0 + threadIdx.x;
+        if (r < rows && c < cols) {
+            cx<T> v = src[r * cols + c];
+            if (n_total) {
+                const unsigned long long q =
+                    (unsigned long long)(((unsigned __int128)(unsigned long long)(row0 + r) * (unsigned long long)c) % n_total);
+                double sn, cs;
+                sincospi(-2.0 * (double)q / (double)n_total, &sn, &cs);
+                const cx<T> w = mk<T>((T)cs, (T)(conj_tw ? -sn : sn));
+                v = cmul(v, w);
+            }
+            tile[i][threadIdx.x] = v;
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const long long c = c0 + i, r = r0 + threadIdx.x;
+        if (r < rows && c < cols) dst[c * rows + r] = tile[threadIdx.x][i];
+    }
+}
+
+// out[b][a][c] = in[a][b][c]: swaps the two outer dimensions, moving contiguous runs of `run` elements
+template <typename T>
+__global__ void permute102_kernel(const cx<T> *__restrict__ in, cx<T> *__restrict__ out, long long A, long long B,
+                                  long long run) {
+    const long long total = A * B * run;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const long long c = i % run, ab = i / run;
+        const long long a = ab % A, b = ab / A;  // i enumerates the OUTPUT [b][a][c]
+        out[i] = in[(a * B + b) * run + c];
+    }
+}
+
 // counter-based uniform [-0.5, 0.5) generator, twin of oracle_fill_uniform_* 
 __device__ __forceinline__ unsigned long long splitmix64(unsigned long long x) {
     x += 0x9E3779B97F4A7C15ull;

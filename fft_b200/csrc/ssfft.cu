@@ -631,6 +631,43 @@ int ssfft_fill_uniform(void *d_dst, size_t count, int precision, uint64_t seed, 
     return SSFFT_OK;
 }
 
+int ssfft_transpose_twiddle(const void *d_in, void *d_out, size_t batch, size_t rows, size_t cols, size_t row0,
+                            uint64_t n_total, int inverse, int precision, void *stream) {
+    if (!batch || !rows || !cols) return SSFFT_OK;
+    if (!d_in || !d_out || d_in == d_out) return SSFFT_ERR_INVALID;
+    if (batch > 65535 || (rows + 31) / 32 > 65535) return SSFFT_ERR_INVALID;
+    dim3 grid((unsigned)((cols + 31) / 32), (unsigned)((rows + 31) / 32), (unsigned)batch), block(32, 8);
+    if (precision == SSFFT_F32)
+        transpose_twiddle_kernel<float><<<grid, block, 0, (cudaStream_t)stream>>>(
+            (const cx<float> *)d_in, (cx<float> *)d_out, (long long)rows, (long long)cols, (long long)row0, n_total, inverse);
+    else if (precision == SSFFT_F64)
+        transpose_twiddle_kernel<double><<<grid, block, 0, (cudaStream_t)stream>>>(
+            (const cx<double> *)d_in, (cx<double> *)d_out, (long long)rows, (long long)cols, (long long)row0, n_total, inverse);
+    else
+        return SSFFT_ERR_INVALID;
+    ++g_launches;
+    CU(cudaGetLastError());
+    return SSFFT_OK;
+}
+
+int ssfft_permute102(const void *d_in, void *d_out, size_t A, size_t B, size_t run, int precision, void *stream) {
+    if (!A || !B || !run) return SSFFT_OK;
+    if (!d_in || !d_out || d_in == d_out) return SSFFT_ERR_INVALID;
+    const size_t total = A * B * run;
+    unsigned blocks = (unsigned)((total + 255) / 256 > 148 * 16 ? 148 * 16 : (total + 255) / 256);
+    if (precision == SSFFT_F32)
+        permute102_kernel<float><<<blocks, 256, 0, (cudaStream_t)stream>>>((const cx<float> *)d_in, (cx<float> *)d_out,
+                                                                            (long long)A, (long long)B, (long long)run);
+    else if (precision == SSFFT_F64)
+        permute102_kernel<double><<<blocks, 256, 0, (cudaStream_t)stream>>>((const cx<double> *)d_in, (cx<double> *)d_out,
+                                                                             (long long)A, (long long)B, (long long)run);
+    else
+        return SSFFT_ERR_INVALID;
+    ++g_launches;
+    CU(cudaGetLastError());
+    return SSFFT_OK;
+}
+
 const char *ssfft_error_string(int status) {
     switch (status) {
         case SSFFT_OK: return "ok";

@@ -103,6 +103,15 @@ SSFFT_API int ssfft_stream_synchronize(void *stream);
 SSFFT_API int ssfft_fill_uniform(void *d_dst, size_t count, int precision, uint64_t seed, uint64_t first_idx,
                                  void *stream);
 
+/* ---- local building blocks of the distributed four-step (single 1-D transform sharded over GPUs,
+ * SURVEY.md section 8e; orchestration in fft_b200/dist.py).  Complex elements, device pointers. ----
+ * out[b][c][r] = in[b][r][c] * W_N^((row0 + r) * c)   (conjugated when inverse != 0; n_total == 0: no twiddle) */
+SSFFT_API int ssfft_transpose_twiddle(const void *d_in, void *d_out, size_t batch, size_t rows, size_t cols,
+                                      size_t row0, uint64_t n_total, int inverse, int precision, void *stream);
+/* out[b][a][c] = in[a][b][c] : swap the two outer dimensions of an [A][B][run] array */
+SSFFT_API int ssfft_permute102(const void *d_in, void *d_out, size_t A, size_t B, size_t run, int precision,
+                               void *stream);
+
 /* ---- diagnostics ---- */
 SSFFT_API const char *ssfft_error_string(int status);
 SSFFT_API const char *ssfft_last_cuda_error(void);

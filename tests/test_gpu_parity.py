@@ -268,3 +268,22 @@ def test_headline_batch_properties(oracle, cuda_device):
     num = torch.linalg.vector_norm((z - n * x).reshape(batch, -1), dim=1)
     den = torch.linalg.vector_norm((n * x).reshape(batch, -1), dim=1)
     assert (num / den).max().item() <= 2 * tol(n, np.complex64)
+
+
+def test_distributed_four_step_logical_ranks_on_one_gpu(oracle, cuda_device):
+    """The multi-GPU four-step code path with P logical ranks on one device (block swaps instead of NCCL):
+    same kernels, same index logic as the real distributed run (fft_b200/dist.py)."""
+    from fft_b200.dist import DistFFT1D
+
+    for n, world in ((1 << 16, 2), (1 << 20, 4), (1 << 22, 8), (3 * (1 << 16), 2)):
+        x = oracle.uniform_complex((n,), 11, np.complex64)
+        plan = DistFFT1D(n, world, dtype=torch.complex64)
+        per = n // world
+        xs = [torch.from_numpy(x[r * per:(r + 1) * per].copy()).cuda() for r in range(world)]
+        ys = plan.run_logical(xs)
+        y = torch.cat(ys).cpu().numpy()
+        ref = oracle.run(oracle.KIND_C2C_FWD, x[None], n, threads=1)[0]
+        assert oracle.rel_l2(y[None], ref) <= tol(n, np.complex64), (n, world, plan.n1, plan.n2)
+        back = torch.cat(plan.run_logical(ys, inverse=True)).cpu().numpy()
+        assert oracle.rel_l2(back[None], (n * x)[None]) <= 2 * tol(n, np.complex64)
+        assert plan.exchanges == 6
