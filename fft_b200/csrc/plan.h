@@ -47,6 +47,7 @@ struct ssfft_plan {
     void *d_tile_tw_a = nullptr, *d_tile_tw_b = nullptr;
     void *d_tw4 = nullptr;                 // W_N^(n2*k1) laid out [k1][n2]
     size_t scratch_per = 0;                // scratch elements (cx) per transform
+    int ctb_log2 = 0;                      // tile-major block height (lanes of the row-stage kernel)
     int fs_id = -1;                        // cluster kernel (both stages in one launch), -1 = two launches per chunk
     int fs_clusters = 0;                   // co-resident clusters the scratch was sized for
     void *d_ep_lo = nullptr, *d_ep_hi = nullptr;

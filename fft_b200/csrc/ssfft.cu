@@ -145,8 +145,10 @@ int env_int(const char *name, int dflt) {
 
 template <typename T>
 int launch_tile_flavor(int id, int flavor, const cx<T> *in, cx<T> *out, const void *tw, const void *tw4, int n1, int n2,
-                       long long batch, long long in_stride, long long out_stride, int inverse, cudaStream_t s) {
+                       long long batch, long long in_stride, long long out_stride, int inverse, int ctb_log2,
+                       cudaStream_t s) {
     TileParams<T> p;
+    p.ctb_log2 = ctb_log2;
     p.in = in; p.out = out;
     p.tw = (const cx<T> *)tw; p.tw4 = (const cx<T> *)tw4;
     p.n1 = n1; p.n2 = n2; p.batch = batch;
@@ -164,7 +166,7 @@ int setup_tiled(ssfft_plan *pl, size_t total, bool real, bool *ok) {
     if (total == 0 || (total & (total - 1))) return SSFFT_OK;  // power-of-two only
     int lg = 0;
     while (((size_t)1 << lg) < total) ++lg;
-    const int min_lg = real ? env_int("SSFFT_TILE_MIN_LOG2_REAL", 15) : env_int("SSFFT_TILE_MIN_LOG2", 14);
+    const int min_lg = real ? env_int("SSFFT_TILE_MIN_LOG2_REAL", 16) : env_int("SSFFT_TILE_MIN_LOG2", 15);
     if (lg < min_lg) return SSFFT_OK;
     size_t n1 = (size_t)1 << (lg / 2), n2 = total / n1;
     int ia = find_tile<T>(n1), ib = find_tile<T>(n2);
@@ -174,14 +176,21 @@ int setup_tiled(ssfft_plan *pl, size_t total, bool real, bool *ok) {
     if (rc) return rc;
     rc = build_tile_twiddles<T>(ib, &pl->d_tile_tw_b);
     if (rc) return rc;
-    const size_t rows = real ? n1 / 2 + 1 : n1;
-    std::vector<T> h(2 * rows * n2);
-    for (size_t k1 = 0; k1 < rows; ++k1)
+    // scratch and twiddles are tile-major in blocks of CTB rows, CTB = lanes of the row-stage kernel (tiled.cuh)
+    const size_t ctb = (size_t)tile_registry()[ib].ct;
+    int ctb_log2 = 0;
+    while (((size_t)1 << ctb_log2) < ctb) ++ctb_log2;
+    pl->ctb_log2 = ctb_log2;
+    const size_t rows_live = real ? n1 / 2 + 1 : n1;
+    const size_t rows = (rows_live + ctb - 1) / ctb * ctb;
+    std::vector<T> h(2 * rows * n2, (T)0);
+    for (size_t k1 = 0; k1 < rows_live; ++k1)
         for (size_t c = 0; c < n2; ++c) {
             unsigned long long q = (unsigned long long)k1 * c % total;
             long double a = 2.0L * 3.14159265358979323846264338327950288L * (long double)q / (long double)total;
-            h[2 * (k1 * n2 + c)] = (T)cosl(a);
-            h[2 * (k1 * n2 + c) + 1] = (T)(-sinl(a));
+            const size_t o = (k1 / ctb) * (ctb * n2) + c * ctb + (k1 % ctb);
+            h[2 * o] = (T)cosl(a);
+            h[2 * o + 1] = (T)(-sinl(a));
         }
     CU(cudaMalloc(&pl->d_tw4, h.size() * sizeof(T)));
     CU(cudaMemcpy(pl->d_tw4, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
@@ -227,6 +236,8 @@ int exec_tiled(ssfft_plan *pl, int kind, const void *in, void *out, long long ba
         q.in = (const cx<T> *)in; q.out = (cx<T> *)out; q.scratch = scratch;
         q.tw_a = (const cx<T> *)pl->d_tile_tw_a; q.tw_b = (const cx<T> *)pl->d_tile_tw_b; q.tw4 = (const cx<T> *)pl->d_tw4;
         q.n1 = n1; q.n2 = n2; q.batch = batch; q.user_stride = user_stride; q.scratch_per = sp; q.inverse = inverse;
+        q.ctb_log2 = pl->ctb_log2;
+        q.discard = env_int("SSFFT_DISCARD", 1);
         int rc = fourstep_registry()[pl->fs_id].launch[kind](&q, pl->fs_clusters, s);
         ++g_launches;
         if (rc) return cuda_fail(cudaGetLastError(), "fourstep_cluster_kernel launch");
@@ -239,22 +250,22 @@ int exec_tiled(ssfft_plan *pl, int kind, const void *in, void *out, long long ba
         int rc;
         if (kind == 0) {
             rc = launch_tile_flavor<T>(pl->tile_a, TILE_A_C2C, cin, scratch, pl->d_tile_tw_a, pl->d_tw4, n1, n2, nb,
-                                       user_stride, sp, inverse, s);
+                                       user_stride, sp, inverse, pl->ctb_log2, s);
             if (rc) return rc;
             rc = launch_tile_flavor<T>(pl->tile_b, TILE_B_C2C, scratch, cout, pl->d_tile_tw_b, pl->d_tw4, n1, n2, nb, sp,
-                                       user_stride, inverse, s);
+                                       user_stride, inverse, pl->ctb_log2, s);
         } else if (kind == 1) {
             rc = launch_tile_flavor<T>(pl->tile_a, TILE_A_R2C, cin, scratch, pl->d_tile_tw_a, pl->d_tw4, n1, n2, nb,
-                                       user_stride, sp, 0, s);
+                                       user_stride, sp, 0, pl->ctb_log2, s);
             if (rc) return rc;
             rc = launch_tile_flavor<T>(pl->tile_b, TILE_B_R2C, scratch, cout, pl->d_tile_tw_b, pl->d_tw4, n1, n2, nb, sp,
-                                       user_stride, 0, s);
+                                       user_stride, 0, pl->ctb_log2, s);
         } else {
             rc = launch_tile_flavor<T>(pl->tile_b, TILE_B_C2R, cin, scratch, pl->d_tile_tw_b, pl->d_tw4, n1, n2, nb,
-                                       user_stride, sp, 1, s);
+                                       user_stride, sp, 1, pl->ctb_log2, s);
             if (rc) return rc;
             rc = launch_tile_flavor<T>(pl->tile_a, TILE_A_C2R, scratch, cout, pl->d_tile_tw_a, pl->d_tw4, n1, n2, nb, sp,
-                                       user_stride, 1, s);
+                                       user_stride, 1, pl->ctb_log2, s);
         }
         if (rc) return rc;
     }
@@ -322,13 +333,16 @@ int build_plan_typed(ssfft_plan *pl) {
                      pl->kind == SSFFT_C2C ? "complex" : "real", pl->kind == SSFFT_C2C ? n : pl->n_real, pl->n1,
                      tile_registry()[pl->tile_a].name, pl->n2, tile_registry()[pl->tile_b].name, pl->chunk);
         pl->desc = buf;
-    } else if (n <= limit) {
+    } else if (n <= limit || find_fused<T>(n, FUSED_CONTIG) >= 0) {
         pl->four_step = false;
-        int rc = build_generic_stage<T>(pl->direct, n, smem_max);
-        if (rc) return rc;
+        int rc = SSFFT_OK;
         pl->fused.id = find_fused<T>(n, FUSED_CONTIG);
         if (pl->fused.id >= 0) {
             rc = build_fused_twiddles<T>(pl->fused.id, &pl->fused.d_twiddles);
+            if (rc) return rc;
+            pl->direct.radix = choose_radices(n);  // description only: the fused kernel has its own radices
+        } else {
+            rc = build_generic_stage<T>(pl->direct, n, smem_max);
             if (rc) return rc;
         }
         std::string rs;

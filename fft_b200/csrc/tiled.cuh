@@ -16,12 +16,13 @@
 // the bins of row N1-k1 (k2 >= N2/2).  Same outputs (bins 0..N/2-1, (DC, Nyquist) packed in bin 0), no
 // cross-CTA exchange, half the traffic of a complex transform.
 //
+//   (scratch = tile-major, see tm_off)
 //   flavor      FFT length  tile over              reads                      writes
 //   A_C2C       N1          n2 (columns)           x[n1][n2]                  Y[k1][n2] * W_N^(n2 k1)   (scratch)
-//   B_C2C       N2          k1 (rows)              Y[k1][n2]   (transposing)  X[k1 + N1 k2]
+//   B_C2C       N2          k1 (rows)              Y[k1][n2]                  X[k1 + N1 k2]
 //   A_R2C       N1          n2/2 (column pairs)    real x as complex pairs    Y[k1<=N1/2][n2] * W       (scratch)
-//   B_R2C       N2          k1 <= N1/2             Y[k1][n2]   (transposing)  packed half spectrum
-//   B_C2R       N2          k1 <= N1/2             packed half spectrum       U[k1][n2] * conj W  (scratch, transposing)
+//   B_R2C       N2          k1 <= N1/2             Y[k1][n2]                  packed half spectrum
+//   B_C2R       N2          k1 <= N1/2             packed half spectrum       U[k1][n2] * conj W        (scratch)
 //   A_C2R       N1          n2/2 (column pairs)    U (Hermitian-extended)     real x as complex pairs
 #pragma once
 #include <cuda_runtime.h>
@@ -68,6 +69,7 @@ struct TileParams {
     long long batch;
     long long in_stride, out_stride;  // cx elements between consecutive transforms
     int inverse;       // C2C only: swap re/im on the way in (A) and out (B)
+    int ctb_log2;      // log2 of the stage-2 tile width: scratch / tw4 are tile-major in blocks of 2^ctb_log2 rows
 };
 
 #ifdef __CUDACC__
@@ -101,45 +103,59 @@ __host__ __device__ constexpr int tile_width(int n1, int n2) {
                                     : n1 / 2 + 1;
 }
 
+// Scratch (and four-step twiddle table) layout, "tile-major": element (k1, n2) lives at
+//     (k1 / CTB) * (CTB * n2) + n2 * CTB + (k1 % CTB)            CTB = lanes of the stage-2 (row) kernel
+// i.e. the [n2][CTB] image a stage-2 CTA wants is one contiguous block, and stage 1 can write 128-byte runs
+// of consecutive k1.  No shared-memory transposition is needed on either side.
+__device__ __forceinline__ long long tm_off(int k1, int n2idx, int n2, int ctb_log2) {
+    const int ctb = 1 << ctb_log2;
+    return (long long)(k1 >> ctb_log2) * ((long long)ctb * n2) + (long long)n2idx * ctb + (k1 & (ctb - 1));
+}
+
 // One tile of one transform: lanes lane0 .. lane0+CT-1 of the tiled dimension.  gin/gout point at the
 // transform (user buffer or scratch, depending on the flavor).  Every thread of the CTA must call this.
-template <typename Cfg, int FLAVOR>
+// N1C / N2C / CTBLOG: compile-time four-step dimensions (0 / -1 = take them from `p` at run time).  With them
+// fixed every global address is base + immediate, which roughly halves the instruction count of a tile.
+template <typename Cfg, int FLAVOR, int N1C = 0, int N2C = 0, int CTBLOG = -1>
 __device__ __forceinline__ void tile_body(const TileParams<typename Cfg::T> &p, const cx<typename Cfg::T> *gin,
                                           cx<typename Cfg::T> *gout, int lane0, cx<typename Cfg::T> *sm) {
     using T = typename Cfg::T;
     constexpr int L = Cfg::L, TX = Cfg::TX, CT = Cfg::CT, E = Cfg::E, NP = Cfg::NP, PITCH = Cfg::PITCH;
     constexpr int THREADS = Cfg::THREADS;
-    constexpr bool kFirstFromSmem = (FLAVOR == TILE_B_C2C || FLAVOR == TILE_B_R2C || FLAVOR == TILE_A_C2R);
-    constexpr bool kLastToSmem = (FLAVOR == TILE_A_R2C || FLAVOR == TILE_B_C2R);
-    // lane / butterfly-thread split from the flat thread id, so stages with different tile shapes (same
-    // thread count) can share one CTA in the cluster kernel
+    constexpr bool kFirstFromSmem = (FLAVOR == TILE_A_C2R);
+    constexpr bool kLastToSmem = (FLAVOR == TILE_A_R2C);
+    // stage-1 C2C: the last pass runs with lanes along the butterfly index so its stores are k1-contiguous
+    constexpr bool kTransposedLast = (FLAVOR == TILE_A_C2C);
+    static_assert(!kTransposedLast || NP >= 2, "transposed last pass needs a shared-memory exchange before it");
     const int tid = threadIdx.x + threadIdx.y * blockDim.x;
-    const int c = tid % CT, t = tid / CT;
-    const int n1 = p.n1, n2 = p.n2;
+    const int c = tid % CT, t = tid / CT;      // lanes along the tiled dimension (global loads coalesce over c)
+    const int c2 = tid / TX, t2 = tid % TX;    // transposed mapping: lanes along the butterfly index
+    const int n1 = N1C ? N1C : p.n1, n2 = N2C ? N2C : p.n2, ctb = CTBLOG >= 0 ? CTBLOG : p.ctb_log2;
     const int width = tile_width<FLAVOR>(n1, n2);
     {
         const int lane = lane0 + c;  // column (A flavors) or row k1 (B flavors)
         const bool live = lane < width;
         cx<T> v[E];
 
-        // ------------------------------------------------------------------ stage-in for the smem-first flavors
-        if constexpr (FLAVOR == TILE_B_C2C || FLAVOR == TILE_B_R2C) {
-            // rows are contiguous in the scratch: read them coalesced along n2, store transposed [n2][row]
-            for (int e = tid; e < CT * L; e += THREADS) {
-                const int rr = e / L, i = e - rr * L;
-                if (lane0 + rr < width) sm[i * PITCH + rr] = ld_l2(gin + (long long)(lane0 + rr) * n2 + i);
-            }
-            __syncthreads();
-        }
         if constexpr (FLAVOR == TILE_A_C2R) {
-            // G[k1] = U[k1][2c'] + i U[k1][2c'+1], Hermitian-extended to k1 > N1/2; scratch holds swap(U)
-            if (live) {
-                for (int k1 = t; k1 <= L / 2; k1 += TX) {
-                    const cx<T> *src = gin + (long long)k1 * n2 + 2 * lane;
-                    const cx<T> a = cswap(ld_l2(src)), b = cswap(ld_l2(src + 1));
-                    sm[k1 * PITCH + c] = cswap(mk<T>(a.x - b.y, a.y + b.x));
-                    if (k1 > 0 && k1 < L / 2) sm[(L - k1) * PITCH + c] = cswap(mk<T>(a.x + b.y, b.x - a.y));
+            // G[k1] = U[k1][2c'] + i U[k1][2c'+1], Hermitian-extended to k1 > N1/2; scratch holds swap(U).
+            // Lanes run along k1 so the tile-major scratch is read in 128-byte runs.
+            constexpr int KH = L / 2;
+            for (int e = tid; e < KH * CT; e += THREADS) {
+                const int k1 = e % KH, cc = e / KH;
+                if (lane0 + cc < width) {
+                    const int col = 2 * (lane0 + cc);
+                    const cx<T> a = cswap(ld_l2(gin + tm_off(k1, col, n2, ctb)));
+                    const cx<T> b = cswap(ld_l2(gin + tm_off(k1, col + 1, n2, ctb)));
+                    sm[k1 * PITCH + cc] = cswap(mk<T>(a.x - b.y, a.y + b.x));
+                    if (k1 > 0) sm[(L - k1) * PITCH + cc] = cswap(mk<T>(a.x + b.y, b.x - a.y));
                 }
+            }
+            if (tid < CT && lane0 + tid < width) {  // k1 = N1/2 (self-conjugate row)
+                const int col = 2 * (lane0 + tid);
+                const cx<T> a = cswap(ld_l2(gin + tm_off(KH, col, n2, ctb)));
+                const cx<T> b = cswap(ld_l2(gin + tm_off(KH, col + 1, n2, ctb)));
+                sm[KH * PITCH + tid] = cswap(mk<T>(a.x - b.y, a.y + b.x));
             }
             __syncthreads();
         }
@@ -148,6 +164,8 @@ __device__ __forceinline__ void tile_body(const TileParams<typename Cfg::T> &p, 
             constexpr int ps = decltype(pc)::value;
             constexpr int R = Cfg::radix(ps), P = Cfg::prod(ps), MN = Cfg::mnext(ps), NR = L / R, U = E / R;
             constexpr bool first = (ps == 0), last = (ps == NP - 1);
+            constexpr bool tr = last && kTransposedLast;  // this pass uses the transposed thread mapping
+            const int tt = tr ? t2 : t, cc = tr ? c2 : c;
             // ---- gather
             if constexpr (first && !kFirstFromSmem) {
                 if (live) {
@@ -162,6 +180,8 @@ __device__ __forceinline__ void tile_body(const TileParams<typename Cfg::T> &p, 
                                 if (p.inverse) x = cswap(x);
                             } else if constexpr (FLAVOR == TILE_A_R2C) {
                                 x = ld_stream(gin + (long long)idx * (n2 / 2) + lane);
+                            } else if constexpr (FLAVOR == TILE_B_C2C || FLAVOR == TILE_B_R2C) {
+                                x = ld_l2(gin + tm_off(lane, idx, n2, ctb));  // row k1 = lane, element n2 = idx
                             } else {  // TILE_B_C2R: row k1 = lane, element k2 = idx, Hermitian-extended packed spectrum
                                 const int k1 = lane, k2 = idx;
                                 if (k2 < L / 2) {
@@ -186,10 +206,10 @@ __device__ __forceinline__ void tile_body(const TileParams<typename Cfg::T> &p, 
 #pragma unroll
                 for (int u = 0; u < U; ++u)
 #pragma unroll
-                    for (int j = 0; j < R; ++j) v[u * R + j] = sm[(t + TX * u + NR * j) * PITCH + c];
+                    for (int j = 0; j < R; ++j) v[u * R + j] = sm[(tt + TX * u + NR * j) * PITCH + cc];
                 __syncthreads();
             }
-            // ---- butterflies + inter-pass twiddles (identical for every lane: broadcast loads)
+            // ---- butterflies + inter-pass twiddles (identical for every lane of a tile)
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 cx<T> w[R];
@@ -197,7 +217,7 @@ __device__ __forceinline__ void tile_body(const TileParams<typename Cfg::T> &p, 
                 for (int j = 0; j < R; ++j) w[j] = v[u * R + j];
                 Dft<R>::run(w);
                 if constexpr (!last) {
-                    const int b = t + TX * u;
+                    const int b = tt + TX * u;
                     const int mp = b / P;
                     const cx<T> *twp = p.tw + Cfg::tw_off(ps) + mp;
 #pragma unroll
@@ -210,83 +230,77 @@ __device__ __forceinline__ void tile_body(const TileParams<typename Cfg::T> &p, 
             if constexpr (!last) {
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
-                    const int b = t + TX * u;
+                    const int b = tt + TX * u;
                     const int mp = b / P, racc = b - mp * P;
                     const int o = racc + P * R * mp;
 #pragma unroll
-                    for (int r = 0; r < R; ++r) sm[(o + P * r) * PITCH + c] = v[u * R + r];
+                    for (int r = 0; r < R; ++r) sm[(o + P * r) * PITCH + cc] = v[u * R + r];
                 }
                 __syncthreads();
             } else if constexpr (kLastToSmem) {
 #pragma unroll
                 for (int u = 0; u < U; ++u)
 #pragma unroll
-                    for (int r = 0; r < R; ++r) {
-                        const int k = t + TX * u + P * r;  // natural-order output index
-                        cx<T> x = v[u * R + r];
-                        if constexpr (FLAVOR == TILE_B_C2R) {
-                            if (live) x = cmul(x, ld_table(p.tw4 + (long long)lane * n2 + k));  // swapped domain: plain W
-                        }
-                        sm[k * PITCH + c] = x;
-                    }
+                    for (int r = 0; r < R; ++r) sm[(t + TX * u + P * r) * PITCH + c] = v[u * R + r];
                 __syncthreads();
-            } else if (live) {
+            } else {
+                const int lane_s = lane0 + cc;  // the lane this thread stores for (differs from `lane` when transposed)
+                if (lane_s < width) {
 #pragma unroll
-                for (int u = 0; u < U; ++u)
+                    for (int u = 0; u < U; ++u)
 #pragma unroll
-                    for (int r = 0; r < R; ++r) {
-                        const int k = t + TX * u + P * r;
-                        cx<T> x = v[u * R + r];
-                        if constexpr (FLAVOR == TILE_A_C2C) {
-                            x = cmul(x, ld_table(p.tw4 + (long long)k * n2 + lane));
-                            st_plain(gout + (long long)k * n2 + lane, x);  // scratch: keep it in L2
-                        } else if constexpr (FLAVOR == TILE_B_C2C) {
-                            if (p.inverse) x = cswap(x);
-                            st_stream(gout + lane + (long long)n1 * k, x);
-                        } else if constexpr (FLAVOR == TILE_A_C2R) {
-                            st_stream(gout + (long long)k * (n2 / 2) + lane, cswap(x));
-                        } else {  // TILE_B_R2C: row k1 = lane, bin k2 = k
-                            const int k1 = lane, k2 = k;
-                            if (k2 < L / 2) {
-                                if (k1 == 0 && k2 == 0) reinterpret_cast<T *>(gout)[0] = x.x;  // DC
-                                else st_stream(gout + k1 + (long long)n1 * k2, x);
-                            } else if (k1 == 0) {
-                                if (k2 == L / 2) reinterpret_cast<T *>(gout)[1] = x.x;  // Nyquist
-                            } else if (k1 < n1 / 2) {
-                                st_stream(gout + (n1 - k1) + (long long)n1 * (L - 1 - k2), cconj(x));
+                        for (int r = 0; r < R; ++r) {
+                            const int k = tt + TX * u + P * r;  // natural-order output index of this stage
+                            cx<T> x = v[u * R + r];
+                            if constexpr (FLAVOR == TILE_A_C2C) {        // column n2 = lane_s, row k1 = k
+                                const long long o = tm_off(k, lane_s, n2, ctb);
+                                st_plain(gout + o, cmul(x, ld_table(p.tw4 + o)));  // scratch: keep it in L2
+                            } else if constexpr (FLAVOR == TILE_B_C2R) {  // row k1 = lane_s, column n2 = k
+                                const long long o = tm_off(lane_s, k, n2, ctb);
+                                st_plain(gout + o, cmul(x, ld_table(p.tw4 + o)));  // swapped domain: plain W
+                            } else if constexpr (FLAVOR == TILE_B_C2C) {
+                                if (p.inverse) x = cswap(x);
+                                st_stream(gout + lane_s + (long long)n1 * k, x);
+                            } else if constexpr (FLAVOR == TILE_A_C2R) {
+                                st_stream(gout + (long long)k * (n2 / 2) + lane_s, cswap(x));
+                            } else {  // TILE_B_R2C: row k1 = lane_s, bin k2 = k
+                                const int k1 = lane_s, k2 = k;
+                                if (k2 < L / 2) {
+                                    if (k1 == 0 && k2 == 0) reinterpret_cast<T *>(gout)[0] = x.x;  // DC
+                                    else st_stream(gout + k1 + (long long)n1 * k2, x);
+                                } else if (k1 == 0) {
+                                    if (k2 == L / 2) reinterpret_cast<T *>(gout)[1] = x.x;  // Nyquist
+                                } else if (k1 < n1 / 2) {
+                                    st_stream(gout + (n1 - k1) + (long long)n1 * (L - 1 - k2), cconj(x));
+                                }
                             }
                         }
-                    }
+                }
             }
         });
 
-        // ------------------------------------------------------------------ epilogues of the smem-last flavors
         if constexpr (FLAVOR == TILE_A_R2C) {
-            // separate the two real columns packed in Z, twiddle, store rows k1 <= N1/2 of the scratch
-            if (live) {
-                for (int k1 = t; k1 <= L / 2; k1 += TX) {
-                    const cx<T> z = sm[k1 * PITCH + c], zc = sm[((L - k1) & (L - 1)) * PITCH + c];
-                    const T half = (T)0.5;
-                    const cx<T> xe = mk<T>((z.x + zc.x) * half, (z.y - zc.y) * half);
-                    const cx<T> xo = mk<T>((z.y + zc.y) * half, (zc.x - z.x) * half);
-                    const cx<T> *w = p.tw4 + (long long)k1 * n2 + 2 * lane;
-                    cx<T> *dst = gout + (long long)k1 * n2 + 2 * lane;
-                    st_plain(dst, cmul(xe, ld_table(w)));
-                    st_plain(dst + 1, cmul(xo, ld_table(w + 1)));
-                }
+            // separate the two real columns packed in Z, twiddle, store rows k1 <= N1/2 of the scratch;
+            // lanes run along k1 so each store instruction writes 128-byte runs of the tile-major scratch
+            constexpr int KH = L / 2;
+            const T half = (T)0.5;
+            auto emit = [&](int k1, int cc) {
+                const cx<T> z = sm[k1 * PITCH + cc], zc = sm[((L - k1) & (L - 1)) * PITCH + cc];
+                const cx<T> xe = mk<T>((z.x + zc.x) * half, (z.y - zc.y) * half);
+                const cx<T> xo = mk<T>((z.y + zc.y) * half, (zc.x - z.x) * half);
+                const int col = 2 * (lane0 + cc);
+                const long long o0 = tm_off(k1, col, n2, ctb), o1 = tm_off(k1, col + 1, n2, ctb);
+                st_plain(gout + o0, cmul(xe, ld_table(p.tw4 + o0)));
+                st_plain(gout + o1, cmul(xo, ld_table(p.tw4 + o1)));
+            };
+            for (int e = tid; e < KH * CT; e += THREADS) {
+                const int k1 = e % KH, cc = e / KH;
+                if (lane0 + cc < width) emit(k1, cc);
             }
+            if (tid < CT && lane0 + tid < width) emit(KH, tid);
             __syncthreads();
         }
-        if constexpr (FLAVOR == TILE_B_C2R) {
-            for (int e = tid; e < CT * L; e += THREADS) {
-                const int rr = e / L, i = e - rr * L;
-                if (lane0 + rr < width) st_plain(gout + (long long)(lane0 + rr) * n2 + i, sm[i * PITCH + rr]);
-            }
-            __syncthreads();
-        }
-        if constexpr (FLAVOR == TILE_A_C2C || FLAVOR == TILE_B_C2C || FLAVOR == TILE_B_R2C || FLAVOR == TILE_A_C2R) {
-            if constexpr (NP == 1) __syncthreads();  // (multi-pass kernels end on a post-gather barrier already)
-        }
+        if constexpr (NP == 1 && FLAVOR != TILE_A_R2C) __syncthreads();
     }
 }
 
@@ -323,7 +337,8 @@ struct FourStepParams {
     const cx<T> *tw_a, *tw_b, *tw4;
     int n1, n2;
     long long batch, user_stride, scratch_per;
-    int inverse;
+    int inverse, ctb_log2;
+    int discard;  // drop consumed scratch lines from L2 (discard.global.L2)
 };
 
 __device__ __forceinline__ unsigned cluster_ctarank() {
@@ -338,6 +353,19 @@ __device__ __forceinline__ unsigned cluster_nctarank() {
 }
 __device__ __forceinline__ void cluster_barrier() {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+// Drop consumed scratch lines from L2 WITHOUT writing them back (the slot is fully rewritten before it is
+// read again), so the intermediate costs no HBM write traffic.  `first_line` .. +count lines of 128 bytes.
+template <typename T>
+__device__ __forceinline__ void discard_lines(const cx<T> *base, long long first_line, int count, int stride_lines,
+                                              int groups, int tid, int nthreads) {
+    // `groups` runs of `count` consecutive lines, run g starting at first_line + g * stride_lines
+    for (int i = tid; i < count * groups; i += nthreads) {
+        const int g = i / count, l = i - g * count;
+        const char *a = reinterpret_cast<const char *>(base) + (first_line + (long long)g * stride_lines + l) * 128;
+        asm volatile("discard.global.L2 [%0], 128;" ::"l"(a) : "memory");
+    }
 }
 
 template <typename CfgA, typename CfgB, int KIND>
@@ -356,21 +384,40 @@ fourstep_cluster_kernel(FourStepParams<typename CfgA::T> q) {
     TileParams<T> p1, p2;
     p1.in = nullptr; p1.out = nullptr; p1.tw = KIND == 2 ? q.tw_b : q.tw_a; p1.tw4 = q.tw4;
     p1.n1 = q.n1; p1.n2 = q.n2; p1.batch = 1; p1.in_stride = 0; p1.out_stride = 0; p1.inverse = q.inverse;
+    p1.ctb_log2 = q.ctb_log2;
     p2 = p1;
     p2.tw = KIND == 2 ? q.tw_a : q.tw_b;
-    const int tiles1 = (tile_width<F1>(q.n1, q.n2) + Cfg1::CT - 1) / Cfg1::CT;
-    const int tiles2 = (tile_width<F2>(q.n1, q.n2) + Cfg2::CT - 1) / Cfg2::CT;
+    constexpr int kCtbLog = CfgB::CT == 32 ? 5 : CfgB::CT == 16 ? 4 : CfgB::CT == 8 ? 3 : CfgB::CT == 4 ? 2 : -1;
+    static_assert(kCtbLog >= 0, "row-stage tile width must be 4, 8, 16 or 32");
+    constexpr int tiles1 = (tile_width<F1>(CfgA::L, CfgB::L) + Cfg1::CT - 1) / Cfg1::CT;
+    constexpr int tiles2 = (tile_width<F2>(CfgA::L, CfgB::L) + Cfg2::CT - 1) / Cfg2::CT;
     int slot = 0;
     for (long long B = cid; B < q.batch; B += nclusters, slot ^= 1) {
         cx<T> *scr = q.scratch + (cid * 2 + slot) * q.scratch_per;
         const cx<T> *uin = q.in + B * q.user_stride;
         cx<T> *uout = q.out + B * q.user_stride;
-        for (int tile = rank; tile < tiles1; tile += csize) tile_body<Cfg1, F1>(p1, uin, scr, tile * Cfg1::CT, sm);
+        for (int tile = rank; tile < tiles1; tile += csize)
+            tile_body<Cfg1, F1, CfgA::L, CfgB::L, kCtbLog>(p1, uin, scr, tile * Cfg1::CT, sm);
         cluster_barrier();  // stage-1 stores of every CTA in the cluster are visible; L1 is invalidated
         // rotate the start so the CTA that gets an extra (ragged) tile changes from transform to transform
         for (int i = rank; i < tiles2; i += csize) {
             const int tile = (int)((i + B) % tiles2);
-            tile_body<Cfg2, F2>(p2, scr, uout, tile * Cfg2::CT, sm);
+            tile_body<Cfg2, F2, CfgA::L, CfgB::L, kCtbLog>(p2, scr, uout, tile * Cfg2::CT, sm);
+            if (q.discard) {
+                // every stage-2 tile consumes a disjoint set of 128-byte scratch lines (tile-major layout)
+                constexpr int kLinesPerRow = CfgB::CT * (int)sizeof(cx<T>) / 128;  // lines per (block, n2)
+                const int tid = threadIdx.x + threadIdx.y * blockDim.x;
+                if constexpr (kLinesPerRow >= 1) {
+                    if constexpr (KIND == 2) {  // A_C2R: columns 2*lane0 .. +2*CT of every row block
+                        constexpr int blocks = (CfgA::L / 2 + CfgB::CT) / CfgB::CT;
+                        discard_lines(scr, (long long)tile * 2 * CfgA::CT * kLinesPerRow, 2 * CfgA::CT * kLinesPerRow,
+                                      CfgB::L * kLinesPerRow, blocks, tid, CfgA::THREADS);
+                    } else {  // B flavors: one contiguous block of CT rows
+                        discard_lines(scr, (long long)tile * CfgB::L * kLinesPerRow, CfgB::L * kLinesPerRow, 0, 1, tid,
+                                      CfgA::THREADS);
+                    }
+                }
+            }
         }
     }
 }
@@ -384,6 +431,7 @@ struct TileEntry {
     int prec, len;
     const char *name;
     int tw_total, np, radix[3];
+    int ct;  // lanes per tile
     int (*launch[6])(const void *params, cudaStream_t s);  // params: TileParams<T>
 };
 const std::vector<TileEntry> &tile_registry();

@@ -1,5 +1,7 @@
 // tiled_launch.cuh -- host launchers for the four-step tile kernels (tiled.cuh).
 #pragma once
+#include <cstdlib>
+
 #include "tiled.cuh"
 
 namespace ssfft {
@@ -47,6 +49,7 @@ TileEntry make_tile_entry(const char *name) {
     e.name = name;
     e.tw_total = Cfg::tw_total;
     e.np = Cfg::NP;
+    e.ct = Cfg::CT;
     for (int i = 0; i < 3; ++i) e.radix[i] = Cfg::radix(i);
     e.launch[TILE_A_C2C] = &launch_tile<Cfg, TILE_A_C2C>;
     e.launch[TILE_B_C2C] = &launch_tile<Cfg, TILE_B_C2C>;
@@ -93,10 +96,41 @@ int launch_fourstep(const void *params, int max_clusters, cudaStream_t s) {
     cfg.blockDim = dim3(CfgA::THREADS);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = s;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = csize; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
+    // Optional (SSFFT_L2_PERSIST=1): pin the scratch in L2 with a persisting access-policy window.  Measured
+    // SLOWER on B200 (65536: 48 % -> 28 % of roofline), so it is off by default; consumed scratch lines are
+    // dropped with discard.global.L2 inside the kernel instead.
+    static int persist_state = 0;  // 0 = unknown, 1 = enabled, -1 = unavailable / disabled
+    static size_t max_window = 0;
+    if (persist_state == 0) {
+        const char *e = getenv("SSFFT_L2_PERSIST");
+        int dev = 0, max_persist = 0, max_win = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev);
+        cudaDeviceGetAttribute(&max_win, cudaDevAttrMaxAccessPolicyWindowSize, dev);
+        if (!(e && e[0] == '1') || max_persist <= 0 || max_win <= 0 ||
+            cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)max_persist) != cudaSuccess) {
+            cudaGetLastError();
+            persist_state = -1;
+        } else {
+            persist_state = 1;
+            max_window = (size_t)max_win;
+        }
+    }
+    if (persist_state == 1) {
+        size_t bytes = (size_t)2 * (size_t)clusters * (size_t)q.scratch_per * sizeof(cx<T>);
+        if (bytes > max_window) bytes = max_window;
+        attr[1].id = cudaLaunchAttributeAccessPolicyWindow;
+        attr[1].val.accessPolicyWindow.base_ptr = (void *)q.scratch;
+        attr[1].val.accessPolicyWindow.num_bytes = bytes;
+        attr[1].val.accessPolicyWindow.hitRatio = 1.0f;
+        attr[1].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        attr[1].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+        cfg.numAttrs = 2;
+    }
     return cudaLaunchKernelEx(&cfg, fourstep_cluster_kernel<CfgA, CfgB, KIND>, q) == cudaSuccess ? 0 : 2;
 }
 
