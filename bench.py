@@ -68,6 +68,23 @@ def measured_peak():
         return 6650.0, "fallback (B200_PROFILING.md: 6.65 TB/s)"
 
 
+def profiled_traffic(workload):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed
+    `ncu --set full` summary of the same command (profiles/*_traffic.json, made by tools/summarize_ncu.py)."""
+    files = {"c2": "c2_fused4096_tma_r01_traffic.json"}
+    name = files.get(workload)
+    if not name:
+        return None, None
+    try:
+        with open(os.path.join(ROOT, "profiles", name)) as f:
+            data = json.load(f)
+        kernel, launches = next(iter(data.items()))
+        l0 = launches[0]
+        return l0["dram_read_bytes"] + l0["dram_write_bytes"], f"profiles/{name}"
+    except Exception:
+        return None, None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -447,6 +464,7 @@ def main():
                          f"threads, one {'FFT' if kind == 'c2c' else 'RealFFT'}<{dtype}> object per thread, plan "
                          "build excluded, best of 2"}
 
+    traffic, traffic_src = profiled_traffic(args.workload) if not args.batch else (None, None)
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": "GFLOP/s", "n_gpus": world, "steps": args.steps,
@@ -459,7 +477,7 @@ def main():
                        "l2": f"working set {2 * batch * n * (2 if kind == 'c2c' else 1) * esz / 2**20:.0f} MiB per GPU "
                              ">> 126 MB L2 (inputs larger than L2, no flush needed)"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src,
+                         "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                          "algorithmic_bytes_per_step_per_gpu": bytes_step_gpu,
                          "kernel_ms": ms_step},
             "clocks": clocks, "gpu_launches": launches,
