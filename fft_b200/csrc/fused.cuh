@@ -182,27 +182,9 @@ fused_fft_kernel(const cx<typename Cfg::T> *__restrict__ in, cx<typename Cfg::T>
             else return ld_stream(gin + idx);
         };
 
-        // ---------------- C2R prologue: pre-twiddle pairs into shared memory (RealFFT::ifft :478-492)
-        if (mode == FUSED_C2R) {
-            if (active) {
-                constexpr int H2 = N / 2 + 1;
-                for (int i = t; i < H2; i += TX) {
-                    if (i == 0) {
-                        cx<T> a = load_in(0);
-                        sm[Cfg::pad(0)] = mk<T>(a.x + a.y, a.x - a.y);
-                    } else {
-                        const int ci = N - i;
-                        cx<T> bi, bc;
-                        c2r_pair(load_in(i), load_in(ci), ld_table(rtw + i), bi, bc);
-                        sm[Cfg::pad(i)] = bi;
-                        sm[Cfg::pad(ci)] = bc;
-                    }
-                }
-            }
-            __syncthreads();
-            if constexpr (PF) prefetch(g + gridDim.x);  // staging buffer fully consumed
-        }
-
+        // C2R (RealFFT::ifft :478-492): the pre-twiddle is applied on the fly while gathering pass 0 -- the
+        // element buf[i] only needs in[i], in[N-i] and tw[min(i, N-i)], all of which this thread can fetch
+        // itself, so no shared-memory round trip is needed (see the gather below).
         sfor<0, NP>([&](auto pc) {
             constexpr int p = decltype(pc)::value;
             constexpr int R = Cfg::radix(p), P = Cfg::prod(p), MN = Cfg::mnext(p), NR = N / R, U = E / R;
@@ -210,11 +192,23 @@ fused_fft_kernel(const cx<typename Cfg::T> *__restrict__ in, cx<typename Cfg::T>
             // ---- gather inputs
             if constexpr (first) {
                 if (mode == FUSED_C2R) {
+                    if (PF || active) {
 #pragma unroll
-                    for (int u = 0; u < U; ++u)
+                        for (int u = 0; u < U; ++u)
 #pragma unroll
-                        for (int j = 0; j < R; ++j) v[u * R + j] = cswap(sm[Cfg::pad(t + TX * u + NR * j)]);
-                    __syncthreads();
+                            for (int j = 0; j < R; ++j) {
+                                const int i = t + TX * u + NR * j;
+                                const int ci = i ? N - i : 0;
+                                const bool lo = 2 * i <= N;  // i is the first (lo) or second element of its pair
+                                const cx<T> vi = load_in(i), vc = load_in(ci);
+                                const cx<T> w = ld_table(rtw + (lo ? i : ci));
+                                cx<T> bi, bc;
+                                c2r_pair(lo ? vi : vc, lo ? vc : vi, w, bi, bc);
+                                cx<T> x = lo ? bi : bc;
+                                if (i == 0) x = mk<T>(vi.x + vi.y, vi.x - vi.y);  // (DC, Nyquist) unpack  :478-481
+                                v[u * R + j] = cswap(x);
+                            }
+                    }
                 } else if (PF || active) {
                     if (inverse) {
 #pragma unroll
@@ -263,9 +257,7 @@ fused_fft_kernel(const cx<typename Cfg::T> *__restrict__ in, cx<typename Cfg::T>
                     for (int r = 0; r < R; ++r) sm[Cfg::pad(o + P * r)] = v[u * R + r];
                 }
                 __syncthreads();
-                if constexpr (PF && first) {
-                    if (mode != FUSED_C2R) prefetch(g + gridDim.x);  // every thread has consumed the staging buffer
-                }
+                if constexpr (PF && first) prefetch(g + gridDim.x);  // every thread has consumed the staging buffer
             } else {
                 // last pass: P == N/R, m' == 0, racc == b  ->  natural-order index b + P*r
                 if (mode == FUSED_R2C) {
