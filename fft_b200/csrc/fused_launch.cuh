@@ -55,6 +55,10 @@ FusedEntry make_entry(const char *name) {
 
 #define SSFFT_FUSED(T, N, R0, R1, R2, R3, TX, FPB, MINB) \
     make_entry<FusedCfg<T, N, R0, R1, R2, R3, TX, FPB, MINB>>(#T "_" #N "_" #R0 "x" #R1 "x" #R2 "x" #R3)
+// general form: PADS = shared-memory padding shift (one extra element per 2^PADS; 31 = none), PF = TMA prefetch.
+// The padding per size comes from an offline bank-conflict model of the exchange.
+#define SSFFT_FUSED_X(T, N, R0, R1, R2, R3, TX, FPB, MINB, PADS, PF) \
+    make_entry<FusedCfg<T, N, R0, R1, R2, R3, TX, FPB, MINB, PADS, PF>>(#T "_" #N "_" #R0 "x" #R1 "x" #R2 "x" #R3 "_p" #PADS "_tma" #PF)
 // same, with the TMA bulk-copy prefetch of the next transform group (cp.async.bulk + mbarrier)
 #define SSFFT_FUSED_PF(T, N, R0, R1, R2, R3, TX, FPB, MINB) \
     make_entry<FusedCfg<T, N, R0, R1, R2, R3, TX, FPB, MINB, 4, 1>>(#T "_" #N "_" #R0 "x" #R1 "x" #R2 "x" #R3 "_tma")
