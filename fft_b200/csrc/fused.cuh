@@ -37,8 +37,16 @@ struct FusedCfg {
     // (cp.async.bulk + mbarrier) while the current group is being transformed.
     static constexpr int PF = PF_;
     static constexpr int NP = (R3_ > 1) ? 4 : (R2_ > 1) ? 3 : (R1_ > 1) ? 2 : 1;
-    static constexpr int E = N / TX;
     __host__ __device__ static constexpr int radix(int i) { return i == 0 ? R0_ : i == 1 ? R1_ : i == 2 ? R2_ : R3_; }
+    // butterflies per thread in pass i (rounded up: a pass whose N/R is not a multiple of TX is "ragged",
+    // the excess threads idle behind a predicate) and the register array size a thread needs
+    __host__ __device__ static constexpr int bfly(int i) { return (N_ / radix(i) + TX_ - 1) / TX_; }
+    __host__ __device__ static constexpr int emax() {
+        int e = 0;
+        for (int i = 0; i < NP; ++i) e = bfly(i) * radix(i) > e ? bfly(i) * radix(i) : e;
+        return e;
+    }
+    static constexpr int E = emax();
     __host__ __device__ static constexpr int prod(int i) { return i == 0 ? 1 : i == 1 ? R0_ : i == 2 ? R0_ * R1_ : R0_ * R1_ * R2_; }
     __host__ __device__ static constexpr int mnext(int i) { return N / (prod(i) * radix(i)); }
     // twiddle table offset (in cx elements) of pass i: passes 0..NP-2 have (R-1)*mnext entries
@@ -56,8 +64,7 @@ struct FusedCfg {
     static_assert(!PF || ((size_t)N * FPB * sizeof(cx<T>)) % 16 == 0, "bulk copies need 16-byte multiples: use an even FPB");
     static_assert(!PF || (R1_ > 1), "prefetch variant needs at least two passes");
     static_assert(R0_ * R1_ * R2_ * R3_ == N_, "radices must multiply to N");
-    static_assert(N_ % TX_ == 0, "TX must divide N");
-    static_assert(E % R0_ == 0 && E % R1_ == 0 && E % R2_ == 0 && E % R3_ == 0, "E must be a multiple of every radix");
+    static_assert(TX_ >= 1 && TX_ <= N_, "bad thread count");
 };
 
 #ifdef __CUDACC__
@@ -187,8 +194,10 @@ fused_fft_kernel(const cx<typename Cfg::T> *__restrict__ in, cx<typename Cfg::T>
         // itself, so no shared-memory round trip is needed (see the gather below).
         sfor<0, NP>([&](auto pc) {
             constexpr int p = decltype(pc)::value;
-            constexpr int R = Cfg::radix(p), P = Cfg::prod(p), MN = Cfg::mnext(p), NR = N / R, U = E / R;
+            constexpr int R = Cfg::radix(p), P = Cfg::prod(p), MN = Cfg::mnext(p), NR = N / R, U = Cfg::bfly(p);
             constexpr bool first = (p == 0), last = (p == NP - 1);
+            constexpr bool ragged = (NR % TX) != 0;  // some threads have no butterfly in their last slot
+            auto has = [&](int u) { return !ragged || (t + TX * u) < NR; };
             // ---- gather inputs
             if constexpr (first) {
                 if (mode == FUSED_C2R) {
@@ -197,6 +206,7 @@ fused_fft_kernel(const cx<typename Cfg::T> *__restrict__ in, cx<typename Cfg::T>
                         for (int u = 0; u < U; ++u)
 #pragma unroll
                             for (int j = 0; j < R; ++j) {
+                                if (!has(u)) continue;
                                 const int i = t + TX * u + NR * j;
                                 const int ci = i ? N - i : 0;
                                 const bool lo = 2 * i <= N;  // i is the first (lo) or second element of its pair
@@ -214,24 +224,28 @@ fused_fft_kernel(const cx<typename Cfg::T> *__restrict__ in, cx<typename Cfg::T>
 #pragma unroll
                         for (int u = 0; u < U; ++u)
 #pragma unroll
-                            for (int j = 0; j < R; ++j) v[u * R + j] = cswap(load_in(t + TX * u + NR * j));
+                            for (int j = 0; j < R; ++j)
+                                if (has(u)) v[u * R + j] = cswap(load_in(t + TX * u + NR * j));
                     } else {
 #pragma unroll
                         for (int u = 0; u < U; ++u)
 #pragma unroll
-                            for (int j = 0; j < R; ++j) v[u * R + j] = load_in(t + TX * u + NR * j);
+                            for (int j = 0; j < R; ++j)
+                                if (has(u)) v[u * R + j] = load_in(t + TX * u + NR * j);
                     }
                 }
             } else {
 #pragma unroll
                 for (int u = 0; u < U; ++u)
 #pragma unroll
-                    for (int j = 0; j < R; ++j) v[u * R + j] = sm[Cfg::pad(t + TX * u + NR * j)];
+                    for (int j = 0; j < R; ++j)
+                        if (has(u)) v[u * R + j] = sm[Cfg::pad(t + TX * u + NR * j)];
                 __syncthreads();  // everyone has read: the buffer may be overwritten
             }
             // ---- butterflies + inter-pass twiddles
 #pragma unroll
             for (int u = 0; u < U; ++u) {
+                if (!has(u)) continue;
                 cx<T> w[R];
 #pragma unroll
                 for (int j = 0; j < R; ++j) w[j] = v[u * R + j];
@@ -253,8 +267,10 @@ fused_fft_kernel(const cx<typename Cfg::T> *__restrict__ in, cx<typename Cfg::T>
                     const int b = t + TX * u;
                     const int mp = b / P, racc = b - mp * P;
                     const int o = racc + P * R * mp;
+                    if (has(u)) {
 #pragma unroll
-                    for (int r = 0; r < R; ++r) sm[Cfg::pad(o + P * r)] = v[u * R + r];
+                        for (int r = 0; r < R; ++r) sm[Cfg::pad(o + P * r)] = v[u * R + r];
+                    }
                 }
                 __syncthreads();
                 if constexpr (PF && first) prefetch(g + gridDim.x);  // every thread has consumed the staging buffer
@@ -264,7 +280,8 @@ fused_fft_kernel(const cx<typename Cfg::T> *__restrict__ in, cx<typename Cfg::T>
 #pragma unroll
                     for (int u = 0; u < U; ++u)
 #pragma unroll
-                        for (int r = 0; r < R; ++r) sm[Cfg::pad(t + TX * u + P * r)] = v[u * R + r];
+                        for (int r = 0; r < R; ++r)
+                            if (has(u)) sm[Cfg::pad(t + TX * u + P * r)] = v[u * R + r];
                     __syncthreads();
                     // ---------------- R2C epilogue: post-twiddle pairs (RealFFT::fft :459-472)
                     if (active) {
@@ -288,12 +305,14 @@ fused_fft_kernel(const cx<typename Cfg::T> *__restrict__ in, cx<typename Cfg::T>
 #pragma unroll
                         for (int u = 0; u < U; ++u)
 #pragma unroll
-                            for (int r = 0; r < R; ++r) st_stream(gout + t + TX * u + P * r, cswap(v[u * R + r]));
+                            for (int r = 0; r < R; ++r)
+                                if (has(u)) st_stream(gout + t + TX * u + P * r, cswap(v[u * R + r]));
                     } else {
 #pragma unroll
                         for (int u = 0; u < U; ++u)
 #pragma unroll
-                            for (int r = 0; r < R; ++r) st_stream(gout + t + TX * u + P * r, v[u * R + r]);
+                            for (int r = 0; r < R; ++r)
+                                if (has(u)) st_stream(gout + t + TX * u + P * r, v[u * R + r]);
                     }
                 }
             }

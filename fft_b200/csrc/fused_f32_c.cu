@@ -6,6 +6,7 @@ void register_fused_f32_c(std::vector<FusedEntry> &v) {
     v.push_back(SSFFT_FUSED_X(float, 1000, 10, 10, 10, 1, 100, 2, 4, 31, 1));
     v.push_back(SSFFT_FUSED_X(float, 2187, 27, 9, 9, 1, 81, 3, 2, 31, 0));
     v.push_back(SSFFT_FUSED_X(float, 3125, 25, 25, 5, 1, 125, 1, 5, 31, 0));
+    // (a 3-pass 16 x 15 x 25 variant with ragged passes measured 43 % vs 59 % for this one)
     v.push_back(SSFFT_FUSED_X(float, 6000, 10, 10, 10, 6, 200, 1, 2, 31, 1));
 }
 }  // namespace ssfft

@@ -9,6 +9,8 @@ void register_fused_f32_b(std::vector<FusedEntry> &);
 void register_fused_f32_c(std::vector<FusedEntry> &);
 void register_fused_f64_a(std::vector<FusedEntry> &);
 void register_fused_f64_b(std::vector<FusedEntry> &);
+void register_fused_f32_d(std::vector<FusedEntry> &);
+void register_fused_f64_c(std::vector<FusedEntry> &);
 
 const std::vector<FusedEntry> &fused_registry() {
     static const std::vector<FusedEntry> reg = [] {
@@ -22,6 +24,8 @@ const std::vector<FusedEntry> &fused_registry() {
         register_fused_f32_c(v);
         register_fused_f64_a(v);
         register_fused_f64_b(v);
+        register_fused_f32_d(v);
+        register_fused_f64_c(v);
         return v;
     }();
     return reg;

@@ -21,6 +21,8 @@ SEED = 7
 REF_TEST_SIZES = [1, 2, 4, 8, 16, 32, 64, 128, 256, 3, 6, 9, 12, 18, 24, 5, 10, 15, 20, 25, 7, 14, 21, 28, 49,
                   11, 13, 17, 19, 22, 23]
 CONFIG_SIZES = [512, 1000, 1024, 2048, 2187, 3125, 4096, 6000, 8192, 16384]
+# the reference's fast sizes 2^k * {3, 9} (FFT::sizeMinimum/sizeMaximum): fused kernels with ragged passes
+FAST_SIZES = [96, 192, 384, 768, 1536, 3072, 6144, 144, 288, 576, 1152, 2304, 4608, 9216]
 LARGE_SIZES = [16384, 32768, 65536, 3 * 2 ** 15, 100000, 2 ** 17, 2 ** 18, 2 ** 19, 2 ** 20]
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_vectors.npz")
 
@@ -64,7 +66,7 @@ def test_c2c_small_sizes_vs_oracle(oracle, cuda_device, prec):
 
 
 @pytest.mark.parametrize("prec", ["float32", "float64"])
-@pytest.mark.parametrize("n", CONFIG_SIZES)
+@pytest.mark.parametrize("n", CONFIG_SIZES + FAST_SIZES)
 def test_c2c_config_sizes_vs_oracle(oracle, cuda_device, prec, n):
     npdt, _ = cdt_of(prec)
     batch = 37  # ragged against every transforms-per-block setting
@@ -149,7 +151,7 @@ def test_real_vs_oracle(oracle, cuda_device, prec, cls_name):
     _, tcdt = cdt_of(prec)
     modified = cls_name == "ModifiedRealFFT"
     cls = getattr(fft_b200, cls_name)
-    for n in list(range(2, 100, 2)) + [128, 256, 1000, 2048, 4096, 8192, 6000, 32768, 65536, 2 ** 17, 2 ** 18, 2 ** 20]:
+    for n in list(range(2, 100, 2)) + [128, 256, 1000, 2048, 4096, 8192, 6000, 192, 1536, 3072, 4608, 32768, 65536, 2 ** 17, 2 ** 18, 2 ** 20]:
         batch = 5
         x = oracle.uniform(batch * n, SEED, npdt).reshape(batch, n)
         r = cls(n, dtype=prec)
