@@ -112,13 +112,84 @@ __device__ __forceinline__ long long tm_off(int k1, int n2idx, int n2, int ctb_l
     return (long long)(k1 >> ctb_log2) * ((long long)ctb * n2) + (long long)n2idx * ctb + (k1 & (ctb - 1));
 }
 
+
+// Where the raw element `idx` of lane `lane` of a first-pass-from-global flavor lives, and what has to be done
+// to it after loading (conjugation / zeroing of the packed bin / re-im swap).  Shared by the direct gather and
+// by the cp.async prefetch into the staging buffer.
+template <int FLAVOR, int L, typename T>
+__device__ __forceinline__ const cx<T> *tile_src(const cx<T> *gin, int lane, int idx, int n1, int n2, int ctb) {
+    if constexpr (FLAVOR == TILE_A_C2C) return gin + (long long)idx * n2 + lane;
+    else if constexpr (FLAVOR == TILE_A_R2C) return gin + (long long)idx * (n2 / 2) + lane;
+    else if constexpr (FLAVOR == TILE_B_C2C || FLAVOR == TILE_B_R2C) return gin + tm_off(lane, idx, n2, ctb);
+    else {  // TILE_B_C2R: row k1 = lane, element k2 = idx of the Hermitian-extended packed spectrum
+        const int k1 = lane, k2 = idx;
+        if (k2 < L / 2) return gin + k1 + (long long)n1 * k2;
+        if (k1 == 0) return (k2 == L / 2) ? gin : gin + (long long)n1 * (L - k2);
+        return gin + (n1 - k1) + (long long)n1 * (L - 1 - k2);
+    }
+}
+template <int FLAVOR, int L, typename T>
+__device__ __forceinline__ cx<T> tile_fix(cx<T> x, int lane, int idx, int inverse) {
+    if constexpr (FLAVOR == TILE_A_C2C) return inverse ? cswap(x) : x;
+    else if constexpr (FLAVOR == TILE_B_C2R) {
+        const int k1 = lane, k2 = idx;
+        if (k2 < L / 2) {
+            if (k1 == 0 && k2 == 0) x.y = (T)0;                      // bin 0 packs (DC, Nyquist)
+        } else if (k1 == 0) {
+            x = (k2 == L / 2) ? mk<T>(x.y, (T)0) : cconj(x);
+        } else {
+            x = cconj(x);
+        }
+        return cswap(x);                                             // inverse transform via the swap trick
+    } else return x;
+}
+
+__device__ __forceinline__ void cp_async8(void *dst_smem, const void *src_gmem) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(dst_smem)),
+                 "l"(src_gmem)
+                 : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// Asynchronously copy the raw first-pass inputs of one tile into the staging buffer `st` ([idx][lane], pitch
+// CT+1): LDGSTS, no registers, completes in the background while the previous tile is being transformed.
+template <typename Cfg, int FLAVOR, int N1C = 0, int N2C = 0, int CTBLOG = -1>
+__device__ __forceinline__ void tile_prefetch(const TileParams<typename Cfg::T> &p, const cx<typename Cfg::T> *gin,
+                                              int lane0, cx<typename Cfg::T> *st) {
+    using T = typename Cfg::T;
+    static_assert(sizeof(cx<T>) == 8, "cp.async staging is implemented for fp32 tiles");
+    constexpr int L = Cfg::L, TX = Cfg::TX, CT = Cfg::CT, E = Cfg::E, PITCH = Cfg::PITCH;
+    constexpr int R = Cfg::radix(0), NR = L / R, U = E / R;
+    const int tid = threadIdx.x + threadIdx.y * blockDim.x;
+    const int c = tid % CT, t = tid / CT;
+    const int n1 = N1C ? N1C : p.n1, n2 = N2C ? N2C : p.n2, ctb = CTBLOG >= 0 ? CTBLOG : p.ctb_log2;
+    const int lane = lane0 + c;
+    if (lane < tile_width<FLAVOR>(n1, n2)) {
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+#pragma unroll
+            for (int j = 0; j < R; ++j) {
+                const int idx = t + TX * u + NR * j;
+                cp_async8(st + idx * PITCH + c, tile_src<FLAVOR, L>(gin, lane, idx, n1, n2, ctb));
+            }
+    }
+    cp_async_commit();
+}
+
 // One tile of one transform: lanes lane0 .. lane0+CT-1 of the tiled dimension.  gin/gout point at the
 // transform (user buffer or scratch, depending on the flavor).  Every thread of the CTA must call this.
 // N1C / N2C / CTBLOG: compile-time four-step dimensions (0 / -1 = take them from `p` at run time).  With them
 // fixed every global address is base + immediate, which roughly halves the instruction count of a tile.
-template <typename Cfg, int FLAVOR, int N1C = 0, int N2C = 0, int CTBLOG = -1>
+struct NoHook {
+    __device__ __forceinline__ void operator()() const {}
+};
+// STAGED: the first-pass inputs were prefetched into `st` by tile_prefetch (the caller has waited for them);
+// `hook` runs right after the first block-wide barrier, i.e. as soon as `st` may be overwritten again.
+template <typename Cfg, int FLAVOR, int N1C = 0, int N2C = 0, int CTBLOG = -1, bool STAGED = false, typename Hook = NoHook>
 __device__ __forceinline__ void tile_body(const TileParams<typename Cfg::T> &p, const cx<typename Cfg::T> *gin,
-                                          cx<typename Cfg::T> *gout, int lane0, cx<typename Cfg::T> *sm) {
+                                          cx<typename Cfg::T> *gout, int lane0, cx<typename Cfg::T> *sm,
+                                          const cx<typename Cfg::T> *st = nullptr, Hook hook = Hook()) {
     using T = typename Cfg::T;
     constexpr int L = Cfg::L, TX = Cfg::TX, CT = Cfg::CT, E = Cfg::E, NP = Cfg::NP, PITCH = Cfg::PITCH;
     constexpr int THREADS = Cfg::THREADS;
@@ -175,30 +246,14 @@ __device__ __forceinline__ void tile_body(const TileParams<typename Cfg::T> &p, 
                         for (int j = 0; j < R; ++j) {
                             const int idx = t + TX * u + NR * j;
                             cx<T> x;
-                            if constexpr (FLAVOR == TILE_A_C2C) {
-                                x = ld_stream(gin + (long long)idx * n2 + lane);
-                                if (p.inverse) x = cswap(x);
-                            } else if constexpr (FLAVOR == TILE_A_R2C) {
-                                x = ld_stream(gin + (long long)idx * (n2 / 2) + lane);
-                            } else if constexpr (FLAVOR == TILE_B_C2C || FLAVOR == TILE_B_R2C) {
-                                x = ld_l2(gin + tm_off(lane, idx, n2, ctb));  // row k1 = lane, element n2 = idx
-                            } else {  // TILE_B_C2R: row k1 = lane, element k2 = idx, Hermitian-extended packed spectrum
-                                const int k1 = lane, k2 = idx;
-                                if (k2 < L / 2) {
-                                    x = ld_stream(gin + k1 + (long long)n1 * k2);
-                                    if (k1 == 0 && k2 == 0) x.y = (T)0;  // bin 0 packs (DC, Nyquist)
-                                } else if (k1 == 0) {
-                                    if (k2 == L / 2) {
-                                        x = ld_stream(gin);
-                                        x = mk<T>(x.y, (T)0);
-                                    } else {
-                                        x = cconj(ld_stream(gin + (long long)n1 * (L - k2)));
-                                    }
-                                } else {
-                                    x = cconj(ld_stream(gin + (n1 - k1) + (long long)n1 * (L - 1 - k2)));
-                                }
-                                x = cswap(x);  // inverse transform via the swap trick
+                            if constexpr (STAGED) {
+                                x = st[idx * PITCH + c];
+                            } else {
+                                const cx<T> *src = tile_src<FLAVOR, L>(gin, lane, idx, n1, n2, ctb);
+                                if constexpr (FLAVOR == TILE_B_C2C || FLAVOR == TILE_B_R2C) x = ld_l2(src);
+                                else x = ld_stream(src);
                             }
+                            x = tile_fix<FLAVOR, L>(x, lane, idx, p.inverse);
                             v[u * R + j] = x;
                         }
                 }
@@ -237,6 +292,7 @@ __device__ __forceinline__ void tile_body(const TileParams<typename Cfg::T> &p, 
                     for (int r = 0; r < R; ++r) sm[(o + P * r) * PITCH + cc] = v[u * R + r];
                 }
                 __syncthreads();
+                if constexpr (first) hook();  // every thread has consumed the staging buffer
             } else if constexpr (kLastToSmem) {
 #pragma unroll
                 for (int u = 0; u < U; ++u)
@@ -368,6 +424,24 @@ __device__ __forceinline__ void discard_lines(const cx<T> *base, long long first
     }
 }
 
+// two tile buffers (exchange + cp.async staging) per CTA, if that still fits the CTAs/SM of the launch bounds.
+// MEASURED SLOWER on B200 (65536 C2C: 50 % -> 36 % of roofline; real 65536: 34 % -> 28 %): the 8-byte LDGSTS
+// copies and the extra wait + barrier per tile cost more than the latency they hide at 3 CTAs/SM.  Kept behind
+// -DSSFFT_FOURSTEP_STAGED=1 for future work (a TMA bulk copy of the contiguous stage-2 block is the next try).
+#ifndef SSFFT_FOURSTEP_STAGED
+#define SSFFT_FOURSTEP_STAGED 0
+#endif
+template <typename CfgA, typename CfgB>
+__host__ __device__ constexpr bool fourstep_staged() {
+    return SSFFT_FOURSTEP_STAGED && sizeof(typename CfgA::T) == 4 &&
+           2 * (CfgA::smem_bytes > CfgB::smem_bytes ? CfgA::smem_bytes : CfgB::smem_bytes) *
+                   (size_t)(CfgA::MINB < CfgB::MINB ? CfgA::MINB : CfgB::MINB) <= 220 * 1024;
+}
+template <typename CfgA, typename CfgB>
+__host__ __device__ constexpr size_t fourstep_smem_bytes() {
+    return (CfgA::smem_bytes > CfgB::smem_bytes ? CfgA::smem_bytes : CfgB::smem_bytes) * (fourstep_staged<CfgA, CfgB>() ? 2 : 1);
+}
+
 template <typename CfgA, typename CfgB, int KIND>
 __global__ void __launch_bounds__(CfgA::THREADS, (CfgA::MINB < CfgB::MINB ? CfgA::MINB : CfgB::MINB))
 fourstep_cluster_kernel(FourStepParams<typename CfgA::T> q) {
@@ -391,18 +465,71 @@ fourstep_cluster_kernel(FourStepParams<typename CfgA::T> q) {
     static_assert(kCtbLog >= 0, "row-stage tile width must be 4, 8, 16 or 32");
     constexpr int tiles1 = (tile_width<F1>(CfgA::L, CfgB::L) + Cfg1::CT - 1) / Cfg1::CT;
     constexpr int tiles2 = (tile_width<F2>(CfgA::L, CfgB::L) + Cfg2::CT - 1) / Cfg2::CT;
+    // cp.async double buffering: the next tile's inputs stream into `st` while the current tile is transformed.
+    // Enabled when two tile buffers per CTA still leave room for the CTAs/SM the launch bounds ask for.
+    constexpr size_t kTileBytes = CfgA::smem_bytes > CfgB::smem_bytes ? CfgA::smem_bytes : CfgB::smem_bytes;
+    constexpr bool kStage = fourstep_staged<CfgA, CfgB>();
+    constexpr bool kStage2 = kStage && (F2 != TILE_A_C2R);  // A_C2R builds its input in shared memory itself
+    cx<T> *st = reinterpret_cast<cx<T> *>(ssfft_smem + kTileBytes);
+    bool s1_ready = false;  // the first stage-1 tile of the coming transform is already in flight
     int slot = 0;
     for (long long B = cid; B < q.batch; B += nclusters, slot ^= 1) {
         cx<T> *scr = q.scratch + (cid * 2 + slot) * q.scratch_per;
         const cx<T> *uin = q.in + B * q.user_stride;
         cx<T> *uout = q.out + B * q.user_stride;
-        for (int tile = rank; tile < tiles1; tile += csize)
-            tile_body<Cfg1, F1, CfgA::L, CfgB::L, kCtbLog>(p1, uin, scr, tile * Cfg1::CT, sm);
+        const long long Bn = B + nclusters;
+        const cx<T> *uin_next = q.in + Bn * q.user_stride;
+        auto prefetch_next_s1 = [&]() {
+            if constexpr (kStage) {
+                if (Bn < q.batch && rank < tiles1) {
+                    tile_prefetch<Cfg1, F1, CfgA::L, CfgB::L, kCtbLog>(p1, uin_next, rank * Cfg1::CT, st);
+                    s1_ready = true;
+                }
+            }
+        };
+        // ---- stage 1
+        for (int tile = rank; tile < tiles1; tile += csize) {
+            if constexpr (kStage) {
+                if (!s1_ready) tile_prefetch<Cfg1, F1, CfgA::L, CfgB::L, kCtbLog>(p1, uin, tile * Cfg1::CT, st);
+                s1_ready = false;
+                cp_async_wait_all();
+                __syncthreads();
+            }
+            const int next = tile + csize;
+            auto hook = [&]() {
+                if constexpr (kStage) {
+                    if (next < tiles1) {
+                        tile_prefetch<Cfg1, F1, CfgA::L, CfgB::L, kCtbLog>(p1, uin, next * Cfg1::CT, st);
+                        s1_ready = true;
+                    }
+                }
+            };
+            tile_body<Cfg1, F1, CfgA::L, CfgB::L, kCtbLog, kStage>(p1, uin, scr, tile * Cfg1::CT, sm, st, hook);
+        }
         cluster_barrier();  // stage-1 stores of every CTA in the cluster are visible; L1 is invalidated
-        // rotate the start so the CTA that gets an extra (ragged) tile changes from transform to transform
+        // ---- stage 2 (start rotates so the CTA that gets an extra, ragged tile changes between transforms)
+        bool s2_ready = false;
+        if constexpr (kStage && !kStage2) prefetch_next_s1();  // stage 2 does not use `st`: overlap all of it
         for (int i = rank; i < tiles2; i += csize) {
             const int tile = (int)((i + B) % tiles2);
-            tile_body<Cfg2, F2, CfgA::L, CfgB::L, kCtbLog>(p2, scr, uout, tile * Cfg2::CT, sm);
+            if constexpr (kStage2) {
+                if (!s2_ready) tile_prefetch<Cfg2, F2, CfgA::L, CfgB::L, kCtbLog>(p2, scr, tile * Cfg2::CT, st);
+                s2_ready = false;
+                cp_async_wait_all();
+                __syncthreads();
+            }
+            const int inext = i + csize;
+            auto hook = [&]() {
+                if constexpr (kStage2) {
+                    if (inext < tiles2) {
+                        tile_prefetch<Cfg2, F2, CfgA::L, CfgB::L, kCtbLog>(p2, scr, (int)((inext + B) % tiles2) * Cfg2::CT, st);
+                        s2_ready = true;
+                    } else {
+                        prefetch_next_s1();
+                    }
+                }
+            };
+            tile_body<Cfg2, F2, CfgA::L, CfgB::L, kCtbLog, kStage2>(p2, scr, uout, tile * Cfg2::CT, sm, st, hook);
             if (q.discard) {
                 // every stage-2 tile consumes a disjoint set of 128-byte scratch lines (tile-major layout)
                 constexpr int kLinesPerRow = CfgB::CT * (int)sizeof(cx<T>) / 128;  // lines per (block, n2)
@@ -420,6 +547,7 @@ fourstep_cluster_kernel(FourStepParams<typename CfgA::T> q) {
             }
         }
     }
+    if constexpr (kStage) cp_async_wait_all();
 }
 
 #endif  // __CUDACC__

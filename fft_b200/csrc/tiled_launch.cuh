@@ -62,7 +62,7 @@ TileEntry make_tile_entry(const char *name) {
 
 template <typename CfgA, typename CfgB, int KIND>
 int fourstep_max_clusters(int cluster_size) {
-    constexpr size_t smem = CfgA::smem_bytes > CfgB::smem_bytes ? CfgA::smem_bytes : CfgB::smem_bytes;
+    constexpr size_t smem = fourstep_smem_bytes<CfgA, CfgB>();
     auto kern = fourstep_cluster_kernel<CfgA, CfgB, KIND>;
     if (smem > 48 * 1024 &&
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
@@ -87,7 +87,7 @@ template <typename CfgA, typename CfgB, int KIND>
 int launch_fourstep(const void *params, int max_clusters, cudaStream_t s) {
     using T = typename CfgA::T;
     const FourStepParams<T> &q = *reinterpret_cast<const FourStepParams<T> *>(params);
-    constexpr size_t smem = CfgA::smem_bytes > CfgB::smem_bytes ? CfgA::smem_bytes : CfgB::smem_bytes;
+    constexpr size_t smem = fourstep_smem_bytes<CfgA, CfgB>();
     const int csize = fourstep_cluster_size();
     long long clusters = q.batch < max_clusters ? q.batch : max_clusters;
     if (clusters <= 0) return 0;
@@ -140,7 +140,7 @@ FourStepEntry make_fourstep_entry(const char *name) {
     e.prec = sizeof(typename CfgA::T) == 4 ? 0 : 1;
     e.n1 = CfgA::L; e.n2 = CfgB::L; e.name = name;
     e.threads = CfgA::THREADS;
-    e.smem_bytes = CfgA::smem_bytes > CfgB::smem_bytes ? CfgA::smem_bytes : CfgB::smem_bytes;
+    e.smem_bytes = fourstep_smem_bytes<CfgA, CfgB>();
     e.launch[0] = &launch_fourstep<CfgA, CfgB, 0>;
     e.launch[1] = &launch_fourstep<CfgA, CfgB, 1>;
     e.launch[2] = &launch_fourstep<CfgA, CfgB, 2>;
