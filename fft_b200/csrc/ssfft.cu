@@ -166,7 +166,9 @@ int setup_tiled(ssfft_plan *pl, size_t total, bool real, bool *ok) {
     if (total == 0 || (total & (total - 1))) return SSFFT_OK;  // power-of-two only
     int lg = 0;
     while (((size_t)1 << lg) < total) ++lg;
-    const int min_lg = real ? env_int("SSFFT_TILE_MIN_LOG2_REAL", 16) : env_int("SSFFT_TILE_MIN_LOG2", 15);
+    // below these sizes a fused single-pass kernel exists and is faster (fp32: up to 16384, fp64: up to 4096)
+    const bool f64 = sizeof(T) == 8;
+    const int min_lg = real ? env_int("SSFFT_TILE_MIN_LOG2_REAL", f64 ? 14 : 16) : env_int("SSFFT_TILE_MIN_LOG2", f64 ? 13 : 15);
     if (lg < min_lg) return SSFFT_OK;
     size_t n1 = (size_t)1 << (lg / 2), n2 = total / n1;
     int ia = find_tile<T>(n1), ib = find_tile<T>(n2);
@@ -347,9 +349,11 @@ int build_plan_typed(ssfft_plan *pl) {
         }
         std::string rs;
         for (int r : pl->direct.radix) { rs += (rs.empty() ? "" : "x"); rs += std::to_string(r); }
-        snprintf(buf, sizeof(buf), "n=%zu single-pass %s radices=%s tx=%d fpb=%d smem=%zu", n,
-                 pl->fused.id >= 0 ? fused_name(pl->fused.id) : "generic", rs.c_str(), pl->direct.tx, pl->direct.fpb,
-                 pl->direct.smem_bytes);
+        if (pl->fused.id >= 0)
+            snprintf(buf, sizeof(buf), "n=%zu single-pass fused kernel %s", n, fused_name(pl->fused.id));
+        else
+            snprintf(buf, sizeof(buf), "n=%zu single-pass generic radices=%s tx=%d fpb=%d smem=%zu", n, rs.c_str(),
+                     pl->direct.tx, pl->direct.fpb, pl->direct.smem_bytes);
         pl->desc = buf;
     } else {
         size_t n1 = 0, n2 = 0;
