@@ -210,8 +210,12 @@ def run_dist(args, n, rank, world, dev, dist):
             dist.barrier()
         torch.cuda.synchronize()
 
+    exchange = "all_to_all_single over NCCL"
     if world == 1:
         plan._all_to_all = lambda send, recv: recv.copy_(send.reshape(-1))  # P = 1: the exchange is the identity
+    elif not args.nccl_exchange:
+        plan.enable_peer_exchange(dev)
+        exchange = "fused transpose + direct peer stores over NVLink (CUDA IPC), no NCCL on the data path"
     for _ in range(args.warmup):
         plan.fft(x, y)
     barrier()
@@ -235,6 +239,12 @@ def run_dist(args, n, rank, world, dev, dist):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_total = float(t.item())
     ms_step = ms_total / args.steps
+    # per-phase breakdown (outside the timed region): two extra calls with CUDA events between the phases
+    plan.profile = {}
+    for _ in range(2):
+        plan.fft(x, y)
+    phases = {k: round(v / plan.profile["calls"], 3) for k, v in plan.profile.items() if k != "calls"}
+    plan.profile = None
     flops = 5.0 * n * math.log2(n)
     peak, peak_src = measured_peak()
     alg_bytes_gpu = 2 * per * 8
@@ -280,7 +290,8 @@ def run_dist(args, n, rank, world, dev, dist):
             "data": f"synthetic uniform[-0.5,0.5), counter-based generator, seed {SEED}",
             "config": {"workload": f"{args.workload}: one c2c float32 transform of N={n} = {plan.n1} x {plan.n2}, "
                                    f"block-sharded over {world} GPUs, natural order in and out",
-                       "parallelism": f"four-step, 3 all-to-all exchanges (all_to_all_single over NCCL) x{world}"},
+                       "parallelism": f"four-step x{world}, 3 exchanges: {exchange}",
+                       "phase_ms_rank0": phases},
             "roofline": {"bound": "hbm", "achieved": alg_bytes_gpu / (ms_step * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                          "frac": alg_bytes_gpu / (ms_step * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
                          "nvlink_bytes_per_gpu_per_step": exch_bytes_gpu,
@@ -306,6 +317,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--verify", action="store_true", help="c5: tone / Parseval / round-trip checks at full size")
+    ap.add_argument("--nccl-exchange", action="store_true", help="c5: use NCCL all_to_all instead of fused peer stores")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

@@ -75,6 +75,11 @@ def load():
         "ssfft_fill_uniform": (i32, [vp, sz, i32, u64, u64, vp]),
         "ssfft_transpose_twiddle": (i32, [vp, vp, sz, sz, sz, sz, u64, i32, i32, vp]),
         "ssfft_permute102": (i32, [vp, vp, sz, sz, sz, i32, vp]),
+        "ssfft_ipc_export": (i32, [vp, vp]),
+        "ssfft_ipc_import": (i32, [vp, c.POINTER(vp)]),
+        "ssfft_ipc_close": (i32, [vp]),
+        "ssfft_exchange_transpose": (i32, [vp, c.POINTER(vp), i32, sz, sz, sz, sz, sz, u64, i32, i32, vp]),
+        "ssfft_memcpy_d2d": (i32, [vp, vp, sz, vp]),
         "ssfft_error_string": (c.c_char_p, [i32]),
         "ssfft_last_cuda_error": (c.c_char_p, []),
         "ssfft_launch_count": (u64, []),

@@ -106,33 +106,99 @@ __global__ void rotate_kernel(cx<T> *__restrict__ dst, const cx<T> *__restrict__
 // out[b][c][r] = in[b][r][c] * W_N^((row0 + r) * c)^(+-1)   (twiddle optional: n_total == 0 -> plain transpose)
 // 32x32 tiles through shared memory, both sides coalesced.  The twiddle phase is evaluated in double
 // (sincospi) from the exact integer (row*col) mod N, so it is correct for N up to 2^40 in both precisions.
+// Each CTA walks kRowTiles consecutive 32x32 tiles down the rows.  A thread always sees the same column c and rows
+// that advance by 8, so its twiddle is W^((row0+r) c) with r stepping by 8: one exact sincospi for the start, one
+// for the step W^(8c), then a rotation recurrence in DOUBLE (<= 4*kRowTiles steps, error ~1e-15) -- 16x fewer
+// sincospi calls than one per element (measured: 7.6 ms -> plain-transpose speed for 4 GiB).
+constexpr int kRowTiles = 8;
 template <typename T>
 __global__ void transpose_twiddle_kernel(const cx<T> *__restrict__ in, cx<T> *__restrict__ out, long long rows,
                                          long long cols, long long row0, unsigned long long n_total, int conj_tw) {
     __shared__ cx<T> tile[32][33];
     const long long b = blockIdx.z;
-    const long long r0 = (long long)blockIdx.y * 32, c0 = (long long)blockIdx.x * 32;
+    const long long rbase = (long long)blockIdx.y * 32 * kRowTiles, c0 = (long long)blockIdx.x * 32;
     const cx<T> *src = in + b * rows * cols;
     cx<T> *dst = out + b * rows * cols;
-    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
-        const long long r = r0 + i, c = c0 + threadIdx.x;
-        if (r < rows && c < cols) {
-            cx<T> v = src[r * cols + c];
-            if (n_total) {
-                const unsigned long long q =
-                    (unsigned long long)(((unsigned __int128)(unsigned long long)(row0 + r) * (unsigned long long)c) % n_total);
-                double sn, cs;
-                sincospi(-2.0 * (double)q / (double)n_total, &sn, &cs);
-                const cx<T> w = mk<T>((T)cs, (T)(conj_tw ? -sn : sn));
-                v = cmul(v, w);
-            }
-            tile[i][threadIdx.x] = v;
-        }
+    const long long c = c0 + threadIdx.x;
+    double wr = 1.0, wi = 0.0, sr = 1.0, si = 0.0;  // current twiddle and the per-8-rows step
+    if (n_total && c < cols) {
+        const unsigned long long q0 = (unsigned long long)(((unsigned __int128)(unsigned long long)(row0 + rbase + threadIdx.y) *
+                                                            (unsigned long long)c) % n_total);
+        const unsigned long long qs = (unsigned long long)(((unsigned __int128)8ull * (unsigned long long)c) % n_total);
+        sincospi(-2.0 * (double)q0 / (double)n_total, &wi, &wr);
+        sincospi(-2.0 * (double)qs / (double)n_total, &si, &sr);
+        if (conj_tw) { wi = -wi; si = -si; }
     }
-    __syncthreads();
-    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
-        const long long c = c0 + i, r = r0 + threadIdx.x;
-        if (r < rows && c < cols) dst[c * rows + r] = tile[threadIdx.x][i];
+    for (int rt = 0; rt < kRowTiles; ++rt) {
+        const long long r0 = rbase + 32 * rt;
+        if (r0 >= rows) break;
+        for (int i = threadIdx.y; i < 32; i += 8) {
+            const long long r = r0 + i;
+            if (r < rows && c < cols) {
+                cx<T> v = src[r * cols + c];
+                if (n_total) v = cmul(v, mk<T>((T)wr, (T)wi));
+                tile[i][threadIdx.x] = v;
+            }
+            const double nr = wr * sr - wi * si, ni = wr * si + wi * sr;  // advance 8 rows
+            wr = nr; wi = ni;
+        }
+        __syncthreads();
+        for (int i = threadIdx.y; i < 32; i += 8) {
+            const long long cc = c0 + i, r = r0 + threadIdx.x;
+            if (r < rows && cc < cols) dst[cc * rows + r] = tile[threadIdx.x][i];
+        }
+        __syncthreads();
+    }
+}
+
+// ---- fused exchange of the distributed four-step: transpose (+ twiddle) + all-to-all + placement in ONE kernel.
+// The local matrix src[rows][cols] is split into `world` column blocks of `blk` columns; block j goes, transposed,
+// straight into rank j's HBM over NVLink (peer pointers from CUDA IPC) at dst_j[cl * dst_pitch + dst_col0 + r]:
+// exactly where the next local FFT wants it, so no pack, no NCCL staging and no unpack pass exist.
+// Stores to a peer are 256-byte runs (32 consecutive r); the twiddle uses the same double recurrence as above.
+constexpr int kMaxPeers = 16;
+template <typename T>
+struct PeerPtrs {
+    cx<T> *p[kMaxPeers];
+};
+template <typename T>
+__global__ void exchange_transpose_kernel(const cx<T> *__restrict__ src, PeerPtrs<T> dst, long long rows, long long cols,
+                                          long long blk, long long dst_pitch, long long dst_col0, long long row0,
+                                          unsigned long long n_total, int conj_tw) {
+    __shared__ cx<T> tile[32][33];
+    const long long rbase = (long long)blockIdx.y * 32 * kRowTiles, c0 = (long long)blockIdx.x * 32;
+    const long long c = c0 + threadIdx.x;
+    double wr = 1.0, wi = 0.0, sr = 1.0, si = 0.0;
+    if (n_total && c < cols) {
+        const unsigned long long q0 = (unsigned long long)(((unsigned __int128)(unsigned long long)(row0 + rbase + threadIdx.y) *
+                                                            (unsigned long long)c) % n_total);
+        const unsigned long long qs = (unsigned long long)(((unsigned __int128)8ull * (unsigned long long)c) % n_total);
+        sincospi(-2.0 * (double)q0 / (double)n_total, &wi, &wr);
+        sincospi(-2.0 * (double)qs / (double)n_total, &si, &sr);
+        if (conj_tw) { wi = -wi; si = -si; }
+    }
+    for (int rt = 0; rt < kRowTiles; ++rt) {
+        const long long r0 = rbase + 32 * rt;
+        if (r0 >= rows) break;
+        for (int i = threadIdx.y; i < 32; i += 8) {
+            const long long r = r0 + i;
+            if (r < rows && c < cols) {
+                cx<T> v = src[r * cols + c];
+                if (n_total) v = cmul(v, mk<T>((T)wr, (T)wi));
+                tile[i][threadIdx.x] = v;
+            }
+            const double nr = wr * sr - wi * si, ni = wr * si + wi * sr;
+            wr = nr; wi = ni;
+        }
+        __syncthreads();
+        for (int i = threadIdx.y; i < 32; i += 8) {
+            const long long cc = c0 + i, r = r0 + threadIdx.x;
+            if (r < rows && cc < cols) {
+                const long long j = cc / blk, cl = cc - j * blk;
+                dst.p[j][cl * dst_pitch + dst_col0 + r] = tile[threadIdx.x][i];  // peer (or own) HBM
+            }
+        }
+        __syncthreads();
     }
 }
 
@@ -140,12 +206,21 @@ __global__ void transpose_twiddle_kernel(const cx<T> *__restrict__ in, cx<T> *__
 template <typename T>
 __global__ void permute102_kernel(const cx<T> *__restrict__ in, cx<T> *__restrict__ out, long long A, long long B,
                                   long long run) {
-    const long long total = A * B * run;
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
-        const long long c = i % run, ab = i / run;
-        const long long a = ab % A, b = ab / A;  // i enumerates the OUTPUT [b][a][c]
-        out[i] = in[(a * B + b) * run + c];
+    // one (a, b) run per blockIdx.y slot, 16-byte copies along the run when it is aligned
+    const long long pairs = A * B;
+    for (long long ab = blockIdx.y; ab < pairs; ab += gridDim.y) {
+        const long long a = ab % A, b = ab / A;  // enumerate the OUTPUT order [b][a]
+        const cx<T> *s = in + (a * B + b) * run;
+        cx<T> *d = out + ab * run;
+        if (sizeof(cx<T>) == 8 && (run % 2 == 0)) {
+            const float4 *s4 = reinterpret_cast<const float4 *>(s);
+            float4 *d4 = reinterpret_cast<float4 *>(d);
+            for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < run / 2; i += (long long)gridDim.x * blockDim.x)
+                d4[i] = s4[i];
+        } else {
+            for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < run; i += (long long)gridDim.x * blockDim.x)
+                d[i] = s[i];
+        }
     }
 }
 

@@ -653,8 +653,9 @@ int ssfft_transpose_twiddle(const void *d_in, void *d_out, size_t batch, size_t 
                             uint64_t n_total, int inverse, int precision, void *stream) {
     if (!batch || !rows || !cols) return SSFFT_OK;
     if (!d_in || !d_out || d_in == d_out) return SSFFT_ERR_INVALID;
-    if (batch > 65535 || (rows + 31) / 32 > 65535) return SSFFT_ERR_INVALID;
-    dim3 grid((unsigned)((cols + 31) / 32), (unsigned)((rows + 31) / 32), (unsigned)batch), block(32, 8);
+    const size_t row_blocks = (rows + 32 * kRowTiles - 1) / (32 * kRowTiles);
+    if (batch > 65535 || row_blocks > 65535) return SSFFT_ERR_INVALID;
+    dim3 grid((unsigned)((cols + 31) / 32), (unsigned)row_blocks, (unsigned)batch), block(32, 8);
     if (precision == SSFFT_F32)
         transpose_twiddle_kernel<float><<<grid, block, 0, (cudaStream_t)stream>>>(
             (const cx<float> *)d_in, (cx<float> *)d_out, (long long)rows, (long long)cols, (long long)row0, n_total, inverse);
@@ -671,16 +672,72 @@ int ssfft_transpose_twiddle(const void *d_in, void *d_out, size_t batch, size_t 
 int ssfft_permute102(const void *d_in, void *d_out, size_t A, size_t B, size_t run, int precision, void *stream) {
     if (!A || !B || !run) return SSFFT_OK;
     if (!d_in || !d_out || d_in == d_out) return SSFFT_ERR_INVALID;
-    const size_t total = A * B * run;
-    unsigned blocks = (unsigned)((total + 255) / 256 > 148 * 16 ? 148 * 16 : (total + 255) / 256);
+    // grid.x covers one run (256 threads x 16 B), grid.y strides over the A*B runs
+    const size_t per_run_blocks = (run / 2 + 255) / 256 ? (run / 2 + 255) / 256 : 1;
+    unsigned gx = (unsigned)(per_run_blocks > 64 ? 64 : per_run_blocks);
+    size_t gy = A * B;
+    if (gy > 65535) gy = 65535;
+    dim3 grid(gx, (unsigned)gy);
     if (precision == SSFFT_F32)
-        permute102_kernel<float><<<blocks, 256, 0, (cudaStream_t)stream>>>((const cx<float> *)d_in, (cx<float> *)d_out,
-                                                                            (long long)A, (long long)B, (long long)run);
+        permute102_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const cx<float> *)d_in, (cx<float> *)d_out,
+                                                                          (long long)A, (long long)B, (long long)run);
     else if (precision == SSFFT_F64)
-        permute102_kernel<double><<<blocks, 256, 0, (cudaStream_t)stream>>>((const cx<double> *)d_in, (cx<double> *)d_out,
-                                                                             (long long)A, (long long)B, (long long)run);
+        permute102_kernel<double><<<grid, 256, 0, (cudaStream_t)stream>>>((const cx<double> *)d_in, (cx<double> *)d_out,
+                                                                           (long long)A, (long long)B, (long long)run);
     else
         return SSFFT_ERR_INVALID;
+    ++g_launches;
+    CU(cudaGetLastError());
+    return SSFFT_OK;
+}
+
+int ssfft_ipc_export(void *d_ptr, void *handle64) {
+    if (!d_ptr || !handle64) return SSFFT_ERR_INVALID;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    CU(cudaIpcGetMemHandle(reinterpret_cast<cudaIpcMemHandle_t *>(handle64), d_ptr));
+    return SSFFT_OK;
+}
+int ssfft_ipc_import(const void *handle64, void **d_ptr) {
+    if (!d_ptr || !handle64) return SSFFT_ERR_INVALID;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, sizeof(h));
+    CU(cudaIpcOpenMemHandle(d_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return SSFFT_OK;
+}
+int ssfft_ipc_close(void *d_ptr) {
+    if (d_ptr) CU(cudaIpcCloseMemHandle(d_ptr));
+    return SSFFT_OK;
+}
+int ssfft_memcpy_d2d(void *d_dst, const void *d_src, size_t bytes, void *stream) {
+    if (!bytes) return SSFFT_OK;
+    CU(cudaMemcpyAsync(d_dst, d_src, bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return SSFFT_OK;
+}
+
+int ssfft_exchange_transpose(const void *d_src, void *const *d_dst_ptrs, int world, size_t rows, size_t cols,
+                             size_t dst_pitch, size_t dst_col0, size_t row0, uint64_t n_total, int inverse, int precision,
+                             void *stream) {
+    if (!rows || !cols) return SSFFT_OK;
+    if (!d_src || !d_dst_ptrs || world < 1 || world > kMaxPeers || cols % (size_t)world) return SSFFT_ERR_INVALID;
+    const size_t row_blocks = (rows + 32 * kRowTiles - 1) / (32 * kRowTiles);
+    if (row_blocks > 65535) return SSFFT_ERR_INVALID;
+    dim3 grid((unsigned)((cols + 31) / 32), (unsigned)row_blocks), block(32, 8);
+    const long long blk = (long long)(cols / (size_t)world);
+    if (precision == SSFFT_F32) {
+        PeerPtrs<float> pp;
+        for (int i = 0; i < kMaxPeers; ++i) pp.p[i] = i < world ? (cx<float> *)d_dst_ptrs[i] : nullptr;
+        exchange_transpose_kernel<float><<<grid, block, 0, (cudaStream_t)stream>>>(
+            (const cx<float> *)d_src, pp, (long long)rows, (long long)cols, blk, (long long)dst_pitch, (long long)dst_col0,
+            (long long)row0, n_total, inverse);
+    } else if (precision == SSFFT_F64) {
+        PeerPtrs<double> pp;
+        for (int i = 0; i < kMaxPeers; ++i) pp.p[i] = i < world ? (cx<double> *)d_dst_ptrs[i] : nullptr;
+        exchange_transpose_kernel<double><<<grid, block, 0, (cudaStream_t)stream>>>(
+            (const cx<double> *)d_src, pp, (long long)rows, (long long)cols, blk, (long long)dst_pitch, (long long)dst_col0,
+            (long long)row0, n_total, inverse);
+    } else {
+        return SSFFT_ERR_INVALID;
+    }
     ++g_launches;
     CU(cudaGetLastError());
     return SSFFT_OK;

@@ -89,6 +89,56 @@ class CudaOps:
         return out.view(b, a, run)
 
 
+class PeerBuffers:
+    """Two exchange buffers per rank, mapped into every other rank with CUDA IPC so kernels can store straight
+    into a peer's HBM over NVLink (one process per GPU).  No CPU fallback; needs world > 1 real CUDA ranks."""
+
+    def __init__(self, elems: int, dtype, rank: int, world: int, group=None, device=None):
+        import torch.distributed as dist
+
+        self.lib = L.load()
+        self.rank, self.world, self.group = rank, world, group
+        self.bytes = elems * (8 if dtype == torch.complex64 else 16)
+        self.local = []     # my two buffers (device pointers)
+        self.tables = []    # per buffer: ctypes array of `world` device pointers (index = rank)
+        self._imported = []
+        self._flag = torch.zeros(1, dtype=torch.float32, device=device)
+        for _ in range(2):
+            ptr = ctypes.c_void_p()
+            L.check(self.lib.ssfft_malloc(ctypes.byref(ptr), self.bytes), "ssfft_malloc")
+            handle = ctypes.create_string_buffer(64)
+            L.check(self.lib.ssfft_ipc_export(ptr, handle), "ssfft_ipc_export")
+            mine = torch.frombuffer(bytearray(handle.raw), dtype=torch.uint8).to(device)
+            gathered = [torch.empty_like(mine) for _ in range(world)]
+            dist.all_gather(gathered, mine, group=group)
+            table = (ctypes.c_void_p * world)()
+            for r in range(world):
+                if r == rank:
+                    table[r] = ptr.value
+                else:
+                    peer = ctypes.c_void_p()
+                    raw = bytes(gathered[r].cpu().numpy().tobytes())
+                    L.check(self.lib.ssfft_ipc_import(raw, ctypes.byref(peer)), f"ssfft_ipc_import(rank {r})")
+                    table[r] = peer.value
+                    self._imported.append(peer)
+            self.local.append(ptr)
+            self.tables.append(table)
+        self.barrier()
+
+    def barrier(self):
+        """Stream-ordered barrier: every rank's preceding kernels (incl. its peer stores) are complete after it."""
+        import torch.distributed as dist
+
+        dist.all_reduce(self._flag, group=self.group)
+
+    def close(self):
+        for p in self._imported:
+            self.lib.ssfft_ipc_close(p)
+        for p in self.local:
+            self.lib.ssfft_free(p)
+        self._imported, self.local = [], []
+
+
 class DistFFT1D:
     """One length-N complex transform sharded over `world` ranks (natural order in, natural order out)."""
 
@@ -108,6 +158,7 @@ class DistFFT1D:
         self.transposed_output = transposed_output
         self.exchanges = 0
         self._work = None  # two work buffers of N/P elements, allocated on first use and kept
+        self.profile = None  # set to {} to accumulate per-phase milliseconds (CUDA events) in _run
 
     # ---- the three local phases; each returns the packed send buffer [P][..][..] for the next exchange
     def _pack_rows(self, x_local, work):
@@ -147,22 +198,125 @@ class DistFFT1D:
             self._work = (torch.empty(per, dtype=self.dtype, device=x_local.device),
                           torch.empty(per, dtype=self.dtype, device=x_local.device))
         w1, w2 = self._work
+        prof = self.profile is not None and x_local.is_cuda
+        marks = []
+
+        def mark(name):
+            if prof:
+                ev = torch.cuda.Event(enable_timing=True)
+                ev.record()
+                marks.append((name, ev))
+
+        mark("start")
         send = self._pack_rows(x_local, w1)
+        mark("transpose1")
         recv = self._all_to_all(send, w2)
-        send = self._columns(recv, self.rank, inverse, w1, w2)          # result lives in w1
+        mark("a2a1")
+        c = self.ops.permute102(recv.view(self.world, self.b, self.a), w1).view(self.b, self.n1)
+        mark("permute1")
+        f = self.ops.fft_rows(c, inverse, w2.view(self.b, self.n1))
+        mark("fft_n1")
+        send = self.ops.transpose(f, w1, row0=self.rank * self.b, n_total=self.n, inverse=inverse)
+        send = send.view(self.world, self.a, self.b)
+        mark("transpose2+twiddle")
         recv = self._all_to_all(send, w2)
-        g = self._rows(recv, inverse, w1, out_local if self.transposed_output else w2)
+        mark("a2a2")
+        c = self.ops.permute102(recv.view(self.world, self.a, self.b), w1).view(self.a, self.n2)
+        mark("permute2")
+        g = self.ops.fft_rows(c, inverse, (out_local if self.transposed_output else w2).view(self.a, self.n2))
+        mark("fft_n2")
+        if not self.transposed_output:
+            send = self.ops.transpose(g, w1).view(self.world, self.b, self.a)
+            mark("transpose3")
+            recv = self._all_to_all(send, w2)
+            mark("a2a3")
+            self._natural(recv, out_local)
+            mark("permute3")
+        if prof:
+            torch.cuda.synchronize()
+            for (_, e0), (name, e1) in zip(marks[:-1], marks[1:]):
+                self.profile[name] = self.profile.get(name, 0.0) + e0.elapsed_time(e1)
+            self.profile["calls"] = self.profile.get("calls", 0) + 1
+        return out_local
+
+    # ---- fused path: every exchange is ONE kernel that transposes (+ twiddles) and stores straight into the peers'
+    # HBM over NVLink at the final position (ssfft_exchange_transpose); no pack, no NCCL all-to-all, no unpack.
+    def enable_peer_exchange(self, device):
+        """Allocate and IPC-share the exchange buffers (collective call).  Needs world > 1 CUDA ranks."""
+        self._peers = PeerBuffers(self.n // self.world, self.dtype, self.rank, self.world, self.group, device)
+        return self
+
+    def _run_p2p(self, x_local, out_local, inverse):
+        ops, pb = self.ops, self._peers
+        lib, prec = ops.lib, ops.prec
+        esz = 8 if self.dtype == torch.complex64 else 16
+        per = self.n // self.world
+        if self._work is None or self._work[0].device != x_local.device:
+            self._work = (torch.empty(per, dtype=self.dtype, device=x_local.device),
+                          torch.empty(per, dtype=self.dtype, device=x_local.device))
+        w = self._work[0]
+        stream = ops._stream(x_local)
+        a, b, n1, n2, r = self.a, self.b, self.n1, self.n2, self.rank
+        inv = 1 if inverse else 0
+        direction = L.SSFFT_INVERSE if inverse else L.SSFFT_FORWARD
+        prof = self.profile is not None
+        marks = []
+
+        def mark(name):
+            if prof:
+                ev = torch.cuda.Event(enable_timing=True)
+                ev.record()
+                marks.append((name, ev))
+
+        def plan_of(n):
+            pl = ops._plans.get(n)
+            if pl is None:
+                pl = ops._plans[n] = FFT(n, dtype="float32" if prec == L.SSFFT_F32 else "float64")
+            return pl._plan
+
+        bufA, bufB = pb.local[0], pb.local[1]
+        mark("start")
+        # exchange 1: x[a][n2] -> peers' A as [b][n1]  (my rows land at columns r*a ..)
+        L.check(lib.ssfft_exchange_transpose(x_local.data_ptr(), pb.tables[0], self.world, a, n2, n1, r * a, 0, 0, 0, prec,
+                                             stream), "ssfft_exchange_transpose")
+        pb.barrier()
+        mark("exchange1")
+        L.check(lib.ssfft_exec_c2c(plan_of(n1), bufA, w.data_ptr(), b, direction, stream), "ssfft_exec_c2c")
+        mark("fft_n1")
+        # exchange 2 (+ twiddle W_N^(n2 k1)): [b][n1] -> peers' B as [a][n2]
+        L.check(lib.ssfft_exchange_transpose(w.data_ptr(), pb.tables[1], self.world, b, n1, n2, r * b, r * b, self.n, inv,
+                                             prec, stream), "ssfft_exchange_transpose")
+        pb.barrier()
+        mark("exchange2+twiddle")
         if self.transposed_output:
-            return out_local
-        send = self.ops.transpose(g, w1).view(self.world, self.b, self.a)
-        recv = self._all_to_all(send, w2)
-        self._natural(recv, out_local)
+            L.check(lib.ssfft_exec_c2c(plan_of(n2), bufB, out_local.data_ptr(), a, direction, stream), "ssfft_exec_c2c")
+            mark("fft_n2")
+        else:
+            L.check(lib.ssfft_exec_c2c(plan_of(n2), bufB, w.data_ptr(), a, direction, stream), "ssfft_exec_c2c")
+            mark("fft_n2")
+            # exchange 3: [a][k2] -> peers' A as [b][n1] == natural order X[k2*n1 + k1]
+            L.check(lib.ssfft_exchange_transpose(w.data_ptr(), pb.tables[0], self.world, a, n2, n1, r * a, 0, 0, 0, prec,
+                                                 stream), "ssfft_exchange_transpose")
+            pb.barrier()
+            mark("exchange3")
+            L.check(lib.ssfft_memcpy_d2d(out_local.data_ptr(), bufA, per * esz, stream), "ssfft_memcpy_d2d")
+            mark("copy_out")
+        self.exchanges += 2 if self.transposed_output else 3
+        if prof:
+            torch.cuda.synchronize()
+            for (_, e0), (name, e1) in zip(marks[:-1], marks[1:]):
+                self.profile[name] = self.profile.get(name, 0.0) + e0.elapsed_time(e1)
+            self.profile["calls"] = self.profile.get("calls", 0) + 1
         return out_local
 
     def fft(self, x_local: torch.Tensor, out_local: torch.Tensor) -> torch.Tensor:
+        if getattr(self, "_peers", None) is not None:
+            return self._run_p2p(x_local, out_local, False)
         return self._run(x_local, out_local, False)
 
     def ifft(self, x_local: torch.Tensor, out_local: torch.Tensor) -> torch.Tensor:
+        if getattr(self, "_peers", None) is not None:
+            return self._run_p2p(x_local, out_local, True)
         return self._run(x_local, out_local, True)
 
     # ---- "fake shard" mode: all logical ranks in one process (single-GPU unit test of the same code path)

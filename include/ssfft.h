@@ -112,6 +112,19 @@ SSFFT_API int ssfft_transpose_twiddle(const void *d_in, void *d_out, size_t batc
 SSFFT_API int ssfft_permute102(const void *d_in, void *d_out, size_t A, size_t B, size_t run, int precision,
                                void *stream);
 
+/* ---- fused exchange over NVLink peer memory (one process per GPU; buffers shared with CUDA IPC) ----
+ * ssfft_ipc_export / import: make a ssfft_malloc'ed buffer visible to the other ranks (64-byte opaque handle).
+ * ssfft_exchange_transpose: src[rows][cols] is cut into `world` column blocks; block j is written, transposed and
+ * optionally multiplied by W_N^((row0 + r) * c), directly into rank j's buffer at
+ * dst_j[cl * dst_pitch + dst_col0 + r]  -- transpose + all-to-all + placement in one kernel, no NCCL on the path. */
+SSFFT_API int ssfft_ipc_export(void *d_ptr, void *handle64);
+SSFFT_API int ssfft_ipc_import(const void *handle64, void **d_ptr);
+SSFFT_API int ssfft_ipc_close(void *d_ptr);
+SSFFT_API int ssfft_exchange_transpose(const void *d_src, void *const *d_dst_ptrs, int world, size_t rows, size_t cols,
+                                       size_t dst_pitch, size_t dst_col0, size_t row0, uint64_t n_total, int inverse,
+                                       int precision, void *stream);
+SSFFT_API int ssfft_memcpy_d2d(void *d_dst, const void *d_src, size_t bytes, void *stream);
+
 /* ---- diagnostics ---- */
 SSFFT_API const char *ssfft_error_string(int status);
 SSFFT_API const char *ssfft_last_cuda_error(void);
