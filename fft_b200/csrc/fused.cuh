@@ -285,17 +285,34 @@ fused_fft_kernel(const cx<typename Cfg::T> *__restrict__ in, cx<typename Cfg::T>
                     __syncthreads();
                     // ---------------- R2C epilogue: post-twiddle pairs (RealFFT::fft :459-472)
                     if (active) {
-                        constexpr int H2 = N / 2 + 1;
-                        for (int i = t; i < H2; i += TX) {
-                            if (i == 0) {
-                                cx<T> z0 = sm[Cfg::pad(0)];
-                                st_stream(gout, mk<T>(z0.x + z0.y, z0.x - z0.y));
-                            } else {
-                                const int ci = N - i;
-                                cx<T> oi, oc;
-                                r2c_pair(sm[Cfg::pad(i)], sm[Cfg::pad(ci)], ld_table(rtw + i), oi, oc);
-                                st_stream(gout + i, oi);
-                                st_stream(gout + ci, oc);
+                        // pairs (i, N-i), i = 0 .. N/2, spread over the threads with a compile-time trip count so
+                        // the shared-memory reads and twiddle loads of all iterations are in flight together
+                        constexpr int H2 = N / 2 + 1, ITER = (H2 + TX - 1) / TX, CH = 4;  // CH pairs in flight
+#pragma unroll
+                        for (int u0 = 0; u0 < ITER; u0 += CH) {
+                            cx<T> zi[CH], zc[CH], tw_[CH];
+#pragma unroll
+                            for (int k = 0; k < CH; ++k) {
+                                const int i = t + TX * (u0 + k);
+                                if (u0 + k < ITER && i < H2) {
+                                    zi[k] = sm[Cfg::pad(i)];
+                                    zc[k] = sm[Cfg::pad(i ? N - i : 0)];
+                                    tw_[k] = ld_table(rtw + i);
+                                }
+                            }
+#pragma unroll
+                            for (int k = 0; k < CH; ++k) {
+                                const int i = t + TX * (u0 + k);
+                                if (u0 + k < ITER && i < H2) {
+                                    if (i == 0) {
+                                        st_stream(gout, mk<T>(zi[k].x + zi[k].y, zi[k].x - zi[k].y));  // (DC, Nyquist) :459-462
+                                    } else {
+                                        cx<T> oi, oc;
+                                        r2c_pair(zi[k], zc[k], tw_[k], oi, oc);
+                                        st_stream(gout + i, oi);
+                                        st_stream(gout + (N - i), oc);  // i == N-i: second write wins, as in the reference
+                                    }
+                                }
                             }
                         }
                     }
