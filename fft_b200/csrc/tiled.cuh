@@ -181,15 +181,44 @@ __device__ __forceinline__ void tile_prefetch(const TileParams<typename Cfg::T> 
 // transform (user buffer or scratch, depending on the flavor).  Every thread of the CTA must call this.
 // N1C / N2C / CTBLOG: compile-time four-step dimensions (0 / -1 = take them from `p` at run time).  With them
 // fixed every global address is base + immediate, which roughly halves the instruction count of a tile.
+// First-pass inputs of one tile into a caller-owned register array (same element order as tile_body's gather).
+// Issued one tile ahead, the loads stay in flight while the previous tile is transformed (register double buffer).
+template <typename Cfg, int FLAVOR, int N1C = 0, int N2C = 0, int CTBLOG = -1>
+__device__ __forceinline__ void tile_load(const TileParams<typename Cfg::T> &p, const cx<typename Cfg::T> *gin, int lane0,
+                                          cx<typename Cfg::T> (&v)[Cfg::E]) {
+    using T = typename Cfg::T;
+    constexpr int L = Cfg::L, TX = Cfg::TX, CT = Cfg::CT, E = Cfg::E;
+    constexpr int R = Cfg::radix(0), NR = L / R, U = E / R;
+    const int tid = threadIdx.x + threadIdx.y * blockDim.x;
+    const int c = tid % CT, t = tid / CT;
+    const int n1 = N1C ? N1C : p.n1, n2 = N2C ? N2C : p.n2, ctb = CTBLOG >= 0 ? CTBLOG : p.ctb_log2;
+    const int lane = lane0 + c;
+    if (lane < tile_width<FLAVOR>(n1, n2)) {
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+#pragma unroll
+            for (int j = 0; j < R; ++j) {
+                const int idx = t + TX * u + NR * j;
+                const cx<T> *src = tile_src<FLAVOR, L>(gin, lane, idx, n1, n2, ctb);
+                cx<T> x;
+                if constexpr (FLAVOR == TILE_B_C2C || FLAVOR == TILE_B_R2C) x = ld_l2(src);
+                else x = ld_stream(src);
+                v[u * R + j] = tile_fix<FLAVOR, L>(x, lane, idx, p.inverse);
+            }
+    }
+}
+
 struct NoHook {
     __device__ __forceinline__ void operator()() const {}
 };
 // STAGED: the first-pass inputs were prefetched into `st` by tile_prefetch (the caller has waited for them);
 // `hook` runs right after the first block-wide barrier, i.e. as soon as `st` may be overwritten again.
-template <typename Cfg, int FLAVOR, int N1C = 0, int N2C = 0, int CTBLOG = -1, bool STAGED = false, typename Hook = NoHook>
+template <typename Cfg, int FLAVOR, int N1C = 0, int N2C = 0, int CTBLOG = -1, bool STAGED = false, typename Hook = NoHook,
+          bool PRE = false>
 __device__ __forceinline__ void tile_body(const TileParams<typename Cfg::T> &p, const cx<typename Cfg::T> *gin,
                                           cx<typename Cfg::T> *gout, int lane0, cx<typename Cfg::T> *sm,
-                                          const cx<typename Cfg::T> *st = nullptr, Hook hook = Hook()) {
+                                          const cx<typename Cfg::T> *st = nullptr, Hook hook = Hook(),
+                                          const cx<typename Cfg::T> *pre = nullptr /* E preloaded inputs, or null */) {
     using T = typename Cfg::T;
     constexpr int L = Cfg::L, TX = Cfg::TX, CT = Cfg::CT, E = Cfg::E, NP = Cfg::NP, PITCH = Cfg::PITCH;
     constexpr int THREADS = Cfg::THREADS;
@@ -239,7 +268,10 @@ __device__ __forceinline__ void tile_body(const TileParams<typename Cfg::T> &p, 
             const int tt = tr ? t2 : t, cc = tr ? c2 : c;
             // ---- gather
             if constexpr (first && !kFirstFromSmem) {
-                if (live) {
+                if constexpr (PRE) {  // inputs were loaded one tile ahead by tile_load (register double buffer)
+#pragma unroll
+                    for (int e = 0; e < E; ++e) v[e] = pre[e];
+                } else if (live) {
 #pragma unroll
                     for (int u = 0; u < U; ++u)
 #pragma unroll
@@ -442,8 +474,21 @@ __host__ __device__ constexpr size_t fourstep_smem_bytes() {
     return (CfgA::smem_bytes > CfgB::smem_bytes ? CfgA::smem_bytes : CfgB::smem_bytes) * (fourstep_staged<CfgA, CfgB>() ? 2 : 1);
 }
 
+#ifndef SSFFT_FOURSTEP_REGPREFETCH
+#define SSFFT_FOURSTEP_REGPREFETCH 0  // measured slower (65536 C2C: 50.6 % -> 43.9 %): 3 CTAs/SM beat 2 CTAs/SM + register prefetch
+#endif
+template <typename CfgA, typename CfgB>
+__host__ __device__ constexpr bool fourstep_regprefetch() {
+    return SSFFT_FOURSTEP_REGPREFETCH && !fourstep_staged<CfgA, CfgB>() && sizeof(typename CfgA::T) == 4 && CfgA::E <= 16 &&
+           CfgB::E <= 16;
+}
+template <typename CfgA, typename CfgB>
+__host__ __device__ constexpr int fourstep_minb() {
+    return fourstep_regprefetch<CfgA, CfgB>() ? 2 : (CfgA::MINB < CfgB::MINB ? CfgA::MINB : CfgB::MINB);
+}
+
 template <typename CfgA, typename CfgB, int KIND>
-__global__ void __launch_bounds__(CfgA::THREADS, (CfgA::MINB < CfgB::MINB ? CfgA::MINB : CfgB::MINB))
+__global__ void __launch_bounds__(CfgA::THREADS, (fourstep_minb<CfgA, CfgB>()))
 fourstep_cluster_kernel(FourStepParams<typename CfgA::T> q) {
     using T = typename CfgA::T;
     static_assert(CfgA::THREADS == CfgB::THREADS, "both stages must use the same CTA size");
@@ -472,6 +517,12 @@ fourstep_cluster_kernel(FourStepParams<typename CfgA::T> q) {
     constexpr bool kStage2 = kStage && (F2 != TILE_A_C2R);  // A_C2R builds its input in shared memory itself
     cx<T> *st = reinterpret_cast<cx<T> *>(ssfft_smem + kTileBytes);
     bool s1_ready = false;  // the first stage-1 tile of the coming transform is already in flight
+    // register double buffering (the adopted overlap scheme): next tile's inputs are loaded into a second register
+    // set while the current tile is transformed; 2 CTAs/SM at <= 128 registers instead of 3 at 80.
+    constexpr bool kRegPf = fourstep_regprefetch<CfgA, CfgB>();
+    constexpr bool kRegPf2 = (F2 != TILE_A_C2R);
+    [[maybe_unused]] cx<T> vn1[Cfg1::E];
+    bool have1 = false;
     int slot = 0;
     for (long long B = cid; B < q.batch; B += nclusters, slot ^= 1) {
         cx<T> *scr = q.scratch + (cid * 2 + slot) * q.scratch_per;
@@ -489,47 +540,84 @@ fourstep_cluster_kernel(FourStepParams<typename CfgA::T> q) {
         };
         // ---- stage 1
         for (int tile = rank; tile < tiles1; tile += csize) {
-            if constexpr (kStage) {
-                if (!s1_ready) tile_prefetch<Cfg1, F1, CfgA::L, CfgB::L, kCtbLog>(p1, uin, tile * Cfg1::CT, st);
-                s1_ready = false;
-                cp_async_wait_all();
-                __syncthreads();
-            }
-            const int next = tile + csize;
-            auto hook = [&]() {
+            if constexpr (kRegPf) {
+                // register double buffer: this tile's inputs were requested one tile ago; request the next one now
+                if (!have1) tile_load<Cfg1, F1, CfgA::L, CfgB::L, kCtbLog>(p1, uin, tile * Cfg1::CT, vn1);
+                cx<T> vc[Cfg1::E];
+#pragma unroll
+                for (int e = 0; e < Cfg1::E; ++e) vc[e] = vn1[e];
+                const int next = tile + csize;
+                have1 = next < tiles1;
+                if (have1) tile_load<Cfg1, F1, CfgA::L, CfgB::L, kCtbLog>(p1, uin, next * Cfg1::CT, vn1);
+                tile_body<Cfg1, F1, CfgA::L, CfgB::L, kCtbLog, false, NoHook, true>(p1, uin, scr, tile * Cfg1::CT, sm, nullptr,
+                                                                                NoHook(), vc);
+            } else {
                 if constexpr (kStage) {
-                    if (next < tiles1) {
-                        tile_prefetch<Cfg1, F1, CfgA::L, CfgB::L, kCtbLog>(p1, uin, next * Cfg1::CT, st);
-                        s1_ready = true;
-                    }
+                    if (!s1_ready) tile_prefetch<Cfg1, F1, CfgA::L, CfgB::L, kCtbLog>(p1, uin, tile * Cfg1::CT, st);
+                    s1_ready = false;
+                    cp_async_wait_all();
+                    __syncthreads();
                 }
-            };
-            tile_body<Cfg1, F1, CfgA::L, CfgB::L, kCtbLog, kStage>(p1, uin, scr, tile * Cfg1::CT, sm, st, hook);
+                const int next = tile + csize;
+                auto hook = [&]() {
+                    if constexpr (kStage) {
+                        if (next < tiles1) {
+                            tile_prefetch<Cfg1, F1, CfgA::L, CfgB::L, kCtbLog>(p1, uin, next * Cfg1::CT, st);
+                            s1_ready = true;
+                        }
+                    }
+                };
+                tile_body<Cfg1, F1, CfgA::L, CfgB::L, kCtbLog, kStage>(p1, uin, scr, tile * Cfg1::CT, sm, st, hook);
+            }
         }
         cluster_barrier();  // stage-1 stores of every CTA in the cluster are visible; L1 is invalidated
         // ---- stage 2 (start rotates so the CTA that gets an extra, ragged tile changes between transforms)
         bool s2_ready = false;
         if constexpr (kStage && !kStage2) prefetch_next_s1();  // stage 2 does not use `st`: overlap all of it
+        [[maybe_unused]] cx<T> vn2[Cfg2::E];
+        bool have2 = false;
         for (int i = rank; i < tiles2; i += csize) {
             const int tile = (int)((i + B) % tiles2);
-            if constexpr (kStage2) {
-                if (!s2_ready) tile_prefetch<Cfg2, F2, CfgA::L, CfgB::L, kCtbLog>(p2, scr, tile * Cfg2::CT, st);
-                s2_ready = false;
-                cp_async_wait_all();
-                __syncthreads();
-            }
             const int inext = i + csize;
-            auto hook = [&]() {
-                if constexpr (kStage2) {
-                    if (inext < tiles2) {
-                        tile_prefetch<Cfg2, F2, CfgA::L, CfgB::L, kCtbLog>(p2, scr, (int)((inext + B) % tiles2) * Cfg2::CT, st);
-                        s2_ready = true;
-                    } else {
-                        prefetch_next_s1();
+            if constexpr (kRegPf && kRegPf2) {
+                if (!have2) tile_load<Cfg2, F2, CfgA::L, CfgB::L, kCtbLog>(p2, scr, tile * Cfg2::CT, vn2);
+                cx<T> vc[Cfg2::E];
+#pragma unroll
+                for (int e = 0; e < Cfg2::E; ++e) vc[e] = vn2[e];
+                have2 = inext < tiles2;
+                if (have2) {
+                    tile_load<Cfg2, F2, CfgA::L, CfgB::L, kCtbLog>(p2, scr, (int)((inext + B) % tiles2) * Cfg2::CT, vn2);
+                } else if (Bn < q.batch && rank < tiles1) {  // last stage-2 tile: request the next transform's first tile
+                    tile_load<Cfg1, F1, CfgA::L, CfgB::L, kCtbLog>(p1, uin_next, rank * Cfg1::CT, vn1);
+                    have1 = true;
+                }
+                tile_body<Cfg2, F2, CfgA::L, CfgB::L, kCtbLog, false, NoHook, true>(p2, scr, uout, tile * Cfg2::CT, sm, nullptr,
+                                                                                NoHook(), vc);
+            } else {
+                if constexpr (kRegPf) {  // stage 2 builds its input itself (A_C2R): still prefetch the next stage-1 tile
+                    if (inext >= tiles2 && Bn < q.batch && rank < tiles1) {
+                        tile_load<Cfg1, F1, CfgA::L, CfgB::L, kCtbLog>(p1, uin_next, rank * Cfg1::CT, vn1);
+                        have1 = true;
                     }
                 }
-            };
-            tile_body<Cfg2, F2, CfgA::L, CfgB::L, kCtbLog, kStage2>(p2, scr, uout, tile * Cfg2::CT, sm, st, hook);
+                if constexpr (kStage2) {
+                    if (!s2_ready) tile_prefetch<Cfg2, F2, CfgA::L, CfgB::L, kCtbLog>(p2, scr, tile * Cfg2::CT, st);
+                    s2_ready = false;
+                    cp_async_wait_all();
+                    __syncthreads();
+                }
+                auto hook = [&]() {
+                    if constexpr (kStage2) {
+                        if (inext < tiles2) {
+                            tile_prefetch<Cfg2, F2, CfgA::L, CfgB::L, kCtbLog>(p2, scr, (int)((inext + B) % tiles2) * Cfg2::CT, st);
+                            s2_ready = true;
+                        } else {
+                            prefetch_next_s1();
+                        }
+                    }
+                };
+                tile_body<Cfg2, F2, CfgA::L, CfgB::L, kCtbLog, kStage2>(p2, scr, uout, tile * Cfg2::CT, sm, st, hook);
+            }
             if (q.discard) {
                 // every stage-2 tile consumes a disjoint set of 128-byte scratch lines (tile-major layout)
                 constexpr int kLinesPerRow = CfgB::CT * (int)sizeof(cx<T>) / 128;  // lines per (block, n2)
