@@ -289,3 +289,29 @@ def test_distributed_four_step_logical_ranks_on_one_gpu(oracle, cuda_device):
         back = torch.cat(plan.run_logical(ys, inverse=True)).cpu().numpy()
         assert oracle.rel_l2(back[None], (n * x)[None]) <= 2 * tol(n, np.complex64)
         assert plan.exchanges == 6
+
+
+def test_exchange_building_blocks(oracle, cuda_device):
+    """ssfft_transpose_twiddle / ssfft_permute102 (local steps of the distributed four-step) against numpy."""
+    import ctypes
+
+    from fft_b200 import _lib as L
+    lib = L.load()
+    for dt, prec, rtol in ((np.complex64, L.SSFFT_F32, 3e-7), (np.complex128, L.SSFFT_F64, 1e-15)):
+        for rows, cols, row0, n_total, inv in ((48, 80, 0, 0, 0), (300, 70, 5, 300 * 70 * 3, 0), (257, 33, 1000, 1 << 30, 1)):
+            x = oracle.uniform_complex((rows, cols), 4, dt)
+            xd = torch.from_numpy(x).cuda()
+            yd = torch.empty((cols, rows), dtype=xd.dtype, device="cuda")
+            L.check(lib.ssfft_transpose_twiddle(xd.data_ptr(), yd.data_ptr(), 1, rows, cols, row0, n_total, inv, prec, None),
+                    "ssfft_transpose_twiddle")
+            ref = x.astype(np.complex128)
+            if n_total:
+                q = (np.arange(row0, row0 + rows, dtype=object)[:, None] * np.arange(cols, dtype=object)[None, :]) % n_total
+                ref = ref * np.exp((2j if inv else -2j) * np.pi * q.astype(np.float64) / n_total)
+            assert oracle.rel_l2(yd.cpu().numpy().reshape(1, -1), ref.T.reshape(1, -1)) <= rtol, (dt, rows, cols, n_total)
+        a, b, run = 3, 5, 14
+        x = oracle.uniform_complex((a, b, run), 6, dt)
+        xd = torch.from_numpy(x).cuda()
+        yd = torch.empty((b, a, run), dtype=xd.dtype, device="cuda")
+        L.check(lib.ssfft_permute102(xd.data_ptr(), yd.data_ptr(), a, b, run, prec, None), "ssfft_permute102")
+        assert np.array_equal(yd.cpu().numpy(), x.transpose(1, 0, 2))
