@@ -26,7 +26,10 @@
 
 namespace ssfft {
 
-enum { FUSED_C2C = 0, FUSED_R2C = 1, FUSED_C2R = 2 };
+// *_MOD: ModifiedRealFFT (RealFFT<V, halfFreqShift>, signalsmith-fft.h:389-395): input rotated by exp(-i pi n/N)
+// on load, pairs (i, N/2-1-i), twiddle phase shifted by half a bin, inverse un-rotated on store.  The rotation
+// table is stored right behind the real twiddles: rot = rtw + (N_complex/2 + 1).
+enum { FUSED_C2C = 0, FUSED_R2C = 1, FUSED_C2R = 2, FUSED_R2C_MOD = 3, FUSED_C2R_MOD = 4 };
 enum { FUSED_CONTIG = 0 };
 
 template <typename T_, int N_, int R0_, int R1_, int R2_, int R3_, int TX_, int FPB_, int MINB_, int PADSHIFT_ = 4, int PF_ = 0>
@@ -142,6 +145,9 @@ fused_fft_kernel(const cx<typename Cfg::T> *__restrict__ in, cx<typename Cfg::T>
     const cx<T> *stage = stage_all + (size_t)f * N;
     const long long groups = (batch + FPB - 1) / FPB;
     const bool leader = (t == 0 && f == 0);
+    const bool mod = mode >= FUSED_R2C_MOD;                               // half-bin-shifted real transform
+    const bool is_r2c = (mode == FUSED_R2C || mode == FUSED_R2C_MOD), is_c2r = (mode == FUSED_C2R || mode == FUSED_C2R_MOD);
+    const cx<T> *rot = rtw + (N / 2 + 1);                                  // modifiedRotations (:426-432), modified plans only
     unsigned parity = 0;
 
     // one thread asks the TMA engine for a whole group of transforms (contiguous in HBM).  Bulk copies
@@ -200,7 +206,7 @@ fused_fft_kernel(const cx<typename Cfg::T> *__restrict__ in, cx<typename Cfg::T>
             auto has = [&](int u) { return !ragged || (t + TX * u) < NR; };
             // ---- gather inputs
             if constexpr (first) {
-                if (mode == FUSED_C2R) {
+                if (is_c2r) {
                     if (PF || active) {
 #pragma unroll
                         for (int u = 0; u < U; ++u)
@@ -208,16 +214,27 @@ fused_fft_kernel(const cx<typename Cfg::T> *__restrict__ in, cx<typename Cfg::T>
                             for (int j = 0; j < R; ++j) {
                                 if (!has(u)) continue;
                                 const int i = t + TX * u + NR * j;
-                                const int ci = i ? N - i : 0;
-                                const bool lo = 2 * i <= N;  // i is the first (lo) or second element of its pair
+                                const int ci = mod ? N - 1 - i : (i ? N - i : 0);
+                                const bool lo = mod ? (2 * i <= N - 1) : (2 * i <= N);  // first or second element of its pair
                                 const cx<T> vi = load_in(i), vc = load_in(ci);
                                 const cx<T> w = ld_table(rtw + (lo ? i : ci));
                                 cx<T> bi, bc;
                                 c2r_pair(lo ? vi : vc, lo ? vc : vi, w, bi, bc);
                                 cx<T> x = lo ? bi : bc;
-                                if (i == 0) x = mk<T>(vi.x + vi.y, vi.x - vi.y);  // (DC, Nyquist) unpack  :478-481
+                                if (i == 0 && !mod) x = mk<T>(vi.x + vi.y, vi.x - vi.y);  // (DC, Nyquist) unpack  :478-481
                                 v[u * R + j] = cswap(x);
                             }
+                    }
+                } else if (mode == FUSED_R2C_MOD) {
+                    if (PF || active) {
+#pragma unroll
+                        for (int u = 0; u < U; ++u)
+#pragma unroll
+                            for (int j = 0; j < R; ++j)
+                                if (has(u)) {
+                                    const int idx = t + TX * u + NR * j;
+                                    v[u * R + j] = cmul(load_in(idx), ld_table(rot + idx));  // pre-rotation :450-452
+                                }
                     }
                 } else if (PF || active) {
                     if (inverse) {
@@ -276,7 +293,7 @@ fused_fft_kernel(const cx<typename Cfg::T> *__restrict__ in, cx<typename Cfg::T>
                 if constexpr (PF && first) prefetch(g + gridDim.x);  // every thread has consumed the staging buffer
             } else {
                 // last pass: P == N/R, m' == 0, racc == b  ->  natural-order index b + P*r
-                if (mode == FUSED_R2C) {
+                if (is_r2c) {
 #pragma unroll
                     for (int u = 0; u < U; ++u)
 #pragma unroll
@@ -294,29 +311,40 @@ fused_fft_kernel(const cx<typename Cfg::T> *__restrict__ in, cx<typename Cfg::T>
 #pragma unroll
                             for (int k = 0; k < CH; ++k) {
                                 const int i = t + TX * (u0 + k);
-                                if (u0 + k < ITER && i < H2) {
+                                if (u0 + k < ITER && i < H2 && (!mod || 2 * i <= N - 1)) {
                                     zi[k] = sm[Cfg::pad(i)];
-                                    zc[k] = sm[Cfg::pad(i ? N - i : 0)];
+                                    zc[k] = sm[Cfg::pad(mod ? N - 1 - i : (i ? N - i : 0))];
                                     tw_[k] = ld_table(rtw + i);
                                 }
                             }
 #pragma unroll
                             for (int k = 0; k < CH; ++k) {
                                 const int i = t + TX * (u0 + k);
-                                if (u0 + k < ITER && i < H2) {
-                                    if (i == 0) {
+                                if (u0 + k < ITER && i < H2 && (!mod || 2 * i <= N - 1)) {
+                                    if (i == 0 && !mod) {
                                         st_stream(gout, mk<T>(zi[k].x + zi[k].y, zi[k].x - zi[k].y));  // (DC, Nyquist) :459-462
                                     } else {
                                         cx<T> oi, oc;
                                         r2c_pair(zi[k], zc[k], tw_[k], oi, oc);
                                         st_stream(gout + i, oi);
-                                        st_stream(gout + (N - i), oc);  // i == N-i: second write wins, as in the reference
+                                        st_stream(gout + (mod ? N - 1 - i : N - i), oc);  // self-pair: second write wins
                                     }
                                 }
                             }
                         }
                     }
                     __syncthreads();
+                } else if (mode == FUSED_C2R_MOD) {
+                    if (active) {
+#pragma unroll
+                        for (int u = 0; u < U; ++u)
+#pragma unroll
+                            for (int r = 0; r < R; ++r)
+                                if (has(u)) {
+                                    const int k = t + TX * u + P * r;
+                                    st_stream(gout + k, cmulc(cswap(v[u * R + r]), ld_table(rot + k)));  // un-rotation :497-498
+                                }
+                    }
                 } else if (active) {
                     if (inverse) {
 #pragma unroll

@@ -383,8 +383,12 @@ int build_plan_typed(ssfft_plan *pl) {
     }
     if (pl->kind != SSFFT_C2C && !pl->tiled) {
         const bool modified = pl->kind == SSFFT_REAL_MODIFIED;
-        std::vector<T> h(2 * (pl->n_real / 4 + 1));
+        // twiddlesMinusI, followed (modified plans) by modifiedRotations so the fused kernel finds both behind one
+        // pointer: rot = rtw + (n/2 + 1), n = complex length
+        const size_t ntw = pl->n_real / 4 + 1, nrot = modified ? pl->n_real / 2 : 0;
+        std::vector<T> h(2 * (ntw + nrot));
         fill_real_twiddles<T>(h.data(), pl->n_real, modified);
+        if (modified) fill_modified_rotations<T>(h.data() + 2 * ntw, pl->n_real);
         CU(cudaMalloc(&pl->d_rtw, h.size() * sizeof(T)));
         CU(cudaMemcpy(pl->d_rtw, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
         if (modified) {
@@ -406,9 +410,9 @@ int exec_r2c_typed(ssfft_plan *pl, const void *in, void *out, long long batch, c
     if (h == 0 || batch <= 0) return SSFFT_OK;
     const bool modified = pl->kind == SSFFT_REAL_MODIFIED;
     if (pl->tiled) return exec_tiled<T>(pl, 1, in, out, batch, 0, s);
-    if (!modified && !pl->four_step && pl->fused.id >= 0)
-        return launch_fused<T>(pl->fused.id, pl->fused.d_twiddles, in, out, batch, 0, FUSED_R2C, pl->d_rtw, s,
-                               &g_launches);
+    if (!pl->four_step && pl->fused.id >= 0)
+        return launch_fused<T>(pl->fused.id, pl->fused.d_twiddles, in, out, batch, 0, modified ? FUSED_R2C_MOD : FUSED_R2C,
+                               pl->d_rtw, s, &g_launches);
     const void *src = in;  // N reals == h complex pairs (:449-455)
     if (modified) {
         rotate_kernel<T><<<blocks_for(h * batch, 256), 256, 0, s>>>((cx<T> *)out, (const cx<T> *)in,
@@ -432,9 +436,9 @@ int exec_c2r_typed(ssfft_plan *pl, const void *in, void *out, long long batch, c
     if (h == 0 || batch <= 0) return SSFFT_OK;
     const bool modified = pl->kind == SSFFT_REAL_MODIFIED;
     if (pl->tiled) return exec_tiled<T>(pl, 2, in, out, batch, 1, s);
-    if (!modified && !pl->four_step && pl->fused.id >= 0)
-        return launch_fused<T>(pl->fused.id, pl->fused.d_twiddles, in, out, batch, 1, FUSED_C2R, pl->d_rtw, s,
-                               &g_launches);
+    if (!pl->four_step && pl->fused.id >= 0)
+        return launch_fused<T>(pl->fused.id, pl->fused.d_twiddles, in, out, batch, 1, modified ? FUSED_C2R_MOD : FUSED_C2R,
+                               pl->d_rtw, s, &g_launches);
     c2r_pre_kernel<T><<<blocks_for((h / 2 + 1) * batch, 256), 256, 0, s>>>(
         (const cx<T> *)in, (cx<T> *)out, (const cx<T> *)pl->d_rtw, h, batch, modified ? 1 : 0);
     ++g_launches;
