@@ -34,6 +34,36 @@ template <typename T> SSFFT_HD cx<T> sub_i(cx<T> a, cx<T> b) { return mk<T>(a.x 
 template <typename T> SSFFT_HD cx<T> add_i(cx<T> a, cx<T> b) { return mk<T>(a.x - b.y, a.y + b.x); }
 
 // ---------------------------------------------------------------------------------------------
+// Blackwell packed fp32: add / mul / fma.f32x2 (SASS FADD2 / FMUL2 / FFMA2) work on an aligned register pair,
+// i.e. on one interleaved complex value, with per-operand swap / negate / broadcast modifiers.  A complex
+// add, a +-i rotation-and-add and a broadcast multiply are ONE instruction each instead of two, which is what
+// would matter for a kernel bound by issue slots.  MEASURED SLOWER on B200 (tools/ubench_f32x2.cu: FADD2 issues at
+// half the rate of FADD, so the fp32 pipe gains nothing, and pairing costs extra MOVs: the headline 4096 kernel went
+// 86.5 % -> 81.7 % of the HBM roofline, 2048 90 -> 80 %, 2^20 28 -> 21 %; profiles/sweep_packed_f32x2_r01_float32.json).
+// Kept behind -DSSFFT_USE_F32X2 as a recorded experiment; parity tests pass with it on.
+// ---------------------------------------------------------------------------------------------
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ >= 1000) && defined(SSFFT_USE_F32X2)
+#define SSFFT_F32X2 1
+__device__ __forceinline__ float2 f2(cx<float> a) { return make_float2(a.x, a.y); }
+__device__ __forceinline__ cx<float> c2(float2 a) { return mk<float>(a.x, a.y); }
+__device__ __forceinline__ cx<float> operator+(cx<float> a, cx<float> b) { return c2(__fadd2_rn(f2(a), f2(b))); }
+__device__ __forceinline__ cx<float> operator-(cx<float> a, cx<float> b) { return c2(__fadd2_rn(f2(a), make_float2(-b.x, -b.y))); }
+__device__ __forceinline__ cx<float> cmul(cx<float> a, cx<float> b) {
+    return c2(__ffma2_rn(make_float2(a.y, a.y), make_float2(-b.y, b.x), __fmul2_rn(make_float2(a.x, a.x), f2(b))));
+}
+__device__ __forceinline__ cx<float> cmulc(cx<float> a, cx<float> b) {  // a * conj(b)
+    return c2(__ffma2_rn(make_float2(a.y, a.y), make_float2(b.y, b.x), __fmul2_rn(make_float2(a.x, a.x), make_float2(b.x, -b.y))));
+}
+__device__ __forceinline__ cx<float> sub_i(cx<float> a, cx<float> b) { return c2(__fadd2_rn(f2(a), make_float2(b.y, -b.x))); }
+__device__ __forceinline__ cx<float> add_i(cx<float> a, cx<float> b) { return c2(__fadd2_rn(f2(a), make_float2(-b.y, b.x))); }
+// v * (c - i s)
+__device__ __forceinline__ cx<float> mul_cs(cx<float> v, float c, float s) {
+    return c2(__ffma2_rn(make_float2(v.y, -v.x), make_float2(s, s), __fmul2_rn(f2(v), make_float2(c, c))));
+}
+__device__ __forceinline__ cx<float> scale2(cx<float> v, float h) { return c2(__fmul2_rn(f2(v), make_float2(h, h))); }
+#endif
+
+// ---------------------------------------------------------------------------------------------
 // constexpr cos/sin of 2*pi*num/den, exact octant reduction on the rational, Taylor on [0, pi/4].
 // Used only for compile-time butterfly constants (evaluated by the front end, never on the GPU).
 // ---------------------------------------------------------------------------------------------
@@ -119,6 +149,14 @@ SSFFT_HD cx<T> mul_root(cx<T> v) {
     } else if constexpr ((8 * NUM) % DEN == 0) {  // odd eighth turns: (+-1 +-i)/sqrt2
         constexpr int e = (8 * NUM) / DEN;        // 1,3,5,7
         constexpr T h = (T)0.70710678118654752440;
+#ifdef SSFFT_F32X2
+        if constexpr (sizeof(T) == 4) {  // (v -+ i v) * (+-h): one packed add (swap + half negate) and one packed multiply
+            if constexpr (e == 1) return scale2(sub_i(v, v), h);        // (x + y, y - x) h
+            else if constexpr (e == 3) return scale2(add_i(v, v), -h);  // (x - y, y + x)(-h) = (y - x, -(x + y)) h
+            else if constexpr (e == 5) return scale2(sub_i(v, v), -h);  // (-(x + y), x - y) h
+            else return scale2(add_i(v, v), h);                          // (x - y, x + y) h
+        }
+#endif
         // exp(-i*pi/4*e): e=1: (1 - i)h ; e=3: (-1 - i)h ; e=5: (-1 + i)h ; e=7: (1 + i)h
         if constexpr (e == 1) return mk<T>((v.x + v.y) * h, (v.y - v.x) * h);
         else if constexpr (e == 3) return mk<T>((v.y - v.x) * h, -(v.x + v.y) * h);
@@ -127,6 +165,9 @@ SSFFT_HD cx<T> mul_root(cx<T> v) {
     } else {
         constexpr ct::cs w = ct::cossin2pi(NUM, DEN);
         constexpr T c = (T)w.c, s = (T)w.s;  // multiply by (c - i s)
+#ifdef SSFFT_F32X2
+        if constexpr (sizeof(T) == 4) return mul_cs(v, c, s);
+#endif
         return mk<T>(v.x * c + v.y * s, v.y * c - v.x * s);
     }
 }

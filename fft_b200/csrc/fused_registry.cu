@@ -2,6 +2,7 @@
 #include <cstdlib>
 
 #include "fused.cuh"
+#include "cluster.cuh"
 #include "tiled.cuh"
 namespace ssfft {
 void register_fused_f32_a(std::vector<FusedEntry> &);
@@ -73,6 +74,23 @@ int fourstep_cluster_size() {
         return (v < 1 || v > 16) ? 4 : v;
     }();
     return c;
+}
+
+void register_cluster_f32_a(std::vector<ClusterEntry> &);
+void register_cluster_f32_b(std::vector<ClusterEntry> &);
+
+const std::vector<ClusterEntry> &cluster_registry() {
+    static const std::vector<ClusterEntry> reg = [] {
+        std::vector<ClusterEntry> v;
+        // SSFFT_DISABLE_DSMEM=1: fall back to the L2-scratch four-step (parity tests exercise both)
+        const char *off = getenv("SSFFT_DISABLE_DSMEM");
+        const char *off2 = getenv("SSFFT_DISABLE_TILED");
+        if ((off && off[0] == '1') || (off2 && off2[0] == '1')) return v;
+        register_cluster_f32_a(v);
+        register_cluster_f32_b(v);
+        return v;
+    }();
+    return reg;
 }
 
 // how many resident "waves" of CTAs a fused launch may create before CTAs start looping

@@ -55,6 +55,13 @@ struct ssfft_plan {
     void *d_scratch = nullptr;  // four-step intermediate, chunk transforms
     size_t chunk = 0;
 
+    // cluster-resident four-step (cluster.cuh): registry id per kind (C2C / R2C / C2R), -1 = not used
+    bool clustered = false;
+    int cl_id[3] = {-1, -1, -1};
+    int cl_clusters[3] = {0, 0, 0};
+    void *d_cl_twa[3] = {nullptr, nullptr, nullptr}, *d_cl_twb[3] = {nullptr, nullptr, nullptr},
+         *d_cl_tw4[3] = {nullptr, nullptr, nullptr};  // tables per kind (kinds that share an entry share the pointers)
+
     // real wrappers
     void *d_rtw = nullptr;  // twiddlesMinusI
     void *d_rot = nullptr;  // modifiedRotations

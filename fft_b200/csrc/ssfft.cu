@@ -15,6 +15,7 @@
 #include <string>
 #include <vector>
 
+#include "cluster.cuh"
 #include "fused.cuh"
 #include "generic.cuh"
 #include "plan.h"
@@ -275,11 +276,65 @@ int exec_tiled(ssfft_plan *pl, int kind, const void *in, void *out, long long ba
     return SSFFT_OK;
 }
 
+// Cluster-resident four-step (cluster.cuh): the transform lives in the shared memory of a thread-block cluster.
+// Complex length pl->n; real plans need both the R2C and the C2R kernel.  *ok = false leaves the plan untouched.
+template <typename T>
+int setup_clustered(ssfft_plan *pl, bool *ok) {
+    *ok = false;
+    if (env_int("SSFFT_DISABLE_DSMEM", 0)) return SSFFT_OK;
+    const bool real = pl->kind != SSFFT_C2C;
+    const int k0 = real ? 1 : 0, k1 = real ? 2 : 0;
+    int ids[3] = {-1, -1, -1}, clusters[3] = {0, 0, 0};
+    for (int k = k0; k <= k1; ++k) {
+        ids[k] = find_cluster<T>(pl->n, k);
+        if (ids[k] < 0) return SSFFT_OK;
+        clusters[k] = cluster_registry()[ids[k]].max_clusters[k]();
+        if (clusters[k] < 1) return SSFFT_OK;  // clusters of this size cannot be scheduled on this device
+    }
+    for (int k = k0; k <= k1; ++k) {
+        pl->cl_id[k] = ids[k];
+        pl->cl_clusters[k] = clusters[k];
+        if (k > k0 && ids[k] == ids[k0]) {  // same kernel geometry: share the tables
+            pl->d_cl_twa[k] = pl->d_cl_twa[k0]; pl->d_cl_twb[k] = pl->d_cl_twb[k0]; pl->d_cl_tw4[k] = pl->d_cl_tw4[k0];
+            continue;
+        }
+        const ClusterEntry &e = cluster_registry()[ids[k]];
+        std::vector<T> h;
+        fill_cluster_pass_twiddles<T>(h, e.n1, e.ra0);
+        CU(cudaMalloc(&pl->d_cl_twa[k], h.size() * sizeof(T)));
+        CU(cudaMemcpy(pl->d_cl_twa[k], h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+        fill_cluster_pass_twiddles<T>(h, e.n2, e.rb0);
+        CU(cudaMalloc(&pl->d_cl_twb[k], h.size() * sizeof(T)));
+        CU(cudaMemcpy(pl->d_cl_twb[k], h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+        fill_cluster_tw4<T>(h, e.n1, e.n2);
+        CU(cudaMalloc(&pl->d_cl_tw4[k], h.size() * sizeof(T)));
+        CU(cudaMemcpy(pl->d_cl_tw4[k], h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+    }
+    pl->clustered = true;
+    *ok = true;
+    return SSFFT_OK;
+}
+
+template <typename T>
+int exec_clustered(ssfft_plan *pl, int kind, const void *in, void *out, long long batch, int inverse, cudaStream_t s) {
+    ClusterParams<T> q;
+    q.in = (const cx<T> *)in; q.out = (cx<T> *)out;
+    q.tw_a = (const cx<T> *)pl->d_cl_twa[kind]; q.tw_b = (const cx<T> *)pl->d_cl_twb[kind];
+    q.tw4 = (const cx<T> *)pl->d_cl_tw4[kind]; q.rtw = (const cx<T> *)pl->d_rtw;
+    q.batch = batch; q.inverse = inverse;
+    q.use_tma = env_int("SSFFT_CLUSTER_TMA", 1);
+    int rc = cluster_registry()[pl->cl_id[kind]].launch[kind](&q, pl->cl_clusters[kind], s);
+    ++g_launches;
+    if (rc) return cuda_fail(cudaGetLastError(), "cluster_fft_kernel launch");
+    return SSFFT_OK;
+}
+
 // Complex core: batch contiguous transforms of length pl->n, in -> out (in == out allowed).
 template <typename T>
 int exec_complex(ssfft_plan *pl, const void *in, void *out, long long batch, int inverse, cudaStream_t s) {
     const long long n = (long long)pl->n;
     if (batch <= 0 || n == 0) return SSFFT_OK;
+    if (pl->clustered && pl->kind == SSFFT_C2C) return exec_clustered<T>(pl, 0, in, out, batch, inverse, s);
     if (pl->tiled && pl->kind == SSFFT_C2C) return exec_tiled<T>(pl, 0, in, out, batch, inverse, s);
     if (!pl->four_step) {
         if (pl->fused.id >= 0)
@@ -315,15 +370,32 @@ int build_plan_typed(ssfft_plan *pl) {
     char buf[512];
     if (n == 0) { pl->desc = "empty"; return SSFFT_OK; }
     const size_t limit = generic_limit(sizeof(cx<T>), smem_max);
-    bool tiled_ok = false;
-    if (pl->kind == SSFFT_C2C) {
+    bool tiled_ok = false, clustered_ok = false;
+    if (pl->kind == SSFFT_C2C || pl->kind == SSFFT_REAL) {
+        int rc = setup_clustered<T>(pl, &clustered_ok);
+        if (rc) return rc;
+    }
+    if (clustered_ok) {
+        // nothing else to build: one kernel does the whole transform
+    } else if (pl->kind == SSFFT_C2C) {
         int rc = setup_tiled<T>(pl, n, false, &tiled_ok);
         if (rc) return rc;
     } else if (pl->kind == SSFFT_REAL) {
         int rc = setup_tiled<T>(pl, pl->n_real, true, &tiled_ok);
         if (rc) return rc;
     }
-    if (tiled_ok) {
+    if (clustered_ok) {
+        const int k = pl->kind == SSFFT_C2C ? 0 : 1;
+        const ClusterEntry &e = cluster_registry()[pl->cl_id[k]];
+        if (pl->kind == SSFFT_C2C)
+            snprintf(buf, sizeof(buf), "complex N=%zu cluster-resident four-step n1=%d x n2=%d (%s): %d-CTA clusters hold a "
+                     "transform in distributed shared memory, one launch, %d co-resident clusters", n, e.n1, e.n2, e.name,
+                     e.csize, pl->cl_clusters[k]);
+        else
+            snprintf(buf, sizeof(buf), "complex N=%zu cluster-resident four-step (%s forward, %s inverse): %d-CTA clusters, "
+                     "RealFFT twiddles fused, one launch", n, e.name, cluster_registry()[pl->cl_id[2]].name, e.csize);
+        pl->desc = buf;
+    } else if (tiled_ok) {
         if (pl->fs_id >= 0)
             snprintf(buf, sizeof(buf), "%s N=%zu four-step n1=%zu x n2=%zu, one persistent launch %s, clusters of %d CTAs x %d, "
                      "L2-resident scratch %.1f MiB", pl->kind == SSFFT_C2C ? "complex" : "real",
@@ -409,6 +481,7 @@ int exec_r2c_typed(ssfft_plan *pl, const void *in, void *out, long long batch, c
     const long long h = (long long)pl->n;
     if (h == 0 || batch <= 0) return SSFFT_OK;
     const bool modified = pl->kind == SSFFT_REAL_MODIFIED;
+    if (pl->clustered) return exec_clustered<T>(pl, 1, in, out, batch, 0, s);
     if (pl->tiled) return exec_tiled<T>(pl, 1, in, out, batch, 0, s);
     if (!pl->four_step && pl->fused.id >= 0)
         return launch_fused<T>(pl->fused.id, pl->fused.d_twiddles, in, out, batch, 0, modified ? FUSED_R2C_MOD : FUSED_R2C,
@@ -435,6 +508,7 @@ int exec_c2r_typed(ssfft_plan *pl, const void *in, void *out, long long batch, c
     const long long h = (long long)pl->n;
     if (h == 0 || batch <= 0) return SSFFT_OK;
     const bool modified = pl->kind == SSFFT_REAL_MODIFIED;
+    if (pl->clustered) return exec_clustered<T>(pl, 2, in, out, batch, 1, s);
     if (pl->tiled) return exec_tiled<T>(pl, 2, in, out, batch, 1, s);
     if (!pl->four_step && pl->fused.id >= 0)
         return launch_fused<T>(pl->fused.id, pl->fused.d_twiddles, in, out, batch, 1, modified ? FUSED_C2R_MOD : FUSED_C2R,
@@ -514,6 +588,13 @@ int ssfft_plan_destroy(ssfft_plan *pl) {
                     pl->d_tw4};
     for (void *p : ptrs)
         if (p) cudaFree(p);
+    for (int k = 0; k < 3; ++k) {
+        const bool shared = k > 0 && pl->d_cl_tw4[k] && (pl->d_cl_tw4[k] == pl->d_cl_tw4[k - 1] || (k == 2 && pl->d_cl_tw4[2] == pl->d_cl_tw4[0]));
+        if (shared) continue;
+        if (pl->d_cl_twa[k]) cudaFree(pl->d_cl_twa[k]);
+        if (pl->d_cl_twb[k]) cudaFree(pl->d_cl_twb[k]);
+        if (pl->d_cl_tw4[k]) cudaFree(pl->d_cl_tw4[k]);
+    }
     if (pl->host_stream) cudaStreamDestroy(pl->host_stream);
     delete pl;
     return SSFFT_OK;

@@ -315,3 +315,51 @@ def test_exchange_building_blocks(oracle, cuda_device):
         yd = torch.empty((b, a, run), dtype=xd.dtype, device="cuda")
         L.check(lib.ssfft_permute102(xd.data_ptr(), yd.data_ptr(), a, b, run, prec, None), "ssfft_permute102")
         assert np.array_equal(yd.cpu().numpy(), x.transpose(1, 0, 2))
+
+
+def test_cluster_resident_four_step(oracle, cuda_device):
+    """cluster.cuh: a transform lives in the shared memory of a thread-block cluster (DSMEM all-to-all, st.async +
+    mbarrier, TMA tensor prefetch).  tests/gpu_cluster_check.py runs batches several times larger than the number of
+    co-resident clusters (every cluster loops over many transforms, exercising the barrier protocol), C2C both
+    directions and RealFFT forward / inverse, for every registered geometry (SSFFT_DSMEM_ALL=1), with and without TMA."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for tma in ("1", "0"):
+        env = dict(os.environ, SSFFT_DSMEM_ALL="1", SSFFT_CLUSTER_TMA=tma)
+        res = subprocess.run([sys.executable, os.path.join(root, "tests", "gpu_cluster_check.py")], cwd=root, env=env,
+                             capture_output=True, text=True, timeout=900)
+        assert "CLUSTER-GPU-OK" in res.stdout, (tma, res.stdout[-2000:] + res.stderr[-2000:])
+    # default planner choice: complex 32768 runs cluster-resident
+    f = fft_b200.FFT(32768)
+    assert "cluster-resident" in f.describe(), f.describe()
+
+
+def test_l2_scratch_four_step_still_matches(oracle, cuda_device):
+    """With the cluster-resident kernels disabled the same sizes run through the L2-scratch four-step (tiled.cuh)."""
+    import subprocess
+    import sys
+    code = r"""
+import os, sys, math
+os.environ["SSFFT_DISABLE_DSMEM"] = "1"
+sys.path.insert(0, os.getcwd())
+import numpy as np, torch, fft_b200
+from oracle import oracle as O
+for n in (32768, 65536):
+    x = O.uniform_complex((5, n), 7, np.complex64)
+    f = fft_b200.FFT(n)
+    assert "cluster-resident" not in f.describe(), f.describe()
+    xd = torch.from_numpy(x).cuda(); out = torch.empty_like(xd)
+    f.fft(xd, out)
+    assert O.rel_l2(out.cpu().numpy(), O.fft(x)) <= 1e-6 * math.log2(n), n
+    xr = O.uniform(3 * 2 * n, 8, np.float32).reshape(3, 2 * n)
+    r = fft_b200.RealFFT(2 * n)
+    assert "cluster-resident" not in r.describe(), r.describe()
+    sp = torch.empty((3, n), dtype=torch.complex64, device="cuda")
+    r.fft(torch.from_numpy(xr).cuda(), sp)
+    assert O.rel_l2(sp.cpu().numpy(), O.rfft(xr)) <= 1e-6 * math.log2(2 * n), n
+print("L2-FOURSTEP-OK")
+"""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = subprocess.run([sys.executable, "-c", code], cwd=root, capture_output=True, text=True, timeout=600)
+    assert "L2-FOURSTEP-OK" in res.stdout, res.stdout + res.stderr
