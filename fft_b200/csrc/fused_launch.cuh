@@ -16,11 +16,13 @@ int launch_cfg(const void *tw, const void *in, void *out, long long batch, int i
     if (dev < 0 || dev >= 32) return 1;
     if (!(ready_mask & (1 << dev))) {
         if (Cfg::smem_bytes > 48 * 1024 &&
-            cudaFuncSetAttribute(fused_fft_kernel<Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)Cfg::smem_bytes) != cudaSuccess)
+            (cudaFuncSetAttribute(fused_fft_kernel<Cfg, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)Cfg::smem_bytes) != cudaSuccess ||
+             cudaFuncSetAttribute(fused_fft_kernel<Cfg, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)Cfg::smem_bytes) != cudaSuccess))
             return 2;
         int per_sm = 0, sms = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fused_fft_kernel<Cfg>, Cfg::TX * Cfg::FPB,
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fused_fft_kernel<Cfg, false>, Cfg::TX * Cfg::FPB,
                                                           Cfg::smem_bytes) != cudaSuccess)
             return 2;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -34,9 +36,12 @@ int launch_cfg(const void *tw, const void *in, void *out, long long batch, int i
     const long long cap = (long long)resident[dev] * fused_waves();
     if (cap > 0 && grid > cap) grid = cap;
     dim3 block(Cfg::TX, Cfg::FPB);
-    fused_fft_kernel<Cfg><<<(unsigned)grid, block, Cfg::smem_bytes, s>>>((const cx<T> *)in, (cx<T> *)out,
-                                                                          (const cx<T> *)tw, (const cx<T> *)rtw, batch,
-                                                                          inverse, mode);
+    if (mode >= FUSED_R2C_MOD)
+        fused_fft_kernel<Cfg, true><<<(unsigned)grid, block, Cfg::smem_bytes, s>>>(
+            (const cx<T> *)in, (cx<T> *)out, (const cx<T> *)tw, (const cx<T> *)rtw, batch, inverse, mode);
+    else
+        fused_fft_kernel<Cfg, false><<<(unsigned)grid, block, Cfg::smem_bytes, s>>>(
+            (const cx<T> *)in, (cx<T> *)out, (const cx<T> *)tw, (const cx<T> *)rtw, batch, inverse, mode);
     return cudaGetLastError() == cudaSuccess ? 0 : 2;
 }
 

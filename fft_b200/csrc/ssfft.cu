@@ -665,7 +665,12 @@ int ssfft_exec_host(ssfft_plan *pl, int op, const void *h_in, void *h_out, size_
     cudaStream_t s = pl->host_stream;
     size_t slices = 1;
     const size_t per = pl->n * pl->elem;
-    if (bytes > (64u << 20)) slices = 8;
+    // more slices = shorter pipeline fill / drain (first H2D and last D2H are not overlapped); each slice still has to
+    // be large enough to run PCIe at full rate (>= 32 MiB)
+    if (bytes > (64u << 20)) {
+        slices = (size_t)env_int("SSFFT_HOST_SLICES", 0);
+        if (slices < 1) { slices = bytes / (64u << 20); if (slices < 8) slices = 8; if (slices > 32) slices = 32; }
+    }
     if (slices > batch) slices = batch;
     cudaStream_t extra[2] = {nullptr, nullptr};
     if (slices > 1)
