@@ -211,7 +211,25 @@ int setup_tiled(ssfft_plan *pl, size_t total, bool real, bool *ok) {
         }
         if (clusters >= 1) {
             pl->fs_clusters = clusters;
-            CU(cudaMalloc(&pl->d_scratch, (size_t)2 * clusters * per));
+            // Transforms in flight = groups; each owns two scratch slots.  Grow the groups (clusters per transform)
+            // until all slots fit the L2 budget or a group already has a CTA per tile.
+            // MEASURED (profiles/sweep_groups_r01_float32.json): the kernels are latency-bound, not DRAM-bound, so keeping
+            // the scratch in L2 only pays where it spills completely -- real transforms of 2^19 and more (+15 %);
+            // complex 2^16..2^18 lost 3-7 points to the extra barrier.  Default: groups for those sizes only.
+            const int dflt_mb = (real && total >= ((size_t)1 << 19)) ? 56 : (1 << 20);
+            const size_t budget = (size_t)env_int("SSFFT_FS_L2_MB", dflt_mb) << 20;
+            int max_groups = 1;
+            for (int kind = real ? 1 : 0; kind <= (real ? 2 : 0); ++kind) {
+                const int tiles = fe.tiles[kind][0] > fe.tiles[kind][1] ? fe.tiles[kind][0] : fe.tiles[kind][1];
+                int g = 1;
+                while ((size_t)2 * (size_t)(clusters / g) * per > budget && g * cs < tiles && 2 * g <= clusters) g *= 2;
+                if (env_int("SSFFT_FS_GROUP", 0) > 0) g = env_int("SSFFT_FS_GROUP", 0);
+                if (g > clusters) g = clusters;
+                pl->fs_group[kind] = g;
+                if (clusters / g > max_groups) max_groups = clusters / g;
+            }
+            CU(cudaMalloc(&pl->d_scratch, (size_t)2 * max_groups * per));
+            CU(cudaMalloc(&pl->d_fs_ctr, (size_t)max_groups * sizeof(unsigned)));
         } else {
             pl->fs_id = -1;  // clusters of this size cannot be scheduled here
         }
@@ -241,7 +259,11 @@ int exec_tiled(ssfft_plan *pl, int kind, const void *in, void *out, long long ba
         q.n1 = n1; q.n2 = n2; q.batch = batch; q.user_stride = user_stride; q.scratch_per = sp; q.inverse = inverse;
         q.ctb_log2 = pl->ctb_log2;
         q.discard = env_int("SSFFT_DISCARD", 1);
-        int rc = fourstep_registry()[pl->fs_id].launch[kind](&q, pl->fs_clusters, s);
+        q.group_clusters = pl->fs_group[kind];
+        q.group_ctr = (unsigned *)pl->d_fs_ctr;
+        const int groups = pl->fs_clusters / q.group_clusters;
+        if (q.group_clusters > 1) CU(cudaMemsetAsync(pl->d_fs_ctr, 0, (size_t)groups * sizeof(unsigned), s));
+        int rc = fourstep_registry()[pl->fs_id].launch[kind](&q, groups * q.group_clusters, s);
         ++g_launches;
         if (rc) return cuda_fail(cudaGetLastError(), "fourstep_cluster_kernel launch");
         return SSFFT_OK;
@@ -398,10 +420,10 @@ int build_plan_typed(ssfft_plan *pl) {
     } else if (tiled_ok) {
         if (pl->fs_id >= 0)
             snprintf(buf, sizeof(buf), "%s N=%zu four-step n1=%zu x n2=%zu, one persistent launch %s, clusters of %d CTAs x %d, "
-                     "L2-resident scratch %.1f MiB", pl->kind == SSFFT_C2C ? "complex" : "real",
+                     "%d cluster(s) per transform, L2-resident scratch %.1f MiB", pl->kind == SSFFT_C2C ? "complex" : "real",
                      pl->kind == SSFFT_C2C ? n : pl->n_real, pl->n1, pl->n2, fourstep_registry()[pl->fs_id].name,
-                     fourstep_cluster_size(), pl->fs_clusters,
-                     2.0 * pl->fs_clusters * pl->scratch_per * sizeof(cx<T>) / 1048576.0);
+                     fourstep_cluster_size(), pl->fs_clusters, pl->fs_group[pl->kind == SSFFT_C2C ? 0 : 1],
+                     2.0 * (pl->fs_clusters / pl->fs_group[pl->kind == SSFFT_C2C ? 0 : 1]) * pl->scratch_per * sizeof(cx<T>) / 1048576.0);
         else
             snprintf(buf, sizeof(buf), "%s N=%zu four-step tiles n1=%zu (%s) x n2=%zu (%s) chunk=%zu L2-resident scratch",
                      pl->kind == SSFFT_C2C ? "complex" : "real", pl->kind == SSFFT_C2C ? n : pl->n_real, pl->n1,
@@ -585,7 +607,7 @@ int ssfft_plan_destroy(ssfft_plan *pl) {
     free_stage(pl->direct); free_stage(pl->col); free_stage(pl->row);
     void *ptrs[] = {pl->fused.d_twiddles, pl->fused_col.d_twiddles, pl->fused_row.d_twiddles, pl->d_ep_lo, pl->d_ep_hi,
                     pl->d_scratch, pl->d_rtw, pl->d_rot, pl->d_stage_in, pl->d_stage_out, pl->d_tile_tw_a, pl->d_tile_tw_b,
-                    pl->d_tw4};
+                    pl->d_tw4, pl->d_fs_ctr};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     for (int k = 0; k < 3; ++k) {

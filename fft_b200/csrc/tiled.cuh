@@ -427,6 +427,11 @@ struct FourStepParams {
     long long batch, user_stride, scratch_per;
     int inverse, ctb_log2;
     int discard;  // drop consumed scratch lines from L2 (discard.global.L2)
+    // A GROUP of `group_clusters` clusters shares one transform (tiles are spread over all its CTAs, the two stages
+    // are separated by a software barrier on group_ctr[group]).  Large transforms use big groups so that the scratch
+    // of all transforms in flight (2 slots per group) stays inside the L2 instead of spilling to HBM.
+    int group_clusters;
+    unsigned *group_ctr;  // one zero-initialised counter per group
 };
 
 __device__ __forceinline__ unsigned cluster_ctarank() {
@@ -441,6 +446,26 @@ __device__ __forceinline__ unsigned cluster_nctarank() {
 }
 __device__ __forceinline__ void cluster_barrier() {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+// Barrier over the CTAs of a group (all co-resident: the launch is cooperative / sized to residency).  The counter
+// only grows; `target` is the value it reaches when every CTA of the group has arrived for this barrier.
+// Bounded spin: a scheduling surprise becomes a trap (launch error), never a hung GPU.
+__device__ __forceinline__ void group_barrier(unsigned *ctr, unsigned target) {
+    __syncthreads();
+    if (threadIdx.x == 0 && threadIdx.y == 0) {
+        __threadfence();  // this CTA's scratch stores are visible device-wide before it signals
+        atomicAdd(ctr, 1u);
+        const long long t0 = clock64();
+        for (;;) {
+            unsigned v;
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
+            if (v >= target) break;
+            __nanosleep(40);
+            if (clock64() - t0 > 4000000000LL) __trap();
+        }
+    }
+    __syncthreads();
 }
 
 // Drop consumed scratch lines from L2 WITHOUT writing them back (the slot is fully rewritten before it is
@@ -494,8 +519,14 @@ fourstep_cluster_kernel(FourStepParams<typename CfgA::T> q) {
     static_assert(CfgA::THREADS == CfgB::THREADS, "both stages must use the same CTA size");
     extern __shared__ __align__(16) unsigned char ssfft_smem[];
     cx<T> *sm = reinterpret_cast<cx<T> *>(ssfft_smem);
-    const int rank = (int)cluster_ctarank(), csize = (int)cluster_nctarank();
-    const long long cid = blockIdx.x / csize, nclusters = gridDim.x / csize;
+    const int crank = (int)cluster_ctarank(), csize0 = (int)cluster_nctarank();
+    const long long cid0 = blockIdx.x / csize0, nclusters0 = gridDim.x / csize0;
+    // group view: `rank` of `csize` CTAs work on a transform, `cid` of `nclusters` groups (a group is one cluster when
+    // group_clusters == 1)
+    const int G = q.group_clusters > 1 ? q.group_clusters : 1;
+    const int rank = (int)(cid0 % G) * csize0 + crank, csize = G * csize0;
+    const long long cid = cid0 / G, nclusters = nclusters0 / G;
+    unsigned bar_target = 0;
     constexpr int F1 = KIND == 0 ? TILE_A_C2C : KIND == 1 ? TILE_A_R2C : TILE_B_C2R;
     constexpr int F2 = KIND == 0 ? TILE_B_C2C : KIND == 1 ? TILE_B_R2C : TILE_A_C2R;
     using Cfg1 = typename std::conditional<KIND == 2, CfgB, CfgA>::type;
@@ -570,7 +601,13 @@ fourstep_cluster_kernel(FourStepParams<typename CfgA::T> q) {
                 tile_body<Cfg1, F1, CfgA::L, CfgB::L, kCtbLog, kStage>(p1, uin, scr, tile * Cfg1::CT, sm, st, hook);
             }
         }
-        cluster_barrier();  // stage-1 stores of every CTA in the cluster are visible; L1 is invalidated
+        // stage-1 stores of every CTA working on this transform are visible (scratch is read through L2: ld.global.cg)
+        if (G == 1) {
+            cluster_barrier();
+        } else {
+            bar_target += (unsigned)csize;
+            group_barrier(q.group_ctr + cid, bar_target);
+        }
         // ---- stage 2 (start rotates so the CTA that gets an extra, ragged tile changes between transforms)
         bool s2_ready = false;
         if constexpr (kStage && !kStage2) prefetch_next_s1();  // stage 2 does not use `st`: overlap all of it
@@ -661,6 +698,7 @@ struct FourStepEntry {
     // returns 0 on success; *clusters_out (may be null) reports how many clusters the launch used
     int (*launch[3])(const void *params, int max_clusters, cudaStream_t s);
     int (*max_clusters[3])(int cluster_size);  // co-resident clusters on the current device
+    int tiles[3][2];  // stage-1 / stage-2 tiles per transform, per kind
 };
 const std::vector<FourStepEntry> &fourstep_registry();
 int fourstep_cluster_size();  // env SSFFT_CLUSTER (default 4)

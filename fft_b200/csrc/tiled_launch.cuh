@@ -89,17 +89,26 @@ int launch_fourstep(const void *params, int max_clusters, cudaStream_t s) {
     const FourStepParams<T> &q = *reinterpret_cast<const FourStepParams<T> *>(params);
     constexpr size_t smem = fourstep_smem_bytes<CfgA, CfgB>();
     const int csize = fourstep_cluster_size();
-    long long clusters = q.batch < max_clusters ? q.batch : max_clusters;
+    // max_clusters = groups * group_clusters (plan time); never start more groups than there are transforms
+    const int G = q.group_clusters > 1 ? q.group_clusters : 1;
+    long long groups = max_clusters / G;
+    if (q.batch < groups) groups = q.batch;
+    long long clusters = groups * G;
     if (clusters <= 0) return 0;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(clusters * csize));
     cfg.blockDim = dim3(CfgA::THREADS);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = s;
-    cudaLaunchAttribute attr[2];
+    cudaLaunchAttribute attr[3];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = csize; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
+    if (G > 1) {  // the software barrier needs every CTA of the grid resident at once
+        attr[1].id = cudaLaunchAttributeCooperative;
+        attr[1].val.cooperative = 1;
+        cfg.numAttrs = 2;
+    }
     // Optional (SSFFT_L2_PERSIST=1): pin the scratch in L2 with a persisting access-policy window.  Measured
     // SLOWER on B200 (65536: 48 % -> 28 % of roofline), so it is off by default; consumed scratch lines are
     // dropped with discard.global.L2 inside the kernel instead.
@@ -120,7 +129,7 @@ int launch_fourstep(const void *params, int max_clusters, cudaStream_t s) {
             max_window = (size_t)max_win;
         }
     }
-    if (persist_state == 1) {
+    if (persist_state == 1 && G == 1) {
         size_t bytes = (size_t)2 * (size_t)clusters * (size_t)q.scratch_per * sizeof(cx<T>);
         if (bytes > max_window) bytes = max_window;
         attr[1].id = cudaLaunchAttributeAccessPolicyWindow;
@@ -147,6 +156,13 @@ FourStepEntry make_fourstep_entry(const char *name) {
     e.max_clusters[0] = &fourstep_max_clusters<CfgA, CfgB, 0>;
     e.max_clusters[1] = &fourstep_max_clusters<CfgA, CfgB, 1>;
     e.max_clusters[2] = &fourstep_max_clusters<CfgA, CfgB, 2>;
+    // tiles per transform of each stage (same formulas as the kernel)
+    e.tiles[0][0] = (tile_width<TILE_A_C2C>(CfgA::L, CfgB::L) + CfgA::CT - 1) / CfgA::CT;
+    e.tiles[0][1] = (tile_width<TILE_B_C2C>(CfgA::L, CfgB::L) + CfgB::CT - 1) / CfgB::CT;
+    e.tiles[1][0] = (tile_width<TILE_A_R2C>(CfgA::L, CfgB::L) + CfgA::CT - 1) / CfgA::CT;
+    e.tiles[1][1] = (tile_width<TILE_B_R2C>(CfgA::L, CfgB::L) + CfgB::CT - 1) / CfgB::CT;
+    e.tiles[2][0] = (tile_width<TILE_B_C2R>(CfgA::L, CfgB::L) + CfgB::CT - 1) / CfgB::CT;
+    e.tiles[2][1] = (tile_width<TILE_A_C2R>(CfgA::L, CfgB::L) + CfgA::CT - 1) / CfgA::CT;
     return e;
 }
 
