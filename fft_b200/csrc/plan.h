@@ -50,6 +50,7 @@ struct ssfft_plan {
     int ctb_log2 = 0;                      // tile-major block height (lanes of the row-stage kernel)
     int fs_id = -1;                        // cluster kernel (both stages in one launch), -1 = two launches per chunk
     int fs_clusters = 0;                   // co-resident clusters of the persistent launch
+    int fs_csize = 4;                      // CTAs per cluster
     int fs_group[3] = {1, 1, 1};           // clusters that share one transform, per kind (keeps the scratch in L2)
     void *d_fs_ctr = nullptr;              // group barrier counters
     void *d_ep_lo = nullptr, *d_ep_hi = nullptr;

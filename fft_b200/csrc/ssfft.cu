@@ -203,7 +203,12 @@ int setup_tiled(ssfft_plan *pl, size_t total, bool real, bool *ok) {
     pl->fs_id = find_fourstep<T>(n1, n2);
     if (pl->fs_id >= 0) {
         const FourStepEntry &fe = fourstep_registry()[pl->fs_id];
-        const int cs = fourstep_cluster_size();
+        // CTAs per cluster.  Real 65536 has 8 + 9 tiles per transform: with 4 CTAs one of them runs 3 row tiles while
+        // the others run 2 and everyone waits at the next cluster barrier; pairs split 4+4 / 5+4 (measured R2C
+        // 35.3 -> 39.7 %, C2R 32.7 -> 36.4 % of roofline).  SSFFT_CLUSTER overrides.
+        int cs = fourstep_cluster_size();
+        if (!getenv("SSFFT_CLUSTER") && real && total == 65536) cs = 2;
+        pl->fs_csize = cs;
         int clusters = 1 << 30;
         for (int kind = real ? 1 : 0; kind <= (real ? 2 : 0); ++kind) {
             int m = fe.max_clusters[kind](cs);
@@ -259,6 +264,7 @@ int exec_tiled(ssfft_plan *pl, int kind, const void *in, void *out, long long ba
         q.n1 = n1; q.n2 = n2; q.batch = batch; q.user_stride = user_stride; q.scratch_per = sp; q.inverse = inverse;
         q.ctb_log2 = pl->ctb_log2;
         q.discard = env_int("SSFFT_DISCARD", 1);
+        q.cluster_size = pl->fs_csize;
         q.group_clusters = pl->fs_group[kind];
         q.group_ctr = (unsigned *)pl->d_fs_ctr;
         const int groups = pl->fs_clusters / q.group_clusters;
@@ -422,7 +428,7 @@ int build_plan_typed(ssfft_plan *pl) {
             snprintf(buf, sizeof(buf), "%s N=%zu four-step n1=%zu x n2=%zu, one persistent launch %s, clusters of %d CTAs x %d, "
                      "%d cluster(s) per transform, L2-resident scratch %.1f MiB", pl->kind == SSFFT_C2C ? "complex" : "real",
                      pl->kind == SSFFT_C2C ? n : pl->n_real, pl->n1, pl->n2, fourstep_registry()[pl->fs_id].name,
-                     fourstep_cluster_size(), pl->fs_clusters, pl->fs_group[pl->kind == SSFFT_C2C ? 0 : 1],
+                     pl->fs_csize, pl->fs_clusters, pl->fs_group[pl->kind == SSFFT_C2C ? 0 : 1],
                      2.0 * (pl->fs_clusters / pl->fs_group[pl->kind == SSFFT_C2C ? 0 : 1]) * pl->scratch_per * sizeof(cx<T>) / 1048576.0);
         else
             snprintf(buf, sizeof(buf), "%s N=%zu four-step tiles n1=%zu (%s) x n2=%zu (%s) chunk=%zu L2-resident scratch",

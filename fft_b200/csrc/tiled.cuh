@@ -432,6 +432,7 @@ struct FourStepParams {
     // of all transforms in flight (2 slots per group) stays inside the L2 instead of spilling to HBM.
     int group_clusters;
     unsigned *group_ctr;  // one zero-initialised counter per group
+    int cluster_size;     // CTAs per hardware cluster of this launch (host side only)
 };
 
 __device__ __forceinline__ unsigned cluster_ctarank() {

@@ -88,7 +88,7 @@ int launch_fourstep(const void *params, int max_clusters, cudaStream_t s) {
     using T = typename CfgA::T;
     const FourStepParams<T> &q = *reinterpret_cast<const FourStepParams<T> *>(params);
     constexpr size_t smem = fourstep_smem_bytes<CfgA, CfgB>();
-    const int csize = fourstep_cluster_size();
+    const int csize = q.cluster_size > 0 ? q.cluster_size : fourstep_cluster_size();
     // max_clusters = groups * group_clusters (plan time); never start more groups than there are transforms
     const int G = q.group_clusters > 1 ? q.group_clusters : 1;
     long long groups = max_clusters / G;
