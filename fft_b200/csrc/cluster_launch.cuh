@@ -5,6 +5,7 @@
 #include <cstring>
 
 #include "cluster.cuh"
+#include "tma_host.cuh"
 
 namespace ssfft {
 
@@ -35,37 +36,11 @@ int cluster_max_clusters() {
     return n;
 }
 
-// Tensor map of the input seen as (batch, N1, N2) elements of 8 bytes (16 for fp64), box = one CTA's [N1][CT1] tile.
-// cuTensorMapEncodeTiled is a driver entry point: fetched through the runtime so libcuda is not a link dependency.
-typedef CUresult (*ssfft_encode_tiled_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
-                                          const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
-                                          CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-inline ssfft_encode_tiled_fn tensor_map_encoder() {
-    static ssfft_encode_tiled_fn fn = [] {
-        void *p = nullptr;
-        cudaDriverEntryPointQueryResult qres;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess ||
-            qres != cudaDriverEntryPointSuccess) {
-            cudaGetLastError();
-            p = nullptr;
-        }
-        return (ssfft_encode_tiled_fn)p;
-    }();
-    return fn;
-}
+// Tensor map of the input seen as (batch, N1, N2) elements of 8 bytes, box = one CTA's [N1][CT1] tile (tma_host.cuh).
 template <typename Cfg>
 bool make_input_tensor_map(CUtensorMap *tm, const void *in, long long batch) {
-    using T = typename Cfg::T;
-    if (sizeof(cx<T>) != 8) return false;  // 8-byte elements only (fp32 complex)
-    ssfft_encode_tiled_fn enc = tensor_map_encoder();
-    if (!enc || (reinterpret_cast<uintptr_t>(in) & 15u) || batch <= 0 || batch > 0x7fffffffLL) return false;
-    const cuuint64_t dims[3] = {(cuuint64_t)Cfg::N2, (cuuint64_t)Cfg::N1, (cuuint64_t)batch};
-    const cuuint64_t strides[2] = {(cuuint64_t)Cfg::N2 * sizeof(cx<T>), (cuuint64_t)Cfg::N * sizeof(cx<T>)};
-    const cuuint32_t box[3] = {(cuuint32_t)Cfg::CT1, (cuuint32_t)Cfg::N1, 1u};
-    const cuuint32_t estr[3] = {1u, 1u, 1u};
-    return enc(tm, CU_TENSOR_MAP_DATA_TYPE_UINT64, 3, const_cast<void *>(in), dims, strides, box, estr,
-               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+    if (sizeof(cx<typename Cfg::T>) != 8) return false;  // 8-byte elements only (fp32 complex)
+    return encode_tensor_map_3d(tm, in, batch, Cfg::N1, Cfg::N2, Cfg::N1, Cfg::CT1);
 }
 
 // one persistent launch: min(batch, co-resident clusters) clusters loop over the transforms

@@ -234,6 +234,7 @@ int setup_tiled(ssfft_plan *pl, size_t total, bool real, bool *ok) {
                 if (clusters / g > max_groups) max_groups = clusters / g;
             }
             CU(cudaMalloc(&pl->d_scratch, (size_t)2 * max_groups * per));
+            pl->chunk = (size_t)2 * max_groups;  // transforms the scratch holds (two-launch fallback path)
             CU(cudaMalloc(&pl->d_fs_ctr, (size_t)max_groups * sizeof(unsigned)));
         } else {
             pl->fs_id = -1;  // clusters of this size cannot be scheduled here
@@ -270,10 +271,14 @@ int exec_tiled(ssfft_plan *pl, int kind, const void *in, void *out, long long ba
         const int groups = pl->fs_clusters / q.group_clusters;
         if (q.group_clusters > 1) CU(cudaMemsetAsync(pl->d_fs_ctr, 0, (size_t)groups * sizeof(unsigned), s));
         int rc = fourstep_registry()[pl->fs_id].launch[kind](&q, groups * q.group_clusters, s);
-        ++g_launches;
-        if (rc) return cuda_fail(cudaGetLastError(), "fourstep_cluster_kernel launch");
-        return SSFFT_OK;
+        if (rc != 3) {
+            ++g_launches;
+            if (rc) return cuda_fail(cudaGetLastError(), "fourstep_cluster_kernel launch");
+            return SSFFT_OK;
+        }
+        // rc == 3: no tensor map for this input (pointer not 16-byte aligned): two launches per chunk instead
     }
+    if (pl->chunk < 1) return SSFFT_ERR_INVALID;
     for (long long b0 = 0; b0 < batch; b0 += (long long)pl->chunk) {
         const long long nb = (batch - b0 < (long long)pl->chunk) ? batch - b0 : (long long)pl->chunk;
         const cx<T> *cin = (const cx<T> *)in + b0 * user_stride;

@@ -25,12 +25,24 @@
 //   B_C2R       N2          k1 <= N1/2             packed half spectrum       U[k1][n2] * conj W        (scratch)
 //   A_C2R       N1          n2/2 (column pairs)    U (Hermitian-extended)     real x as complex pairs
 #pragma once
+#include <cuda.h>  // CUtensorMap (types only)
 #include <cuda_runtime.h>
 
 #include <type_traits>
 
 #include "codelets.cuh"
 #include "fused.cuh"
+
+// Same double buffering, but the tile is brought by the TMA engine: ONE tensor copy (stage 1: box [N1][CT] of the
+// (batch, N1, N2) input) or ONE bulk copy (stage 2: the contiguous tile-major scratch block) per tile, signalled
+// through an mbarrier -- no per-thread copy instructions, no registers.  Staging layout is dense ([idx][CT]).
+// MEASURED on B200 (profiles/sweep_fourstep_tma_r01_float32.json): no gain for complex (65536: 50.1 % vs 50.5 %,
+// 32768: 45.5 % both) and a loss for real 65536 (3.45 -> 4.03 ms per forward+inverse): with 3 CTAs/SM the loads of one
+// CTA already overlap the butterflies of the others, the kernels are bound by issue slots and dependent latency.
+// Off by default; parity tests pass with it on.
+#ifndef SSFFT_FOURSTEP_TMA
+#define SSFFT_FOURSTEP_TMA 0
+#endif
 
 namespace ssfft {
 
@@ -279,7 +291,7 @@ __device__ __forceinline__ void tile_body(const TileParams<typename Cfg::T> &p, 
                             const int idx = t + TX * u + NR * j;
                             cx<T> x;
                             if constexpr (STAGED) {
-                                x = st[idx * PITCH + c];
+                                x = st[idx * (SSFFT_FOURSTEP_TMA ? CT : PITCH) + c];
                             } else {
                                 const cx<T> *src = tile_src<FLAVOR, L>(gin, lane, idx, n1, n2, ctb);
                                 if constexpr (FLAVOR == TILE_B_C2C || FLAVOR == TILE_B_R2C) x = ld_l2(src);
@@ -396,7 +408,7 @@ __device__ __forceinline__ void tile_body(const TileParams<typename Cfg::T> &p, 
 template <typename Cfg, int FLAVOR>
 __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINB) tile_fft_kernel(TileParams<typename Cfg::T> p) {
     using T = typename Cfg::T;
-    extern __shared__ __align__(16) unsigned char ssfft_smem[];
+    extern __shared__ __align__(128) unsigned char ssfft_smem[];
     cx<T> *sm = reinterpret_cast<cx<T> *>(ssfft_smem);
     const int width = tile_width<FLAVOR>(p.n1, p.n2);
     const int tiles = (width + Cfg::CT - 1) / Cfg::CT;
@@ -433,6 +445,7 @@ struct FourStepParams {
     int group_clusters;
     unsigned *group_ctr;  // one zero-initialised counter per group
     int cluster_size;     // CTAs per hardware cluster of this launch (host side only)
+    int use_tma;          // the tensor map passed next to these parameters is valid (set by the launcher)
 };
 
 __device__ __forceinline__ unsigned cluster_ctarank() {
@@ -491,7 +504,7 @@ __device__ __forceinline__ void discard_lines(const cx<T> *base, long long first
 #endif
 template <typename CfgA, typename CfgB>
 __host__ __device__ constexpr bool fourstep_staged() {
-    return SSFFT_FOURSTEP_STAGED && sizeof(typename CfgA::T) == 4 &&
+    return (SSFFT_FOURSTEP_STAGED || SSFFT_FOURSTEP_TMA) && sizeof(typename CfgA::T) == 4 &&
            2 * (CfgA::smem_bytes > CfgB::smem_bytes ? CfgA::smem_bytes : CfgB::smem_bytes) *
                    (size_t)(CfgA::MINB < CfgB::MINB ? CfgA::MINB : CfgB::MINB) <= 220 * 1024;
 }
@@ -515,10 +528,11 @@ __host__ __device__ constexpr int fourstep_minb() {
 
 template <typename CfgA, typename CfgB, int KIND>
 __global__ void __launch_bounds__(CfgA::THREADS, (fourstep_minb<CfgA, CfgB>()))
-fourstep_cluster_kernel(FourStepParams<typename CfgA::T> q) {
+fourstep_cluster_kernel(FourStepParams<typename CfgA::T> q, const __grid_constant__ CUtensorMap tmap) {
     using T = typename CfgA::T;
     static_assert(CfgA::THREADS == CfgB::THREADS, "both stages must use the same CTA size");
-    extern __shared__ __align__(16) unsigned char ssfft_smem[];
+    extern __shared__ __align__(128) unsigned char ssfft_smem[];
+    __shared__ __align__(8) unsigned long long stage_bar;
     cx<T> *sm = reinterpret_cast<cx<T> *>(ssfft_smem);
     const int crank = (int)cluster_ctarank(), csize0 = (int)cluster_nctarank();
     const long long cid0 = blockIdx.x / csize0, nclusters0 = gridDim.x / csize0;
@@ -545,10 +559,55 @@ fourstep_cluster_kernel(FourStepParams<typename CfgA::T> q) {
     // cp.async double buffering: the next tile's inputs stream into `st` while the current tile is transformed.
     // Enabled when two tile buffers per CTA still leave room for the CTAs/SM the launch bounds ask for.
     constexpr size_t kTileBytes = CfgA::smem_bytes > CfgB::smem_bytes ? CfgA::smem_bytes : CfgB::smem_bytes;
-    constexpr bool kStage = fourstep_staged<CfgA, CfgB>();
+    constexpr bool kTma = SSFFT_FOURSTEP_TMA != 0;
+    // (C2R gathers a Hermitian-extended spectrum and builds its second stage in shared memory: not staged by TMA)
+    constexpr bool kStage = fourstep_staged<CfgA, CfgB>() && (!kTma || KIND != 2);
     constexpr bool kStage2 = kStage && (F2 != TILE_A_C2R);  // A_C2R builds its input in shared memory itself
     cx<T> *st = reinterpret_cast<cx<T> *>(ssfft_smem + kTileBytes);
     bool s1_ready = false;  // the first stage-1 tile of the coming transform is already in flight
+    unsigned st_par = 0;
+    const bool tid0 = (threadIdx.x == 0 && threadIdx.y == 0);
+    if constexpr (kStage && kTma) {
+        if (tid0) mbar_init(&stage_bar, 1);
+        __syncthreads();
+    }
+    // request the first-pass inputs of a tile into `st`
+    auto issue_s1 = [&](long long Bx, int tile) {  // stage-1 tile `tile` of transform Bx (user buffer)
+        if constexpr (kTma) {
+            if (tid0) {
+                constexpr unsigned bytes = (unsigned)(Cfg1::L * Cfg1::CT * sizeof(cx<T>));
+                mbar_expect_tx(&stage_bar, bytes);
+                asm volatile(
+                    "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+                        smem_u32(st)),
+                    "l"(reinterpret_cast<unsigned long long>(&tmap)), "r"(tile * Cfg1::CT), "r"(0), "r"((int)Bx), "r"(smem_u32(&stage_bar))
+                    : "memory");
+            }
+        } else {
+            tile_prefetch<Cfg1, F1, CfgA::L, CfgB::L, kCtbLog>(p1, q.in + Bx * q.user_stride, tile * Cfg1::CT, st);
+        }
+    };
+    auto issue_s2 = [&](const cx<T> *scr_, int tile) {  // stage-2 tile: one contiguous tile-major scratch block
+        if constexpr (kTma) {
+            if (tid0) {
+                constexpr unsigned bytes = (unsigned)(Cfg2::L * Cfg2::CT * sizeof(cx<T>));
+                mbar_expect_tx(&stage_bar, bytes);
+                asm volatile("fence.proxy.async;" ::: "memory");  // peers' generic-proxy scratch stores -> async-proxy read
+                bulk_g2s(st, scr_ + (long long)tile * Cfg2::CT * Cfg2::L, bytes, &stage_bar);
+            }
+        } else {
+            tile_prefetch<Cfg2, F2, CfgA::L, CfgB::L, kCtbLog>(p2, scr_, tile * Cfg2::CT, st);
+        }
+    };
+    auto stage_wait = [&]() {
+        if constexpr (kTma) {
+            mbar_wait(&stage_bar, st_par);
+            st_par ^= 1u;
+        } else {
+            cp_async_wait_all();
+            __syncthreads();
+        }
+    };
     // register double buffering (the adopted overlap scheme): next tile's inputs are loaded into a second register
     // set while the current tile is transformed; 2 CTAs/SM at <= 128 registers instead of 3 at 80.
     constexpr bool kRegPf = fourstep_regprefetch<CfgA, CfgB>();
@@ -565,7 +624,7 @@ fourstep_cluster_kernel(FourStepParams<typename CfgA::T> q) {
         auto prefetch_next_s1 = [&]() {
             if constexpr (kStage) {
                 if (Bn < q.batch && rank < tiles1) {
-                    tile_prefetch<Cfg1, F1, CfgA::L, CfgB::L, kCtbLog>(p1, uin_next, rank * Cfg1::CT, st);
+                    issue_s1(Bn, rank);
                     s1_ready = true;
                 }
             }
@@ -585,16 +644,15 @@ fourstep_cluster_kernel(FourStepParams<typename CfgA::T> q) {
                                                                                 NoHook(), vc);
             } else {
                 if constexpr (kStage) {
-                    if (!s1_ready) tile_prefetch<Cfg1, F1, CfgA::L, CfgB::L, kCtbLog>(p1, uin, tile * Cfg1::CT, st);
+                    if (!s1_ready) issue_s1(B, tile);
                     s1_ready = false;
-                    cp_async_wait_all();
-                    __syncthreads();
+                    stage_wait();
                 }
                 const int next = tile + csize;
                 auto hook = [&]() {
                     if constexpr (kStage) {
                         if (next < tiles1) {
-                            tile_prefetch<Cfg1, F1, CfgA::L, CfgB::L, kCtbLog>(p1, uin, next * Cfg1::CT, st);
+                            issue_s1(B, next);
                             s1_ready = true;
                         }
                     }
@@ -639,15 +697,14 @@ fourstep_cluster_kernel(FourStepParams<typename CfgA::T> q) {
                     }
                 }
                 if constexpr (kStage2) {
-                    if (!s2_ready) tile_prefetch<Cfg2, F2, CfgA::L, CfgB::L, kCtbLog>(p2, scr, tile * Cfg2::CT, st);
+                    if (!s2_ready) issue_s2(scr, tile);
                     s2_ready = false;
-                    cp_async_wait_all();
-                    __syncthreads();
+                    stage_wait();
                 }
                 auto hook = [&]() {
                     if constexpr (kStage2) {
                         if (inext < tiles2) {
-                            tile_prefetch<Cfg2, F2, CfgA::L, CfgB::L, kCtbLog>(p2, scr, (int)((inext + B) % tiles2) * Cfg2::CT, st);
+                            issue_s2(scr, (int)((inext + B) % tiles2));
                             s2_ready = true;
                         } else {
                             prefetch_next_s1();
@@ -673,7 +730,7 @@ fourstep_cluster_kernel(FourStepParams<typename CfgA::T> q) {
             }
         }
     }
-    if constexpr (kStage) cp_async_wait_all();
+    if constexpr (kStage && !kTma) cp_async_wait_all();
 }
 
 #endif  // __CUDACC__

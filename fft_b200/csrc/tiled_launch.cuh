@@ -2,7 +2,10 @@
 #pragma once
 #include <cstdlib>
 
+#include <cstring>
+
 #include "tiled.cuh"
+#include "tma_host.cuh"
 
 namespace ssfft {
 
@@ -140,7 +143,17 @@ int launch_fourstep(const void *params, int max_clusters, cudaStream_t s) {
         attr[1].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
         cfg.numAttrs = 2;
     }
-    return cudaLaunchKernelEx(&cfg, fourstep_cluster_kernel<CfgA, CfgB, KIND>, q) == cudaSuccess ? 0 : 2;
+    // staged variants: stage-1 tiles come through a tensor map of the user input, [batch][N1][W] complex
+    CUtensorMap tmap;
+    memset(&tmap, 0, sizeof(tmap));
+    FourStepParams<T> qq = q;
+    qq.use_tma = 0;
+    if (SSFFT_FOURSTEP_TMA && fourstep_staged<CfgA, CfgB>() && KIND != 2) {
+        const int W = KIND == 0 ? CfgB::L : CfgB::L / 2;
+        if (!encode_tensor_map_3d(&tmap, q.in, q.batch, CfgA::L, W, CfgA::L, CfgA::CT)) return 3;  // caller falls back
+        qq.use_tma = 1;
+    }
+    return cudaLaunchKernelEx(&cfg, fourstep_cluster_kernel<CfgA, CfgB, KIND>, qq, tmap) == cudaSuccess ? 0 : 2;
 }
 
 template <typename CfgA, typename CfgB>
