@@ -275,6 +275,9 @@ class DistFFT1D:
             return pl._plan
 
         bufA, bufB = pb.local[0], pb.local[1]
+        # every rank has finished reading its exchange buffers in the previous call (its copy-out of buffer A) before
+        # anyone stores into them again
+        pb.barrier()
         mark("start")
         # exchange 1: x[a][n2] -> peers' A as [b][n1]  (my rows land at columns r*a ..)
         L.check(lib.ssfft_exchange_transpose(x_local.data_ptr(), pb.tables[0], self.world, a, n2, n1, r * a, 0, 0, 0, prec,
