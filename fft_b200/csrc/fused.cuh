@@ -154,6 +154,8 @@ fused_fft_kernel(const cx<typename Cfg::T> *__restrict__ in, cx<typename Cfg::T>
 
     // one thread asks the TMA engine for a whole group of transforms (contiguous in HBM).  Bulk copies
     // move multiples of 16 bytes: a ragged last group of an odd-length size falls back to plain loads.
+    // (the source must be 16-byte aligned as well: a user pointer offset by one complex element uses plain loads)
+    const bool in_aligned = (reinterpret_cast<unsigned long long>(in) & 15ull) == 0;
     auto group_bytes = [&](long long g) -> unsigned {
         const long long first_tr = g * FPB;
         const long long cnt = (batch - first_tr < FPB) ? (batch - first_tr) : FPB;
@@ -162,7 +164,7 @@ fused_fft_kernel(const cx<typename Cfg::T> *__restrict__ in, cx<typename Cfg::T>
     auto prefetch = [&](long long g) {
         if (leader && g < groups) {
             const unsigned bytes = group_bytes(g);
-            if (bytes % 16 == 0) {
+            if (bytes % 16 == 0 && in_aligned) {
                 mbar_expect_tx(&mbar, bytes);
                 bulk_g2s(const_cast<cx<T> *>(stage_all), in + g * FPB * N, bytes, &mbar);
             }
@@ -182,7 +184,7 @@ fused_fft_kernel(const cx<typename Cfg::T> *__restrict__ in, cx<typename Cfg::T>
         cx<T> v[E];
         if constexpr (PF) {
             const unsigned bytes = group_bytes(g);
-            if (bytes % 16 == 0) {
+            if (bytes % 16 == 0 && in_aligned) {
                 mbar_wait(&mbar, parity);  // this group's input has landed in the staging buffer
                 parity ^= 1u;
             } else {  // ragged tail: cooperative plain copy into the staging buffer
