@@ -394,3 +394,26 @@ def test_pointers_offset_by_one_element(oracle, cuda_device):
         r.fft(xin, spec)
         torch.cuda.synchronize()
         assert oracle.rel_l2(spec.cpu().numpy(), oracle.rfft(xr)) <= tol(n, np.float32), n
+
+
+def test_in_place_device_transforms(oracle, cuda_device):
+    """The reference is out-of-place only (input must not alias output); the device path also accepts in == out:
+    every kernel has consumed a transform's input before it stores the first output of that transform."""
+    for n in (64, 1000, 4096, 16384, 32768, 65536, 2 ** 18):
+        batch = 7
+        x = oracle.uniform_complex((batch, n), SEED, np.complex64)
+        xd = torch.from_numpy(x).cuda()
+        f = fft_b200.FFT(n)
+        f.fft(xd, xd)
+        torch.cuda.synchronize()
+        ref = oracle.run(oracle.KIND_C2C_FWD, x, n, threads=4)[0]
+        assert oracle.rel_l2(xd.cpu().numpy(), ref) <= tol(n, np.complex64), (n, f.describe())
+    for n in (256, 4096, 65536):
+        batch = 5
+        xr = oracle.uniform(batch * n, SEED, np.float32).reshape(batch, n)
+        buf = torch.from_numpy(xr).cuda()
+        r = fft_b200.RealFFT(n)
+        spec = buf.view(torch.complex64)  # same bytes: N reals -> N/2 complex per transform
+        r.fft(buf, spec)
+        torch.cuda.synchronize()
+        assert oracle.rel_l2(spec.cpu().numpy(), oracle.rfft(xr)) <= tol(n, np.float32), (n, r.describe())
