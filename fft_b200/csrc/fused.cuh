@@ -380,6 +380,7 @@ struct FusedEntry {
     const char *name;
     int tw_total;  // cx elements
     int radix[4], np;
+    int real_only;  // 1: tuned for the R2C / C2R flavours, picked for real plans only (the C2C entry of the size differs)
     int (*launch)(const void *tw, const void *in, void *out, long long batch, int inverse, int mode, const void *rtw,
                   cudaStream_t s);
 };
@@ -387,13 +388,18 @@ struct FusedEntry {
 const std::vector<FusedEntry> &fused_registry();
 int fused_waves();  // resident-CTA waves per launch before CTAs loop (env SSFFT_FUSED_WAVES, default 4)
 
+// for_real: the plan is a RealFFT -- prefer an entry tuned for the real flavours when the size has one
 template <typename T>
-inline int find_fused(size_t n, int /*layout*/) {
+inline int find_fused(size_t n, int for_real) {
     const int prec = sizeof(T) == 4 ? 0 : 1;
     const auto &reg = fused_registry();
+    int any = -1;
     for (size_t i = 0; i < reg.size(); ++i)
-        if (reg[i].prec == prec && (size_t)reg[i].n == n) return (int)i;
-    return -1;
+        if (reg[i].prec == prec && (size_t)reg[i].n == n) {
+            if (reg[i].real_only) { if (for_real) return (int)i; }
+            else if (any < 0) any = (int)i;
+        }
+    return any;
 }
 inline const char *fused_name(int id) { return fused_registry()[id].name; }
 

@@ -54,6 +54,7 @@ FusedEntry make_entry(const char *name) {
     e.tw_total = Cfg::tw_total;
     e.np = Cfg::NP;
     for (int i = 0; i < 4; ++i) e.radix[i] = Cfg::radix(i);
+    e.real_only = 0;
     e.launch = &launch_cfg<Cfg>;
     return e;
 }
@@ -67,5 +68,15 @@ FusedEntry make_entry(const char *name) {
 // same, with the TMA bulk-copy prefetch of the next transform group (cp.async.bulk + mbarrier)
 #define SSFFT_FUSED_PF(T, N, R0, R1, R2, R3, TX, FPB, MINB) \
     make_entry<FusedCfg<T, N, R0, R1, R2, R3, TX, FPB, MINB, 4, 1>>(#T "_" #N "_" #R0 "x" #R1 "x" #R2 "x" #R3 "_tma")
+
+template <typename Cfg>
+FusedEntry make_real_entry(const char *name) {
+    FusedEntry e = make_entry<Cfg>(name);
+    e.real_only = 1;
+    return e;
+}
+// entry used for RealFFT plans only (R2C epilogue / C2R on-the-fly gather have their own optimum: tools/kbench.cu real)
+#define SSFFT_FUSED_REAL(T, N, R0, R1, R2, R3, TX, FPB, MINB, PADS, PF) \
+    make_real_entry<FusedCfg<T, N, R0, R1, R2, R3, TX, FPB, MINB, PADS, PF>>(#T "_" #N "_" #R0 "x" #R1 "x" #R2 "x" #R3 "_p" #PADS "_tma" #PF "_real")
 
 }  // namespace ssfft

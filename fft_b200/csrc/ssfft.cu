@@ -440,10 +440,10 @@ int build_plan_typed(ssfft_plan *pl) {
                      pl->kind == SSFFT_C2C ? "complex" : "real", pl->kind == SSFFT_C2C ? n : pl->n_real, pl->n1,
                      tile_registry()[pl->tile_a].name, pl->n2, tile_registry()[pl->tile_b].name, pl->chunk);
         pl->desc = buf;
-    } else if (n <= limit || find_fused<T>(n, FUSED_CONTIG) >= 0) {
+    } else if (n <= limit || find_fused<T>(n, pl->kind != SSFFT_C2C ? 1 : 0) >= 0) {
         pl->four_step = false;
         int rc = SSFFT_OK;
-        pl->fused.id = find_fused<T>(n, FUSED_CONTIG);
+        pl->fused.id = find_fused<T>(n, pl->kind != SSFFT_C2C ? 1 : 0);
         if (pl->fused.id >= 0) {
             rc = build_fused_twiddles<T>(pl->fused.id, &pl->fused.d_twiddles);
             if (rc) return rc;

@@ -47,17 +47,34 @@ __global__ void diff_kernel(const float *a, const float *b, size_t n, unsigned *
 static void *g_ref = nullptr; static int g_ref_n = 0; static size_t g_ref_sz = 0;
 static unsigned *g_maxbits = nullptr;
 
+static int g_mode = 0;            // FUSED_C2C / FUSED_R2C / FUSED_C2R
+static const void *g_rtw = nullptr;  // RealFFT twiddles for the current complex length
+
+template <typename T>
+void *make_rtw(int n_complex) {
+    std::vector<T> h(2 * (size_t)(n_complex / 2 + 1));
+    fill_real_twiddles<T>(h.data(), 2 * (size_t)n_complex, false);
+    void *d; cudaMalloc(&d, h.size() * sizeof(T));
+    cudaMemcpy(d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice);
+    return d;
+}
+
 template <typename Cfg>
 void bench(const char *name, const void *in, void *out, long long batch, int waves, int iters = 10) {
     using T = typename Cfg::T;
     g_waves = waves;
     void *tw = make_tw<Cfg>();
-    int rc = launch_cfg<Cfg>(tw, in, out, batch, 0, 0, nullptr, 0);
+    void *rtw = g_mode ? make_rtw<T>(Cfg::N) : nullptr;
+    g_rtw = rtw;
+    const int inv_ = g_mode == 2 ? 1 : 0;
+#define launch_cfg_m(tw_, in_, out_, batch_) launch_cfg<Cfg>(tw_, in_, out_, batch_, inv_, g_mode, g_rtw, 0)
+    int rc = launch_cfg_m(tw, in, out, batch);
     if (rc || cudaDeviceSynchronize() != cudaSuccess) { printf("%-40s FAILED rc=%d %s\n", name, rc, cudaGetErrorString(cudaGetLastError())); return; }
-    for (int i = 0; i < 2; ++i) launch_cfg<Cfg>(tw, in, out, batch, 0, 0, nullptr, 0);
+    for (int i = 0; i < 2; ++i) launch_cfg_m(tw, in, out, batch);
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
     cudaEventRecord(e0);
-    for (int i = 0; i < iters; ++i) launch_cfg<Cfg>(tw, in, out, batch, 0, 0, nullptr, 0);
+    for (int i = 0; i < iters; ++i) launch_cfg_m(tw, in, out, batch);
+#undef launch_cfg_m
     cudaEventRecord(e1); cudaEventSynchronize(e1);
     float ms; cudaEventElapsedTime(&ms, e0, e1); ms /= iters;
     int occ = 0;
@@ -69,8 +86,8 @@ void bench(const char *name, const void *in, void *out, long long batch, int wav
     float maxdiff = -1.f;
     if (sizeof(T) == 4) {
         if (!g_ref) { cudaMalloc(&g_ref, cmp_floats * 4); cudaMalloc(&g_maxbits, 4); }
-        if (g_ref_n != Cfg::N || g_ref_sz != sizeof(T)) {
-            cudaMemcpy(g_ref, out, cmp_floats * 4, cudaMemcpyDeviceToDevice); g_ref_n = Cfg::N; g_ref_sz = sizeof(T);
+        if (g_ref_n != Cfg::N + 100000 * g_mode || g_ref_sz != sizeof(T)) {
+            cudaMemcpy(g_ref, out, cmp_floats * 4, cudaMemcpyDeviceToDevice); g_ref_n = Cfg::N + 100000 * g_mode; g_ref_sz = sizeof(T);
         } else {
             cudaMemset(g_maxbits, 0, 4);
             diff_kernel<<<1184, 256>>>((const float *)out, (const float *)g_ref, cmp_floats, g_maxbits);
@@ -78,7 +95,8 @@ void bench(const char *name, const void *in, void *out, long long batch, int wav
             memcpy(&maxdiff, &bits, 4);
         }
     }
-    printf("%-46s waves=%d  %8.4f ms  %7.1f GB/s  frac %.3f  regs=%d occ=%d smem=%zu  maxdiff=%g\n", name, waves, ms,
+    if (rtw) cudaFree(rtw);
+    printf("%s %-46s waves=%d  %8.4f ms  %7.1f GB/s  frac %.3f  regs=%d occ=%d smem=%zu  maxdiff=%g\n", g_mode == 0 ? "C2C" : g_mode == 1 ? "R2C" : "C2R", name, waves, ms,
            bytes / ms / 1e6, bytes / ms / 1e6 / 6528.1, fa.numRegs, occ, Cfg::smem_bytes, maxdiff);
     cudaFree(tw);
 }
@@ -149,6 +167,35 @@ int main(int argc, char **argv) {
         P(float, 6000, 10, 10, 10, 6, 200, 1, 2, 4, 4);
         P(float, 6000, 10, 10, 10, 6, 200, 1, 3, 4, 4);
         P(float, 6000, 10, 10, 10, 6, 200, 2, 1, 4, 4);
+    }
+    if (w == "real") {
+        // real transforms of length 2N through the fused kernel of complex length N: R2C epilogue / C2R on-the-fly gather
+        for (int mode = 1; mode <= 2; ++mode) {
+            g_mode = mode;
+            B(float, 128, 16, 8, 1, 1, 8, 32, 2, 4, 4);   // registered
+            B(float, 128, 16, 8, 1, 1, 8, 32, 3, 4, 4);
+            B(float, 128, 16, 8, 1, 1, 8, 16, 4, 4, 4);
+            B(float, 128, 16, 8, 1, 1, 8, 16, 6, 4, 4);
+            B(float, 128, 8, 16, 1, 1, 8, 32, 3, 4, 4);
+            B(float, 128, 8, 4, 4, 1, 16, 16, 4, 4, 4);
+            B(float, 128, 8, 4, 4, 1, 16, 16, 6, 4, 4);
+            B(float, 512, 32, 16, 1, 1, 16, 8, 4, 5, 4);  // registered
+            P(float, 512, 32, 16, 1, 1, 16, 8, 3, 5, 4);
+            B(float, 512, 16, 16, 2, 1, 32, 4, 3, 4, 4);
+            B(float, 512, 16, 16, 2, 1, 32, 4, 4, 4, 4);
+            B(float, 512, 8, 8, 8, 1, 64, 4, 4, 4, 4);
+            B(float, 512, 8, 8, 8, 1, 64, 4, 6, 4, 4);
+            P(float, 512, 8, 8, 8, 1, 64, 4, 4, 4, 4);
+            B(float, 2048, 16, 16, 8, 1, 128, 1, 6, 4, 4);  // registered
+            P(float, 2048, 16, 16, 8, 1, 128, 2, 3, 4, 4);
+            P(float, 4096, 16, 16, 16, 1, 256, 1, 2, 4, 4);  // registered
+            P(float, 4096, 16, 16, 16, 1, 256, 1, 3, 4, 4);
+            B(float, 4096, 16, 16, 16, 1, 256, 1, 3, 4, 4);
+            P(float, 8192, 32, 16, 16, 1, 256, 1, 1, 5, 4);  // registered
+            B(float, 8192, 32, 16, 16, 1, 256, 1, 1, 5, 4);
+            B(float, 16384, 32, 32, 16, 1, 512, 1, 1, 5, 4);  // registered
+        }
+        g_mode = 0;
     }
     if (w == "pow2" || w == "all") {
         B(float, 1024, 32, 32, 1, 1, 32, 4, 2, 4, 4);
