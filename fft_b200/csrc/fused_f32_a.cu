@@ -3,14 +3,13 @@
 #include "fused_launch.cuh"
 namespace ssfft {
 void register_fused_f32_a(std::vector<FusedEntry> &v) {
-    v.push_back(SSFFT_FUSED(float, 64, 8, 8, 1, 1, 8, 32, 2));
-    v.push_back(SSFFT_FUSED(float, 128, 16, 8, 1, 1, 8, 32, 2));
-    v.push_back(SSFFT_FUSED(float, 256, 16, 16, 1, 1, 16, 8, 4));             // 96 % of HBM peak
-    v.push_back(SSFFT_FUSED_X(float, 512, 32, 16, 1, 1, 16, 8, 4, 5, 0));     // 93 %+
+    v.push_back(SSFFT_FUSED_X(float, 64, 8, 8, 1, 1, 8, 32, 2, 4, 1));        // TMA prefetch: 72 -> 82 %
+    v.push_back(SSFFT_FUSED_X(float, 128, 16, 8, 1, 1, 8, 32, 2, 4, 1));      // 83 -> 94 %
+    v.push_back(SSFFT_FUSED_X(float, 256, 16, 16, 1, 1, 16, 8, 4, 4, 1));     // 97 -> 100 % of the measured copy peak
+    v.push_back(SSFFT_FUSED_X(float, 512, 32, 16, 1, 1, 16, 8, 3, 5, 1));     // TMA prefetch, 3 CTAs/SM: 96 -> 100 % (real: 82/60 -> 87/87 %)
     v.push_back(SSFFT_FUSED_X(float, 1024, 32, 32, 1, 1, 32, 4, 2, 5, 1));    // 97 %
-    v.push_back(SSFFT_FUSED(float, 2048, 16, 16, 8, 1, 128, 1, 6));           // 91 %
+    v.push_back(SSFFT_FUSED_X(float, 2048, 16, 16, 8, 1, 128, 2, 3, 4, 1));   // 90 -> 92 %
     // RealFFT plans (complex core of half the real length), profiles/kbench_real_r01.txt:
-    v.push_back(SSFFT_FUSED_REAL(float, 128, 16, 8, 1, 1, 8, 16, 4, 4, 0));   // C2R 62 -> 69 %
-    v.push_back(SSFFT_FUSED_REAL(float, 512, 32, 16, 1, 1, 16, 8, 3, 5, 1));  // TMA staging: R2C 82 -> 87 %, C2R 60 -> 87 %
+    v.push_back(SSFFT_FUSED_REAL(float, 1024, 32, 32, 1, 1, 32, 4, 3, 5, 1)); // 3 CTAs/SM: C2R 77 -> 84 %
 }
 }  // namespace ssfft

@@ -4,9 +4,11 @@
 namespace ssfft {
 void register_fused_f32_c(std::vector<FusedEntry> &v) {
     v.push_back(SSFFT_FUSED_X(float, 1000, 10, 10, 10, 1, 100, 2, 4, 31, 1));
-    v.push_back(SSFFT_FUSED_X(float, 2187, 27, 9, 9, 1, 81, 3, 2, 31, 0));
+    v.push_back(SSFFT_FUSED_X(float, 2187, 9, 9, 27, 1, 81, 2, 3, 31, 1));   // 70 % (27x9x9 without prefetch: 63 %)
     v.push_back(SSFFT_FUSED_X(float, 3125, 25, 25, 5, 1, 125, 1, 5, 31, 0));
     // (a 3-pass 16 x 15 x 25 variant with ragged passes measured 43 % vs 59 % for this one)
-    v.push_back(SSFFT_FUSED_X(float, 6000, 10, 10, 10, 6, 200, 1, 2, 31, 1));
+    // three passes 25 x 24 x 10 on 250 threads (ragged first and last pass): 77 % -- the four-pass 10x10x10x6 reached 59 %,
+    // and the ORDER matters: 24x25x10 only 51 % (profiles/kbench_tune2_r01.txt, kbench_tune3_r01.txt)
+    v.push_back(SSFFT_FUSED_X(float, 6000, 25, 24, 10, 1, 250, 1, 2, 31, 1));
 }
 }  // namespace ssfft

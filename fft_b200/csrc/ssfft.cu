@@ -167,9 +167,9 @@ int setup_tiled(ssfft_plan *pl, size_t total, bool real, bool *ok) {
     if (total == 0 || (total & (total - 1))) return SSFFT_OK;  // power-of-two only
     int lg = 0;
     while (((size_t)1 << lg) < total) ++lg;
-    // below these sizes a fused single-pass kernel exists and is faster (fp32: up to 16384, fp64: up to 4096)
+    // below these sizes a fused single-pass kernel exists and is faster (fp32: up to 16384, fp64: up to 8192)
     const bool f64 = sizeof(T) == 8;
-    const int min_lg = real ? env_int("SSFFT_TILE_MIN_LOG2_REAL", f64 ? 14 : 16) : env_int("SSFFT_TILE_MIN_LOG2", f64 ? 13 : 15);
+    const int min_lg = real ? env_int("SSFFT_TILE_MIN_LOG2_REAL", f64 ? 15 : 16) : env_int("SSFFT_TILE_MIN_LOG2", f64 ? 14 : 15);
     if (lg < min_lg) return SSFFT_OK;
     size_t n1 = (size_t)1 << (lg / 2), n2 = total / n1;
     int ia = find_tile<T>(n1), ib = find_tile<T>(n2);

@@ -129,6 +129,7 @@ int main(int argc, char **argv) {
     // input must be non-trivial for the correctness guard
     { std::vector<float> h(1 << 20); for (size_t i = 0; i < h.size(); ++i) h[i] = (float)((i * 2654435761u) >> 8 & 0xffff) / 65536.f - 0.5f;
       for (size_t off = 0; off < bytes; off += h.size() * 4) cudaMemcpy((char *)in + off, h.data(), std::min(h.size() * 4, bytes - off), cudaMemcpyHostToDevice); }
+#ifdef KBENCH_ALL  // earlier sweeps (results under profiles/kbench_*.txt); compile with -DKBENCH_ALL to rerun them
     if (w == "4096" || w == "all") {
         B(float, 4096, 16, 16, 16, 1, 256, 1, 2, 4, 4);
         B(float, 4096, 16, 16, 16, 1, 256, 1, 3, 4, 4);
@@ -197,6 +198,102 @@ int main(int argc, char **argv) {
         }
         g_mode = 0;
     }
+    if (w == "tune2") {
+        B(float, 16384, 32, 32, 16, 1, 512, 1, 1, 5, 4);   // registered
+        B(float, 16384, 16, 32, 32, 1, 512, 1, 1, 5, 4);
+        B(float, 16384, 32, 16, 32, 1, 512, 1, 1, 5, 4);
+        B(float, 16384, 32, 32, 16, 1, 512, 1, 1, 4, 4);
+        B(float, 16384, 16, 16, 8, 8, 1024, 1, 1, 4, 4);
+        B(float, 16384, 16, 16, 16, 4, 1024, 1, 1, 4, 4);
+        P(float, 8192, 32, 16, 16, 1, 256, 1, 1, 5, 4);    // registered
+        P(float, 8192, 16, 16, 32, 1, 256, 1, 1, 5, 4);
+        P(float, 8192, 16, 32, 16, 1, 256, 1, 1, 5, 4);
+        B(float, 8192, 16, 16, 8, 4, 512, 1, 2, 4, 4);
+        P(float, 8192, 16, 16, 8, 4, 512, 1, 1, 4, 4);
+        P(float, 6000, 10, 10, 10, 6, 200, 1, 2, 31, 4);   // registered
+        P(float, 6000, 24, 25, 10, 1, 250, 1, 2, 31, 4);
+        P(float, 6000, 25, 24, 10, 1, 250, 1, 2, 31, 4);
+        P(float, 6000, 20, 20, 15, 1, 300, 1, 2, 31, 4);
+        P(float, 6000, 15, 20, 20, 1, 300, 1, 2, 31, 4);
+        P(float, 6000, 16, 15, 25, 1, 250, 1, 2, 31, 4);
+        B(float, 6000, 20, 20, 15, 1, 300, 1, 3, 31, 4);
+        B(float, 2187, 27, 9, 9, 1, 81, 3, 2, 31, 4);      // registered
+        B(float, 2187, 27, 27, 3, 1, 81, 3, 2, 31, 4);
+        B(float, 2187, 9, 9, 27, 1, 81, 3, 2, 31, 4);
+        B(float, 2187, 9, 27, 9, 1, 81, 3, 2, 31, 4);
+        B(float, 2187, 27, 9, 9, 1, 81, 3, 3, 31, 4);
+        B(float, 3125, 25, 25, 5, 1, 125, 1, 5, 31, 4);    // registered
+        B(float, 3125, 5, 25, 25, 1, 125, 1, 5, 31, 4);
+        B(float, 3125, 25, 5, 25, 1, 125, 1, 5, 31, 4);
+        B(float, 3125, 25, 25, 5, 1, 125, 2, 3, 31, 4);
+        P(float, 1000, 10, 10, 10, 1, 100, 2, 4, 31, 4);   // registered
+        P(float, 1000, 25, 8, 5, 1, 125, 2, 4, 31, 4);
+        P(float, 1000, 8, 25, 5, 1, 125, 2, 4, 31, 4);
+        P(float, 1000, 10, 10, 10, 1, 100, 4, 3, 31, 4);
+    }
+    if (w == "tune3") {
+        P(float, 6000, 25, 24, 10, 1, 250, 1, 2, 31, 4);
+        P(float, 6000, 25, 24, 10, 1, 250, 1, 2, 4, 4);
+        P(float, 6000, 25, 24, 10, 1, 250, 1, 2, 5, 4);
+        B(float, 6000, 25, 24, 10, 1, 250, 1, 3, 31, 4);
+        B(float, 6000, 25, 24, 10, 1, 250, 1, 4, 31, 4);
+        P(float, 6000, 25, 12, 20, 1, 300, 1, 2, 31, 4);
+        P(float, 6000, 25, 20, 12, 1, 300, 1, 2, 31, 4);
+        P(float, 6000, 25, 15, 16, 1, 400, 1, 2, 31, 4);
+        B(float, 2187, 9, 9, 27, 1, 81, 3, 2, 31, 4);
+        B(float, 2187, 9, 9, 27, 1, 81, 3, 3, 31, 4);
+        P(float, 2187, 9, 9, 27, 1, 81, 2, 3, 31, 4);
+        B(float, 2187, 9, 9, 27, 1, 81, 2, 4, 31, 4);
+        B(double, 6000, 10, 10, 10, 6, 200, 1, 1, 31, 4);   // registered
+        B(double, 6000, 25, 24, 10, 1, 250, 1, 1, 31, 4);
+        B(double, 6000, 20, 20, 15, 1, 300, 1, 1, 31, 4);
+        B(double, 6000, 15, 20, 20, 1, 300, 1, 1, 31, 4);
+        P(double, 6000, 10, 10, 10, 6, 200, 1, 1, 31, 4);
+        B(double, 6000, 10, 10, 10, 6, 200, 1, 2, 31, 4);
+        B(double, 3125, 25, 25, 5, 1, 125, 2, 1, 31, 4);    // registered
+        B(double, 3125, 25, 25, 5, 1, 125, 1, 2, 31, 4);
+        B(double, 3125, 25, 25, 5, 1, 125, 1, 3, 31, 4);
+        B(double, 3125, 5, 25, 25, 1, 125, 1, 3, 31, 4);
+        B(double, 2187, 9, 9, 9, 3, 243, 1, 2, 31, 4);      // registered
+        B(double, 2187, 9, 9, 27, 1, 81, 3, 1, 31, 4);
+        B(double, 2187, 9, 9, 27, 1, 81, 2, 2, 31, 4);
+        B(double, 2187, 27, 9, 9, 1, 81, 2, 2, 31, 4);
+        B(double, 1000, 10, 10, 10, 1, 100, 2, 2, 31, 4);   // registered
+        B(double, 1000, 10, 10, 10, 1, 100, 2, 3, 31, 4);
+        B(double, 1000, 10, 10, 10, 1, 100, 2, 4, 31, 4);
+        P(double, 1000, 10, 10, 10, 1, 100, 2, 2, 31, 4);
+        P(double, 1000, 10, 10, 10, 1, 100, 2, 3, 31, 4);
+    }
+    if (w == "tune4") {
+        P(double, 6000, 25, 24, 10, 1, 250, 1, 1, 31, 4);
+        P(double, 6000, 25, 20, 12, 1, 300, 1, 1, 31, 4);
+        P(double, 3125, 25, 25, 5, 1, 125, 1, 2, 31, 4);   // odd N: bulk copies of 50000 B (multiple of 16)
+        P(double, 2187, 9, 9, 9, 3, 243, 1, 2, 31, 4);
+        P(double, 2187, 9, 9, 9, 3, 243, 2, 1, 31, 4);
+        B(double, 1024, 8, 8, 4, 4, 128, 2, 3, 3, 4);      // registered is the PF form of this
+        P(double, 1024, 8, 8, 4, 4, 128, 2, 3, 3, 4);
+        P(double, 1024, 16, 8, 8, 1, 64, 2, 3, 3, 4);
+        P(double, 1024, 8, 8, 16, 1, 64, 2, 3, 3, 4);
+        P(double, 1024, 16, 16, 4, 1, 64, 2, 3, 3, 4);
+        P(double, 1024, 8, 8, 4, 4, 128, 4, 1, 3, 4);
+        P(double, 4096, 8, 8, 8, 8, 512, 1, 1, 3, 4);      // registered
+        P(double, 4096, 16, 16, 16, 1, 256, 1, 1, 3, 4);
+        P(double, 4096, 16, 16, 16, 1, 256, 1, 1, 4, 4);
+        P(double, 4096, 16, 16, 4, 4, 512, 1, 1, 3, 4);
+        B(double, 8192, 8, 8, 8, 16, 512, 1, 1, 3, 4);
+        B(double, 8192, 16, 8, 8, 8, 512, 1, 1, 3, 4);
+        B(double, 8192, 8, 8, 8, 16, 1024, 1, 1, 3, 4);
+        P(float, 1536, 16, 16, 6, 1, 96, 2, 3, 4, 4);
+        B(float, 1536, 16, 16, 6, 1, 96, 2, 3, 4, 4);      // registered
+        P(float, 2304, 16, 16, 9, 1, 144, 2, 2, 4, 4);
+        B(float, 2304, 16, 16, 9, 1, 144, 1, 3, 4, 4);     // registered
+        P(float, 3072, 16, 16, 12, 1, 192, 1, 3, 4, 4);
+        B(float, 3072, 16, 16, 12, 1, 192, 1, 3, 4, 4);    // registered
+        P(float, 6144, 16, 16, 24, 1, 384, 1, 1, 4, 4);
+        B(float, 6144, 16, 16, 24, 1, 384, 1, 1, 4, 4);    // registered
+        P(float, 4608, 16, 16, 18, 1, 288, 1, 2, 4, 4);
+        B(float, 4608, 16, 16, 18, 1, 288, 1, 2, 4, 4);    // registered
+    }
     if (w == "pow2" || w == "all") {
         B(float, 1024, 32, 32, 1, 1, 32, 4, 2, 4, 4);
         B(float, 1024, 32, 32, 1, 1, 32, 4, 3, 4, 4);
@@ -224,6 +321,82 @@ int main(int argc, char **argv) {
         P(double, 4096, 8, 8, 8, 8, 512, 1, 1, 4, 4);
         P(double, 2048, 8, 8, 8, 4, 256, 1, 2, 4, 4);
         B(double, 2048, 8, 8, 8, 4, 256, 1, 2, 4, 4);
+    }
+#endif  // KBENCH_ALL
+    if (w == "tune6") {
+        P(float, 96, 16, 6, 1, 1, 6, 32, 2, 4, 4);      B(float, 96, 16, 6, 1, 1, 6, 32, 2, 4, 4);
+        P(float, 192, 16, 12, 1, 1, 12, 16, 2, 4, 4);   B(float, 192, 16, 12, 1, 1, 12, 16, 2, 4, 4);
+        P(float, 144, 16, 9, 1, 1, 9, 16, 2, 4, 4);     B(float, 144, 16, 9, 1, 1, 9, 16, 2, 4, 4);
+        P(float, 288, 16, 18, 1, 1, 18, 8, 2, 4, 4);    B(float, 288, 16, 18, 1, 1, 18, 8, 2, 4, 4);
+        P(float, 512, 32, 16, 1, 1, 16, 8, 4, 5, 4);    B(float, 512, 32, 16, 1, 1, 16, 8, 4, 5, 4);
+        P(float, 512, 32, 16, 1, 1, 16, 8, 3, 5, 4);
+        P(float, 2048, 16, 16, 8, 1, 128, 2, 3, 4, 4);  B(float, 2048, 16, 16, 8, 1, 128, 1, 6, 4, 4);
+        P(float, 2048, 8, 16, 16, 1, 128, 2, 3, 4, 4);
+        P(float, 16384, 32, 32, 16, 1, 512, 1, 1, 31, 4);   // staging does not fit next to 128 KiB: expected FAILED
+        P(float, 3125, 25, 25, 5, 1, 125, 2, 3, 31, 4); B(float, 3125, 25, 25, 5, 1, 125, 1, 5, 31, 4);
+        P(float, 3125, 25, 25, 5, 1, 125, 2, 2, 31, 4);
+        P(double, 64, 8, 8, 1, 1, 8, 32, 2, 3, 4);      B(double, 64, 8, 8, 1, 1, 8, 32, 2, 3, 4);
+        P(double, 128, 8, 4, 4, 1, 16, 16, 2, 3, 4);    B(double, 128, 8, 4, 4, 1, 16, 16, 2, 3, 4);
+        P(double, 128, 16, 8, 1, 1, 8, 16, 3, 3, 4);
+        P(double, 96, 8, 12, 1, 1, 12, 16, 2, 3, 4);    B(double, 96, 8, 12, 1, 1, 12, 16, 2, 3, 4);
+        P(double, 192, 8, 8, 3, 1, 24, 8, 2, 3, 4);     B(double, 192, 8, 8, 3, 1, 24, 8, 2, 3, 4);
+        P(double, 384, 8, 8, 6, 1, 48, 4, 2, 3, 4);     B(double, 384, 8, 8, 6, 1, 48, 4, 2, 3, 4);
+        P(double, 144, 8, 18, 1, 1, 18, 8, 2, 3, 4);    B(double, 144, 8, 18, 1, 1, 18, 8, 2, 3, 4);
+        P(double, 288, 8, 4, 9, 1, 36, 4, 2, 3, 4);     B(double, 288, 8, 4, 9, 1, 36, 4, 2, 3, 4);
+        P(double, 576, 8, 8, 9, 1, 72, 2, 2, 3, 4);     B(double, 576, 8, 8, 9, 1, 72, 2, 2, 3, 4);
+        P(double, 4096, 16, 16, 16, 1, 256, 1, 1, 4, 4);
+        for (int mode = 1; mode <= 2; ++mode) {  // real flavours of the new complex entries
+            g_mode = mode;
+            P(float, 128, 16, 8, 1, 1, 8, 32, 2, 4, 4);   B(float, 128, 16, 8, 1, 1, 8, 16, 4, 4, 4);
+            P(float, 256, 16, 16, 1, 1, 16, 8, 4, 4, 4);  B(float, 256, 16, 16, 1, 1, 16, 8, 4, 4, 4);
+            P(float, 64, 8, 8, 1, 1, 8, 32, 2, 4, 4);     B(float, 64, 8, 8, 1, 1, 8, 32, 2, 4, 4);
+            P(float, 1024, 32, 32, 1, 1, 32, 4, 2, 5, 4); P(float, 1024, 32, 32, 1, 1, 32, 4, 3, 5, 4);
+        }
+        g_mode = 0;
+    }
+    if (w == "tune5") {
+        P(float, 768, 16, 16, 3, 1, 48, 4, 3, 4, 4);
+        B(float, 768, 16, 16, 3, 1, 48, 4, 3, 4, 4);      // registered
+        P(float, 384, 16, 24, 1, 1, 24, 8, 2, 4, 4);
+        B(float, 384, 16, 24, 1, 1, 24, 8, 2, 4, 4);      // registered
+        P(float, 576, 16, 4, 9, 1, 36, 4, 3, 4, 4);
+        B(float, 576, 16, 4, 9, 1, 36, 4, 3, 4, 4);       // registered
+        P(float, 1152, 16, 8, 9, 1, 72, 2, 3, 4, 4);
+        B(float, 1152, 16, 8, 9, 1, 72, 2, 3, 4, 4);      // registered
+        P(float, 9216, 32, 16, 18, 1, 288, 1, 1, 5, 4);
+        B(float, 9216, 32, 16, 18, 1, 288, 1, 1, 5, 4);   // registered
+        P(float, 256, 16, 16, 1, 1, 16, 8, 4, 4, 4);
+        P(float, 128, 16, 8, 1, 1, 8, 32, 2, 4, 4);
+        B(float, 128, 16, 8, 1, 1, 8, 32, 2, 4, 4);       // registered
+        P(float, 64, 8, 8, 1, 1, 8, 32, 2, 4, 4);
+        B(float, 64, 8, 8, 1, 1, 8, 32, 2, 4, 4);         // registered
+        P(double, 2048, 8, 8, 8, 4, 256, 1, 2, 3, 4);     // registered
+        P(double, 2048, 16, 16, 8, 1, 128, 1, 2, 3, 4);
+        P(double, 2048, 8, 16, 16, 1, 128, 1, 2, 3, 4);
+        P(double, 2048, 16, 16, 8, 1, 128, 1, 2, 4, 4);
+        B(double, 512, 8, 8, 8, 1, 64, 4, 3, 3, 4);       // registered
+        P(double, 512, 8, 8, 8, 1, 64, 4, 3, 3, 4);
+        P(double, 512, 8, 8, 8, 1, 64, 2, 4, 3, 4);
+        P(double, 512, 16, 8, 4, 1, 32, 4, 3, 3, 4);
+        P(double, 512, 8, 4, 16, 1, 32, 4, 3, 3, 4);
+        B(double, 256, 8, 8, 4, 1, 32, 8, 2, 3, 4);       // registered
+        P(double, 256, 8, 8, 4, 1, 32, 8, 2, 3, 4);
+        P(double, 256, 16, 16, 1, 1, 16, 8, 3, 3, 4);
+        P(double, 256, 8, 8, 4, 1, 32, 4, 4, 3, 4);
+        B(double, 1536, 8, 8, 8, 3, 192, 1, 2, 3, 4);     // registered
+        P(double, 1536, 8, 8, 8, 3, 192, 1, 2, 3, 4);
+        P(double, 1536, 16, 16, 6, 1, 96, 2, 2, 3, 4);
+        B(double, 2304, 8, 8, 4, 9, 288, 1, 2, 3, 4);     // registered
+        P(double, 2304, 8, 8, 4, 9, 288, 1, 2, 3, 4);
+        P(double, 2304, 16, 16, 9, 1, 144, 1, 2, 3, 4);
+        B(double, 3072, 8, 8, 8, 6, 384, 1, 1, 3, 4);     // registered
+        P(double, 3072, 8, 8, 8, 6, 384, 1, 1, 3, 4);
+        P(double, 3072, 16, 16, 12, 1, 192, 1, 1, 3, 4);
+        P(double, 768, 8, 8, 12, 1, 96, 2, 2, 3, 4);
+        B(double, 768, 8, 8, 12, 1, 96, 2, 2, 3, 4);      // registered
+        P(double, 1152, 8, 8, 18, 1, 144, 1, 2, 3, 4);
+        B(double, 1152, 8, 8, 18, 1, 144, 1, 2, 3, 4);    // registered
+        P(double, 8192, 16, 8, 8, 8, 512, 1, 1, 31, 4);   // does not fit with staging? (2 x 128 KiB) -> expected FAILED
     }
     return 0;
 }
