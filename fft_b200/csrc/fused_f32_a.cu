@@ -7,9 +7,7 @@ void register_fused_f32_a(std::vector<FusedEntry> &v) {
     v.push_back(SSFFT_FUSED_X(float, 128, 16, 8, 1, 1, 8, 32, 2, 4, 1));      // 83 -> 94 %
     v.push_back(SSFFT_FUSED_X(float, 256, 16, 16, 1, 1, 16, 8, 4, 4, 1));     // 97 -> 100 % of the measured copy peak
     v.push_back(SSFFT_FUSED_X(float, 512, 32, 16, 1, 1, 16, 8, 3, 5, 1));     // TMA prefetch, 3 CTAs/SM: 96 -> 100 % (real: 82/60 -> 87/87 %)
-    v.push_back(SSFFT_FUSED_X(float, 1024, 32, 32, 1, 1, 32, 4, 2, 5, 1));    // 97 %
+    v.push_back(SSFFT_FUSED_X(float, 1024, 32, 32, 1, 1, 32, 4, 3, 5, 1));    // 3 CTAs/SM: 99 -> 101 % of the measured copy peak; C2R 77 -> 84 %
     v.push_back(SSFFT_FUSED_X(float, 2048, 16, 16, 8, 1, 128, 2, 3, 4, 1));   // 90 -> 92 %
-    // RealFFT plans (complex core of half the real length), profiles/kbench_real_r01.txt:
-    v.push_back(SSFFT_FUSED_REAL(float, 1024, 32, 32, 1, 1, 32, 4, 3, 5, 1)); // 3 CTAs/SM: C2R 77 -> 84 %
 }
 }  // namespace ssfft

@@ -3,7 +3,7 @@
 #include "fused_launch.cuh"
 namespace ssfft {
 void register_fused_f32_c(std::vector<FusedEntry> &v) {
-    v.push_back(SSFFT_FUSED_X(float, 1000, 10, 10, 10, 1, 100, 2, 4, 31, 1));
+    v.push_back(SSFFT_FUSED_X(float, 1000, 10, 10, 10, 1, 100, 2, 5, 31, 1));
     v.push_back(SSFFT_FUSED_X(float, 2187, 9, 9, 27, 1, 81, 2, 3, 31, 1));   // 70 % (27x9x9 without prefetch: 63 %)
     v.push_back(SSFFT_FUSED_X(float, 3125, 25, 25, 5, 1, 125, 1, 5, 31, 0));
     // (a 3-pass 16 x 15 x 25 variant with ragged passes measured 43 % vs 59 % for this one)

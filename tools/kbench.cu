@@ -323,6 +323,35 @@ int main(int argc, char **argv) {
         B(double, 2048, 8, 8, 8, 4, 256, 1, 2, 4, 4);
     }
 #endif  // KBENCH_ALL
+    if (w == "tune7") {
+        P(float, 8192, 32, 16, 16, 1, 256, 1, 1, 5, 4);    // registered
+        P(float, 8192, 16, 16, 32, 1, 512, 1, 1, 5, 4);    // radix-32 pass ragged over 512 threads
+        P(float, 8192, 32, 16, 16, 1, 512, 1, 1, 5, 4);
+        P(float, 8192, 16, 32, 16, 1, 512, 1, 1, 5, 4);
+        P(float, 8192, 32, 16, 16, 1, 256, 1, 1, 4, 4);
+        P(float, 8192, 32, 16, 16, 1, 256, 1, 1, 31, 4);
+        P(float, 4096, 16, 16, 16, 1, 256, 1, 2, 4, 4);    // registered
+        P(float, 4096, 16, 16, 16, 1, 256, 1, 2, 5, 4);
+        P(float, 4096, 16, 16, 16, 1, 256, 1, 2, 31, 4);
+        P(float, 1024, 32, 32, 1, 1, 32, 4, 2, 5, 4);      // registered
+        P(float, 1024, 32, 32, 1, 1, 32, 4, 3, 5, 4);
+        P(float, 1024, 16, 16, 4, 1, 64, 4, 3, 4, 4);
+        P(float, 1000, 10, 10, 10, 1, 100, 2, 4, 31, 4);   // registered
+        P(float, 1000, 10, 10, 10, 1, 100, 2, 5, 31, 4);
+        P(float, 1000, 10, 10, 10, 1, 100, 2, 3, 31, 4);
+        P(float, 1000, 25, 40, 1, 1, 40, 4, 2, 31, 4);
+        P(float, 2187, 9, 9, 27, 1, 81, 2, 3, 31, 4);      // registered
+        P(float, 2187, 27, 81, 1, 1, 81, 2, 2, 31, 4);
+        P(float, 2187, 9, 9, 27, 1, 81, 2, 2, 31, 4);
+        P(double, 8192, 16, 8, 8, 8, 512, 1, 1, 3, 4);
+        B(double, 8192, 16, 16, 32, 1, 512, 1, 1, 3, 4);
+        B(double, 8192, 16, 16, 32, 1, 256, 1, 1, 3, 4);
+        P(double, 4096, 16, 16, 16, 1, 256, 1, 1, 4, 4);   // registered
+        P(double, 4096, 16, 16, 16, 1, 512, 1, 1, 4, 4);
+        P(double, 2187, 9, 9, 27, 1, 81, 2, 2, 31, 4);
+        P(double, 6000, 25, 24, 10, 1, 250, 1, 1, 31, 4);  // registered
+        P(double, 6000, 25, 24, 10, 1, 500, 1, 1, 31, 4);
+    }
     if (w == "tune6") {
         P(float, 96, 16, 6, 1, 1, 6, 32, 2, 4, 4);      B(float, 96, 16, 6, 1, 1, 6, 32, 2, 4, 4);
         P(float, 192, 16, 12, 1, 1, 12, 16, 2, 4, 4);   B(float, 192, 16, 12, 1, 1, 12, 16, 2, 4, 4);
