@@ -3,6 +3,10 @@
 #include "fused_launch.cuh"
 namespace ssfft {
 void register_fused_f32_c(std::vector<FusedEntry> &v) {
+    // complex cores of RealFFT<float>(1000) / (6000) (profiles/kbench_tune8_r01.txt): real 1000 / 6000 went from the
+    // generic kernel + separate twiddle passes (16 / 22 % of roofline) to 59-68 %
+    v.push_back(SSFFT_FUSED_X(float, 500, 10, 10, 5, 1, 50, 4, 4, 31, 1));
+    v.push_back(SSFFT_FUSED_X(float, 3000, 25, 12, 10, 1, 125, 1, 4, 31, 1));
     v.push_back(SSFFT_FUSED_X(float, 1000, 10, 10, 10, 1, 100, 2, 5, 31, 1));
     v.push_back(SSFFT_FUSED_X(float, 2187, 9, 9, 27, 1, 81, 2, 3, 31, 1));   // 70 % (27x9x9 without prefetch: 63 %)
     v.push_back(SSFFT_FUSED_X(float, 3125, 25, 25, 5, 1, 125, 1, 5, 31, 0));

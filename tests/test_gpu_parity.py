@@ -20,7 +20,7 @@ import fft_b200  # noqa: E402
 SEED = 7
 REF_TEST_SIZES = [1, 2, 4, 8, 16, 32, 64, 128, 256, 3, 6, 9, 12, 18, 24, 5, 10, 15, 20, 25, 7, 14, 21, 28, 49,
                   11, 13, 17, 19, 22, 23]
-CONFIG_SIZES = [512, 1000, 1024, 2048, 2187, 3125, 4096, 6000, 8192, 16384]
+CONFIG_SIZES = [500, 512, 1000, 1024, 2048, 2187, 3125, 3000, 4096, 6000, 8192, 16384]
 # the reference's fast sizes 2^k * {3, 9} (FFT::sizeMinimum/sizeMaximum): fused kernels with ragged passes
 FAST_SIZES = [96, 192, 384, 768, 1536, 3072, 6144, 144, 288, 576, 1152, 2304, 4608, 9216]
 LARGE_SIZES = [16384, 32768, 65536, 3 * 2 ** 15, 100000, 2 ** 17, 2 ** 18, 2 ** 19, 2 ** 20]

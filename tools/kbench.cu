@@ -323,6 +323,28 @@ int main(int argc, char **argv) {
         B(double, 2048, 8, 8, 8, 4, 256, 1, 2, 4, 4);
     }
 #endif  // KBENCH_ALL
+    if (w == "tune8") {  // complex cores of RealFFT 1000 / 6000 (C2C + both real flavours)
+        for (int mode = 0; mode <= 2; ++mode) {
+            g_mode = mode;
+            P(float, 500, 10, 10, 5, 1, 50, 4, 4, 31, 4);
+            P(float, 500, 10, 10, 5, 1, 50, 4, 3, 31, 4);
+            P(float, 500, 10, 10, 5, 1, 50, 8, 2, 31, 4);
+            P(float, 500, 25, 20, 1, 1, 25, 8, 2, 31, 4);
+            P(float, 500, 20, 25, 1, 1, 25, 8, 2, 31, 4);
+            P(float, 3000, 25, 12, 10, 1, 125, 2, 2, 31, 4);
+            P(float, 3000, 25, 12, 10, 1, 125, 1, 4, 31, 4);
+            P(float, 3000, 10, 10, 30, 1, 100, 2, 2, 31, 4);
+            P(float, 3000, 15, 20, 10, 1, 150, 1, 3, 31, 4);
+            P(float, 3000, 25, 24, 5, 1, 125, 2, 2, 31, 4);
+            P(double, 500, 10, 10, 5, 1, 50, 4, 3, 31, 4);
+            P(double, 500, 10, 10, 5, 1, 50, 4, 2, 31, 4);
+            P(double, 500, 25, 20, 1, 1, 25, 4, 2, 31, 4);
+            P(double, 3000, 25, 12, 10, 1, 125, 1, 2, 31, 4);
+            P(double, 3000, 10, 10, 30, 1, 100, 1, 2, 31, 4);
+            P(double, 3000, 25, 24, 5, 1, 125, 1, 2, 31, 4);
+        }
+        g_mode = 0;
+    }
     if (w == "tune7") {
         P(float, 8192, 32, 16, 16, 1, 256, 1, 1, 5, 4);    // registered
         P(float, 8192, 16, 16, 32, 1, 512, 1, 1, 5, 4);    // radix-32 pass ragged over 512 threads
