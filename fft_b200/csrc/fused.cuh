@@ -38,6 +38,9 @@ struct FusedCfg {
     static constexpr int N = N_, TX = TX_, FPB = FPB_, MINB = MINB_, PADSHIFT = PADSHIFT_;
     // PF = 1: the next group of transforms is prefetched HBM -> shared staging buffer by one TMA bulk copy
     // (cp.async.bulk + mbarrier) while the current group is being transformed.
+    // PF = 2: same, but the copy lands IN the exchange buffer (dense, in front of the padded image) as soon as the last
+    // pass has gathered its inputs, so no second buffer is needed: half the shared memory of PF = 1 (more CTAs per SM,
+    // and prefetch for sizes whose staging buffer would not fit), for a shorter lead time and one more barrier.
     static constexpr int PF = PF_;
     static constexpr int NP = (R3_ > 1) ? 4 : (R2_ > 1) ? 3 : (R1_ > 1) ? 2 : 1;
     __host__ __device__ static constexpr int radix(int i) { return i == 0 ? R0_ : i == 1 ? R1_ : i == 2 ? R2_ : R3_; }
@@ -62,7 +65,7 @@ struct FusedCfg {
     __host__ __device__ static constexpr int pad(int e) { return e + (e >> PADSHIFT); }
     static constexpr int SM_STRIDE = pad(N) + 1;  // cx elements of shared memory per transform
     static constexpr size_t xchg_bytes = (((size_t)SM_STRIDE * FPB * sizeof(cx<T>)) + 127) / 128 * 128;
-    static constexpr size_t stage_bytes = PF ? (size_t)N * FPB * sizeof(cx<T>) : 0;
+    static constexpr size_t stage_bytes = PF == 1 ? (size_t)N * FPB * sizeof(cx<T>) : 0;
     static constexpr size_t smem_bytes = xchg_bytes + stage_bytes;
     static_assert(!PF || ((size_t)N * FPB * sizeof(cx<T>)) % 16 == 0, "bulk copies need 16-byte multiples: use an even FPB");
     static_assert(!PF || (R1_ > 1), "prefetch variant needs at least two passes");
@@ -143,7 +146,7 @@ fused_fft_kernel(const cx<typename Cfg::T> *__restrict__ in, cx<typename Cfg::T>
     __shared__ __align__(8) unsigned long long mbar;
     const int t = threadIdx.x, f = threadIdx.y;
     cx<T> *sm = reinterpret_cast<cx<T> *>(ssfft_smem) + (size_t)f * Cfg::SM_STRIDE;
-    const cx<T> *stage_all = reinterpret_cast<const cx<T> *>(ssfft_smem + Cfg::xchg_bytes);
+    const cx<T> *stage_all = reinterpret_cast<const cx<T> *>(Cfg::PF == 2 ? ssfft_smem : ssfft_smem + Cfg::xchg_bytes);
     const cx<T> *stage = stage_all + (size_t)f * N;
     const long long groups = (batch + FPB - 1) / FPB;
     const bool leader = (t == 0 && f == 0);
@@ -263,6 +266,10 @@ fused_fft_kernel(const cx<typename Cfg::T> *__restrict__ in, cx<typename Cfg::T>
                         if (has(u)) v[u * R + j] = sm[Cfg::pad(t + TX * u + NR * j)];
                 __syncthreads();  // everyone has read: the buffer may be overwritten
             }
+            if constexpr (first && Cfg::PF == 2) __syncthreads();  // everyone holds its inputs: the dense image may be overwritten
+            if constexpr (last && !first && Cfg::PF == 2) {
+                if (!is_r2c) prefetch(g + gridDim.x);  // the exchange buffer is free from here on (R2C: after its epilogue)
+            }
             // ---- butterflies + inter-pass twiddles
 #pragma unroll
             for (int u = 0; u < U; ++u) {
@@ -294,7 +301,7 @@ fused_fft_kernel(const cx<typename Cfg::T> *__restrict__ in, cx<typename Cfg::T>
                     }
                 }
                 __syncthreads();
-                if constexpr (PF && first) prefetch(g + gridDim.x);  // every thread has consumed the staging buffer
+                if constexpr (Cfg::PF == 1 && first) prefetch(g + gridDim.x);  // every thread has consumed the staging buffer
             } else {
                 // last pass: P == N/R, m' == 0, racc == b  ->  natural-order index b + P*r
                 if (is_r2c) {
@@ -338,6 +345,7 @@ fused_fft_kernel(const cx<typename Cfg::T> *__restrict__ in, cx<typename Cfg::T>
                         }
                     }
                     __syncthreads();
+                    if constexpr (Cfg::PF == 2) prefetch(g + gridDim.x);
                 } else if (mod && mode == FUSED_C2R_MOD) {
                     if (active) {
 #pragma unroll

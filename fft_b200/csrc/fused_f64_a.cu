@@ -9,6 +9,6 @@ void register_fused_f64_a(std::vector<FusedEntry> &v) {
     v.push_back(SSFFT_FUSED_X(double, 1024, 8, 8, 16, 1, 64, 2, 3, 3, 1));   // three passes: 64-72 -> 97 % (kbench_tune4)
     v.push_back(SSFFT_FUSED_X(double, 2048, 8, 16, 16, 1, 128, 1, 2, 3, 1));  // three passes: 76 -> 90 %
     v.push_back(SSFFT_FUSED_X(double, 4096, 16, 16, 16, 1, 256, 1, 1, 4, 1));  // three radix-16 passes: 66 -> 80 %
-    v.push_back(SSFFT_FUSED_X(double, 8192, 16, 16, 32, 1, 256, 1, 1, 3, 0));  // 54 % (four-step tiles: 33 %)
+    v.push_back(SSFFT_FUSED_X(double, 8192, 16, 16, 32, 1, 256, 1, 1, 3, 2));  // in-place staging: 69 % (no prefetch 54 %, four-step tiles 33 %)
 }
 }  // namespace ssfft

@@ -106,6 +106,9 @@ void bench(const char *name, const void *in, void *out, long long batch, int wav
 #define P(T, N, R0, R1, R2, R3, TX, FPB, MINB, PADS, W) \
     bench<FusedCfg<T, N, R0, R1, R2, R3, TX, FPB, MINB, PADS, 1>>(#T " " #N " " #R0 "x" #R1 "x" #R2 "x" #R3 " tx" #TX " fpb" #FPB " mb" #MINB " ps" #PADS " PF", in, out, batch_for(N, sizeof(T)), W)
 
+#define P2(T, N, R0, R1, R2, R3, TX, FPB, MINB, PADS, W) \
+    bench<FusedCfg<T, N, R0, R1, R2, R3, TX, FPB, MINB, PADS, 2>>(#T " " #N " " #R0 "x" #R1 "x" #R2 "x" #R3 " tx" #TX " fpb" #FPB " mb" #MINB " ps" #PADS " PF2", in, out, batch_for(N, sizeof(T)), W)
+
 static long long batch_for(int n, size_t sz) { return (long long)((2ull << 30) / (2 * sz * n)); }  // 2 GiB of input
 
 int main(int argc, char **argv) {
@@ -323,6 +326,93 @@ int main(int argc, char **argv) {
         B(double, 2048, 8, 8, 8, 4, 256, 1, 2, 4, 4);
     }
 #endif  // KBENCH_ALL
+    if (w == "tune10") {  // real flavours of the PF = 2 entries, and a few more PF = 2 candidates
+        for (int mode = 1; mode <= 2; ++mode) {
+            g_mode = mode;
+            P(float, 8192, 32, 16, 16, 1, 256, 1, 1, 5, 4);
+            P2(float, 8192, 32, 16, 16, 1, 256, 1, 2, 5, 4);
+            P(float, 2048, 16, 16, 8, 1, 128, 2, 3, 4, 4);
+            P2(float, 2048, 16, 16, 8, 1, 128, 1, 6, 4, 4);
+            B(float, 2048, 16, 16, 8, 1, 128, 1, 6, 4, 4);
+            P2(float, 4096, 16, 16, 16, 1, 256, 1, 3, 4, 4);
+            P2(float, 4096, 16, 16, 16, 1, 256, 1, 4, 4, 4);
+            P2(float, 1024, 32, 32, 1, 1, 32, 4, 3, 5, 4);
+            P(float, 1024, 32, 32, 1, 1, 32, 4, 3, 5, 4);
+            P2(float, 512, 32, 16, 1, 1, 16, 8, 4, 5, 4);
+            P(float, 512, 32, 16, 1, 1, 16, 8, 3, 5, 4);
+            P2(float, 256, 16, 16, 1, 1, 16, 8, 6, 4, 4);
+            P(float, 256, 16, 16, 1, 1, 16, 8, 4, 4, 4);
+            P2(float, 128, 16, 8, 1, 1, 8, 32, 3, 4, 4);
+            P(float, 128, 16, 8, 1, 1, 8, 32, 2, 4, 4);
+            P2(double, 4096, 16, 16, 16, 1, 256, 1, 2, 4, 4);
+            P(double, 4096, 16, 16, 16, 1, 256, 1, 1, 4, 4);
+            P2(double, 8192, 16, 16, 32, 1, 256, 1, 1, 3, 4);
+        }
+        g_mode = 0;
+        P2(float, 1024, 32, 32, 1, 1, 32, 4, 3, 5, 4);
+        P2(float, 1024, 32, 32, 1, 1, 32, 2, 6, 5, 4);
+        P2(float, 512, 32, 16, 1, 1, 16, 8, 4, 5, 4);
+        P2(float, 512, 32, 16, 1, 1, 16, 4, 6, 5, 4);
+        P2(float, 1536, 16, 16, 6, 1, 96, 2, 3, 4, 4);
+        P2(float, 1536, 16, 16, 6, 1, 96, 2, 5, 4, 4);
+        P2(float, 3072, 16, 16, 12, 1, 192, 1, 3, 4, 4);
+        P2(float, 3072, 16, 16, 12, 1, 192, 1, 5, 4, 4);
+        P2(float, 2304, 16, 16, 9, 1, 144, 2, 3, 4, 4);
+        P2(float, 2304, 16, 16, 9, 1, 144, 1, 5, 4, 4);
+        P2(float, 1000, 10, 10, 10, 1, 100, 2, 5, 31, 4);
+        P2(float, 1000, 10, 10, 10, 1, 100, 2, 8, 31, 4);
+        P2(double, 1024, 8, 8, 16, 1, 64, 2, 4, 3, 4);
+        P2(double, 1024, 8, 8, 16, 1, 64, 2, 3, 3, 4);
+        P2(double, 1536, 8, 8, 8, 3, 192, 1, 3, 3, 4);
+        P2(double, 2304, 8, 8, 4, 9, 288, 1, 3, 3, 4);
+        P2(double, 1000, 10, 10, 10, 1, 100, 2, 4, 31, 4);
+        P2(double, 6000, 25, 24, 10, 1, 250, 1, 1, 31, 4);
+    }
+    if (w == "tune9") {  // PF = 2: the prefetch lands in the exchange buffer itself (half the shared memory)
+        P(float, 8192, 32, 16, 16, 1, 256, 1, 1, 5, 4);     // registered
+        P2(float, 8192, 32, 16, 16, 1, 256, 1, 1, 5, 4);
+        P2(float, 8192, 32, 16, 16, 1, 256, 1, 2, 5, 4);
+        P2(float, 8192, 16, 16, 32, 1, 512, 1, 1, 5, 4);
+        B(float, 16384, 32, 32, 16, 1, 512, 1, 1, 5, 4);    // registered
+        P2(float, 16384, 32, 32, 16, 1, 512, 1, 1, 5, 4);
+        P2(float, 9216, 32, 16, 18, 1, 288, 1, 1, 5, 4);
+        P2(float, 9216, 32, 16, 18, 1, 288, 1, 2, 5, 4);
+        P(float, 4096, 16, 16, 16, 1, 256, 1, 2, 4, 4);     // registered
+        P2(float, 4096, 16, 16, 16, 1, 256, 1, 2, 4, 4);
+        P2(float, 4096, 16, 16, 16, 1, 256, 1, 3, 4, 4);
+        P2(float, 4096, 16, 16, 16, 1, 256, 1, 4, 4, 4);
+        P2(float, 6144, 16, 16, 24, 1, 384, 1, 1, 4, 4);
+        P2(float, 6144, 16, 16, 24, 1, 384, 1, 2, 4, 4);
+        P2(float, 6000, 25, 24, 10, 1, 250, 1, 2, 31, 4);
+        P2(float, 6000, 25, 24, 10, 1, 250, 1, 3, 31, 4);
+        P2(float, 4608, 16, 16, 18, 1, 288, 1, 2, 4, 4);
+        P2(float, 4608, 16, 16, 18, 1, 288, 1, 3, 4, 4);
+        P2(float, 2048, 16, 16, 8, 1, 128, 2, 3, 4, 4);
+        P2(float, 2048, 16, 16, 8, 1, 128, 1, 6, 4, 4);
+        P2(float, 2187, 9, 9, 27, 1, 81, 2, 3, 31, 4);
+        P2(float, 2187, 9, 9, 27, 1, 81, 2, 4, 31, 4);
+        P2(float, 3125, 25, 25, 5, 1, 125, 2, 3, 31, 4);
+        P2(double, 4096, 16, 16, 16, 1, 256, 1, 1, 4, 4);
+        P2(double, 4096, 16, 16, 16, 1, 256, 1, 2, 4, 4);
+        P2(double, 8192, 16, 16, 32, 1, 256, 1, 1, 3, 4);
+        P2(double, 2048, 8, 16, 16, 1, 128, 1, 2, 3, 4);
+        P2(double, 2048, 8, 16, 16, 1, 128, 1, 3, 3, 4);
+        P2(double, 6000, 25, 24, 10, 1, 250, 1, 1, 31, 4);
+        P2(double, 6000, 25, 24, 10, 1, 250, 1, 2, 31, 4);
+        P2(double, 3072, 16, 16, 12, 1, 192, 1, 1, 3, 4);
+        P2(double, 3072, 16, 16, 12, 1, 192, 1, 2, 3, 4);
+        P2(double, 3125, 25, 25, 5, 1, 125, 1, 3, 31, 4);
+        P2(double, 2187, 9, 9, 9, 3, 243, 1, 3, 31, 4);
+        for (int mode = 1; mode <= 2; ++mode) {
+            g_mode = mode;
+            P(float, 8192, 32, 16, 16, 1, 256, 1, 1, 5, 4);
+            P2(float, 8192, 32, 16, 16, 1, 256, 1, 1, 5, 4);
+            B(float, 16384, 32, 32, 16, 1, 512, 1, 1, 5, 4);
+            P2(float, 16384, 32, 32, 16, 1, 512, 1, 1, 5, 4);
+            P2(float, 4096, 16, 16, 16, 1, 256, 1, 3, 4, 4);
+        }
+        g_mode = 0;
+    }
     if (w == "tune8") {  // complex cores of RealFFT 1000 / 6000 (C2C + both real flavours)
         for (int mode = 0; mode <= 2; ++mode) {
             g_mode = mode;
