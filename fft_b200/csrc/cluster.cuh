@@ -420,6 +420,10 @@ cluster_fft_kernel(ClusterParams<typename Cfg::T> q, const __grid_constant__ CUt
         __syncthreads();      // every thread has consumed its part of bufB (and the previous transform left it long ago)
         cl_arrive_relaxed();  // "my bufB is free": peers may start their all-to-all stores into it
         cl_a1<Cfg, KIND>(env, tid, rank, bufA, q.tw4, v);
+        // bufA is rewritten by B0 below.  The "bufB full" mbarrier already orders that after every thread's A1 gather
+        // (each thread contributes elements to every CTA of the cluster, its own included), but a block barrier makes
+        // the ordering explicit -- and visible to compute-sanitizer's racecheck -- for well under 1 % of the time.
+        __syncthreads();
         cl_wait();            // every bufB of the cluster is free
         cl_a1_scatter<Cfg, KIND>(env, tid, rank, v);
         mbar_wait_cluster(&bars[0], par_full);  // all M elements of my rows have arrived
