@@ -53,6 +53,8 @@ void register_fourstep_f32_a(std::vector<FourStepEntry> &);
 void register_fourstep_f32_b(std::vector<FourStepEntry> &);
 void register_fourstep_f32_c(std::vector<FourStepEntry> &);
 void register_fourstep_f32_d(std::vector<FourStepEntry> &);
+void register_fourstep_f64_a(std::vector<FourStepEntry> &);
+void register_fourstep_f64_b(std::vector<FourStepEntry> &);
 
 const std::vector<FourStepEntry> &fourstep_registry() {
     static const std::vector<FourStepEntry> reg = [] {
@@ -63,6 +65,8 @@ const std::vector<FourStepEntry> &fourstep_registry() {
         register_fourstep_f32_b(v);
         register_fourstep_f32_c(v);
         register_fourstep_f32_d(v);
+        register_fourstep_f64_a(v);
+        register_fourstep_f64_b(v);
         return v;
     }();
     return reg;

@@ -583,7 +583,7 @@ fourstep_cluster_kernel(FourStepParams<typename CfgA::T> q, const __grid_constan
                     "l"(reinterpret_cast<unsigned long long>(&tmap)), "r"(tile * Cfg1::CT), "r"(0), "r"((int)Bx), "r"(smem_u32(&stage_bar))
                     : "memory");
             }
-        } else {
+        } else if constexpr (kStage) {
             tile_prefetch<Cfg1, F1, CfgA::L, CfgB::L, kCtbLog>(p1, q.in + Bx * q.user_stride, tile * Cfg1::CT, st);
         }
     };
@@ -595,7 +595,7 @@ fourstep_cluster_kernel(FourStepParams<typename CfgA::T> q, const __grid_constan
                 asm volatile("fence.proxy.async;" ::: "memory");  // peers' generic-proxy scratch stores -> async-proxy read
                 bulk_g2s(st, scr_ + (long long)tile * Cfg2::CT * Cfg2::L, bytes, &stage_bar);
             }
-        } else {
+        } else if constexpr (kStage) {
             tile_prefetch<Cfg2, F2, CfgA::L, CfgB::L, kCtbLog>(p2, scr_, tile * Cfg2::CT, st);
         }
     };
