@@ -5,5 +5,7 @@ namespace ssfft {
 void register_fourstep_f64_a(std::vector<FourStepEntry> &v) {
     v.push_back(make_fourstep_entry<TileCfg<double, 128, 8, 4, 4, 16, 8, 3>, TileCfg<double, 128, 8, 4, 4, 16, 8, 3>>("double_cluster_128x128"));
     v.push_back(make_fourstep_entry<TileCfg<double, 256, 8, 8, 4, 32, 8, 2>, TileCfg<double, 256, 8, 8, 4, 32, 8, 2>>("double_cluster_256x256"));
+    // 2^15: the column stage runs the 128-point tile on 16 lanes x 16 threads so that both stages have 256 threads
+    v.push_back(make_fourstep_entry<TileCfg<double, 128, 8, 4, 4, 16, 16, 2>, TileCfg<double, 256, 8, 8, 4, 32, 8, 2>>("double_cluster_128x256"));
 }
 }  // namespace ssfft
