@@ -326,6 +326,34 @@ int main(int argc, char **argv) {
         B(double, 2048, 8, 8, 8, 4, 256, 1, 2, 4, 4);
     }
 #endif  // KBENCH_ALL
+    if (w == "tune11") {
+        P2(float, 16384, 32, 32, 16, 1, 512, 1, 1, 5, 4);   // registered
+        P2(float, 16384, 32, 32, 16, 1, 512, 1, 1, 4, 4);
+        P2(float, 16384, 32, 16, 32, 1, 512, 1, 1, 5, 4);
+        P2(float, 16384, 16, 32, 32, 1, 512, 1, 1, 5, 4);
+        P2(float, 16384, 32, 32, 16, 1, 512, 1, 1, 5, 16);
+        P2(float, 16384, 32, 32, 16, 1, 512, 1, 1, 5, 1);
+        P(float, 4096, 16, 16, 16, 1, 256, 1, 2, 4, 2);
+        P(float, 4096, 16, 16, 16, 1, 256, 1, 2, 4, 8);
+        P(float, 4096, 16, 16, 16, 1, 256, 1, 2, 4, 32);
+        P2(float, 8192, 32, 16, 16, 1, 256, 1, 2, 5, 16);
+        P2(float, 8192, 32, 16, 16, 1, 256, 1, 2, 5, 1);
+        for (int mode = 1; mode <= 2; ++mode) {
+            g_mode = mode;
+            P(float, 128, 16, 8, 1, 1, 8, 32, 2, 4, 4);     // registered
+            P(float, 128, 16, 8, 1, 1, 8, 16, 4, 4, 4);
+            P(float, 128, 16, 8, 1, 1, 8, 16, 3, 4, 4);
+            P(float, 128, 8, 16, 1, 1, 8, 32, 2, 4, 4);
+            P(float, 128, 8, 16, 1, 1, 16, 16, 3, 4, 4);
+            P2(float, 128, 16, 8, 1, 1, 8, 16, 6, 4, 4);
+            P(float, 64, 8, 8, 1, 1, 8, 32, 2, 4, 4);       // registered
+            P(float, 64, 8, 8, 1, 1, 8, 32, 3, 4, 4);
+            P(float, 64, 8, 8, 1, 1, 8, 16, 4, 4, 4);
+            P2(float, 16384, 32, 32, 16, 1, 512, 1, 1, 5, 4);
+            P2(float, 16384, 32, 32, 16, 1, 512, 1, 1, 4, 4);
+        }
+        g_mode = 0;
+    }
     if (w == "tune10") {  // real flavours of the PF = 2 entries, and a few more PF = 2 candidates
         for (int mode = 1; mode <= 2; ++mode) {
             g_mode = mode;
