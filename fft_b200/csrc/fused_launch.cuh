@@ -1,5 +1,7 @@
 // fused_launch.cuh -- host launcher shared by the fused-kernel translation units.
 #pragma once
+#include <mutex>
+
 #include "fused.cuh"
 
 namespace ssfft {
@@ -11,9 +13,11 @@ int launch_cfg(const void *tw, const void *in, void *out, long long batch, int i
     using T = typename Cfg::T;
     static int ready_mask = 0;      // per-device one-time setup
     static int resident[64] = {0};  // SMs * CTAs/SM per device
+    static std::mutex setup_mutex;  // plans may be executed from several host threads
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return 2;
     if (dev < 0 || dev >= 32) return 1;
+    std::unique_lock<std::mutex> lock(setup_mutex);
     if (!(ready_mask & (1 << dev))) {
         if (Cfg::smem_bytes > 48 * 1024 &&
             (cudaFuncSetAttribute(fused_fft_kernel<Cfg, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -30,10 +34,12 @@ int launch_cfg(const void *tw, const void *in, void *out, long long batch, int i
         resident[dev] = per_sm * sms;
         ready_mask |= 1 << dev;
     }
+    const int resident_dev = resident[dev];
+    lock.unlock();
     const long long groups = (batch + Cfg::FPB - 1) / Cfg::FPB;
     if (groups <= 0) return 0;
     long long grid = groups;
-    const long long cap = (long long)resident[dev] * fused_waves();
+    const long long cap = (long long)resident_dev * fused_waves();
     if (cap > 0 && grid > cap) grid = cap;
     dim3 block(Cfg::TX, Cfg::FPB);
     if (mode >= FUSED_R2C_MOD)

@@ -3,6 +3,7 @@
 #include <cstdlib>
 
 #include <cstring>
+#include <mutex>
 
 #include "tiled.cuh"
 #include "tma_host.cuh"
@@ -15,9 +16,11 @@ int launch_tile(const void *params, cudaStream_t s) {
     const TileParams<T> &p = *reinterpret_cast<const TileParams<T> *>(params);
     static int ready_mask = 0;
     static int resident[32] = {0};
+    static std::mutex setup_mutex;
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return 2;
     if (dev < 0 || dev >= 32) return 1;
+    std::unique_lock<std::mutex> lock(setup_mutex);
     if (!(ready_mask & (1 << dev))) {
         if (Cfg::smem_bytes > 48 * 1024 &&
             cudaFuncSetAttribute(tile_fft_kernel<Cfg, FLAVOR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -31,6 +34,8 @@ int launch_tile(const void *params, cudaStream_t s) {
         resident[dev] = (per_sm < 1 ? 1 : per_sm) * sms;
         ready_mask |= 1 << dev;
     }
+    const int resident_dev = resident[dev];
+    lock.unlock();
     const int width = (FLAVOR == TILE_A_C2C)   ? p.n2
                       : (FLAVOR == TILE_B_C2C) ? p.n1
                       : (FLAVOR == TILE_A_R2C || FLAVOR == TILE_A_C2R) ? p.n2 / 2
@@ -38,7 +43,7 @@ int launch_tile(const void *params, cudaStream_t s) {
     const long long items = p.batch * ((width + Cfg::CT - 1) / Cfg::CT);
     if (items <= 0) return 0;
     long long grid = items;
-    const long long cap = (long long)resident[dev] * fused_waves();
+    const long long cap = (long long)resident_dev * fused_waves();
     if (cap > 0 && grid > cap) grid = cap;
     tile_fft_kernel<Cfg, FLAVOR><<<(unsigned)grid, dim3(Cfg::CT, Cfg::TX), Cfg::smem_bytes, s>>>(p);
     return cudaGetLastError() == cudaSuccess ? 0 : 2;
@@ -117,6 +122,8 @@ int launch_fourstep(const void *params, int max_clusters, cudaStream_t s) {
     // dropped with discard.global.L2 inside the kernel instead.
     static int persist_state = 0;  // 0 = unknown, 1 = enabled, -1 = unavailable / disabled
     static size_t max_window = 0;
+    static std::mutex persist_mutex;
+    std::unique_lock<std::mutex> plock(persist_mutex);
     if (persist_state == 0) {
         const char *e = getenv("SSFFT_L2_PERSIST");
         int dev = 0, max_persist = 0, max_win = 0;
@@ -132,6 +139,7 @@ int launch_fourstep(const void *params, int max_clusters, cudaStream_t s) {
             max_window = (size_t)max_win;
         }
     }
+    plock.unlock();
     if (persist_state == 1 && G == 1) {
         size_t bytes = (size_t)2 * (size_t)clusters * (size_t)q.scratch_per * sizeof(cx<T>);
         if (bytes > max_window) bytes = max_window;
