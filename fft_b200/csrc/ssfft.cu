@@ -705,13 +705,19 @@ int ssfft_exec_host(ssfft_plan *pl, int op, const void *h_in, void *h_out, size_
         if (slices < 1) { slices = bytes / (64u << 20); if (slices < 8) slices = 8; if (slices > 32) slices = 32; }
     }
     if (slices > batch) slices = batch;
-    cudaStream_t extra[2] = {nullptr, nullptr};
+    // slices rotate over a few streams so that the H2D copy of one slice, the kernels of another and the D2H copy of a
+    // third are in flight together (PCIe is full duplex)
+    int nstreams = env_int("SSFFT_HOST_STREAMS", 3);
+    if (nstreams < 1) nstreams = 1;
+    if (nstreams > 8) nstreams = 8;
+    cudaStream_t extra[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     if (slices > 1)
-        for (auto &e : extra) CU(cudaStreamCreateWithFlags(&e, cudaStreamNonBlocking));
+        for (int k = 0; k + 1 < nstreams; ++k) CU(cudaStreamCreateWithFlags(&extra[k], cudaStreamNonBlocking));
     int rc = SSFFT_OK;
     for (size_t i = 0; i < slices && rc == SSFFT_OK; ++i) {
         const size_t b0 = batch * i / slices, b1 = batch * (i + 1) / slices;
-        cudaStream_t cs = slices > 1 ? (i % 3 == 0 ? s : extra[i % 3 - 1]) : s;
+        const int which = (int)(i % (size_t)nstreams);
+        cudaStream_t cs = (slices > 1 && which > 0) ? extra[which - 1] : s;
         const char *hi = (const char *)h_in + b0 * per;
         char *ho = (char *)h_out + b0 * per;
         char *di = (char *)pl->d_stage_in + b0 * per, *dout = (char *)pl->d_stage_out + b0 * per;
