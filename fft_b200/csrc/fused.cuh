@@ -14,6 +14,11 @@
 //      tw  : W_N^(P*m'*r) from a per-pass table laid out [r][m'] (HBM-resident, L1/L2-cached)
 //      out : dst[racc + P*r + P*R*m']        (padded index keeps power-of-two strides off one bank group)
 // Only a forward transform is generated; the inverse swaps re/im on load and store.
+//
+// Input staging (FusedCfg::PF): 0 = plain streaming loads; 1 = the next group of transforms is fetched by ONE TMA bulk
+// copy into a separate staging buffer while the current group is transformed; 2 = the same copy lands in the exchange
+// buffer itself as soon as the last pass has gathered (half the shared memory).  Which one a size uses, and its
+// radices / threads / CTAs per SM, come from the tools/kbench.cu sweeps kept under profiles/kbench_*_r01.txt.
 #pragma once
 #include <cuda_runtime.h>
 

@@ -1,6 +1,11 @@
 // tools/kbench.cu -- times fused-kernel template variants in ONE GPU call (development tool, not shipped).
 //   nvcc -std=c++17 -O3 -gencode arch=compute_100a,code=sm_100a -lineinfo --expt-relaxed-constexpr \
-//        -I fft_b200/csrc -o gpurun_out/kbench tools/kbench.cu && gpurun -- ./gpurun_out/kbench
+//        -I fft_b200/csrc -o tools/kbench.bin tools/kbench.cu && gpurun -- ./tools/kbench.bin tuneN
+// B(...) = plain loads, P(...) = TMA prefetch into a staging buffer (PF = 1), P2(...) = in-place staging (PF = 2);
+// arguments: type, N, four radices, threads per transform, transforms per CTA, min CTAs/SM, padding shift, waves.
+// g_mode selects C2C / R2C / C2R.  Every variant of a size must reproduce the first variant's output (maxdiff column).
+// Sections tune2 ... tune11 are the rounds whose outputs are kept under profiles/kbench_*_r01.txt; the earliest
+// sections (4096, c4, pow2, real, tune2-4) compile only with -DKBENCH_ALL.
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
