@@ -104,6 +104,15 @@ __device__ __forceinline__ cx<T> ld_table(const cx<T> *p) {
     return mk<T>(v.x, v.y);
 }
 
+#ifdef SSFFT_EMUL
+// Host emulation of the kernels (tests/host/simt/simt_emul.h, CPU tests only): same call sites, hooks instead of PTX.
+inline void mbar_init(unsigned long long *, unsigned) { simt::mbar_init(); }
+inline void mbar_expect_tx(unsigned long long *, unsigned bytes) { simt::mbar_expect_tx(bytes); }
+inline void mbar_wait(unsigned long long *, unsigned parity) { simt::mbar_wait(parity); }
+inline void bulk_g2s(void *dst_smem, const void *src_gmem, unsigned bytes, unsigned long long *) {
+    simt::bulk_g2s(dst_smem, src_gmem, bytes);
+}
+#else
 // ---- TMA bulk copy + mbarrier (sm_90+/sm_100a PTX; SASS: UBLKCP / SYNCS)
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) {
@@ -136,6 +145,7 @@ __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, u
                  "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
+#endif  // SSFFT_EMUL
 
 // MOD: the ModifiedRealFFT flavours live in their own instantiation so that the plain kernels carry none of their
 // address arithmetic (with a run-time flag the C2R gather of the unmodified transform lost 7-20 % of roofline).
