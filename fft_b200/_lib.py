@@ -17,6 +17,16 @@ SSFFT_OK, SSFFT_ERR_INVALID, SSFFT_ERR_CUDA, SSFFT_ERR_UNSUPPORTED, SSFFT_ERR_NO
 SSFFT_C2C, SSFFT_REAL, SSFFT_REAL_MODIFIED = 0, 1, 2
 SSFFT_F32, SSFFT_F64 = 0, 1
 SSFFT_FORWARD, SSFFT_INVERSE = 1, -1
+SSFFT_MUL_NONE, SSFFT_MUL_REAL, SSFFT_MUL_COMPLEX = 0, 1, 2
+
+
+class SsfftIo(ctypes.Structure):
+    """struct ssfft_io (include/ssfft.h): layouts and fused multipliers of the extended execution calls."""
+    _fields_ = [("in_stride", ctypes.c_int64), ("in_dist", ctypes.c_int64),
+                ("out_stride", ctypes.c_int64), ("out_dist", ctypes.c_int64),
+                ("pre", ctypes.c_void_p), ("pre_kind", ctypes.c_int32), ("post_kind", ctypes.c_int32),
+                ("pre_dist", ctypes.c_int64), ("post", ctypes.c_void_p), ("post_dist", ctypes.c_int64)]
+
 
 _lib = None
 
@@ -65,6 +75,9 @@ def load():
         "ssfft_exec_c2c": (i32, [vp, vp, vp, sz, i32, vp]),
         "ssfft_exec_r2c": (i32, [vp, vp, vp, sz, vp]),
         "ssfft_exec_c2r": (i32, [vp, vp, vp, sz, vp]),
+        "ssfft_exec_c2c_ex": (i32, [vp, vp, vp, sz, i32, c.POINTER(SsfftIo), vp]),
+        "ssfft_exec_r2c_ex": (i32, [vp, vp, vp, sz, c.POINTER(SsfftIo), vp]),
+        "ssfft_exec_c2r_ex": (i32, [vp, vp, vp, sz, c.POINTER(SsfftIo), vp]),
         "ssfft_exec_host": (i32, [vp, i32, vp, vp, sz]),
         "ssfft_device_count": (i32, [c.POINTER(i32)]),
         "ssfft_malloc": (i32, [c.POINTER(vp), sz]),

@@ -104,6 +104,39 @@ class _PlanOwner:
         if t.shape[-1] != last:
             raise ValueError(f"{what}: last dimension must be {last}, got {t.shape[-1]}")
 
+    # -- extended execution (ssfft_exec_*_ex): explicit layouts + multipliers fused into the first load / last store --
+    def _io(self, in_real, out_real, in_stride, in_dist, out_stride, out_dist, pre, post, pre_dist, post_dist):
+        """Build a struct ssfft_io.  pre / post are CUDA tensors: a real dtype is a window (SSFFT_MUL_REAL), a complex
+        dtype a filter (SSFFT_MUL_COMPLEX).  The tensors must stay alive until the call has been enqueued."""
+        io = L.SsfftIo()
+        io.in_stride, io.in_dist, io.out_stride, io.out_dist = int(in_stride), int(in_dist), int(out_stride), int(out_dist)
+        io.pre_dist, io.post_dist = int(pre_dist), int(post_dist)
+        for name, t in (("pre", pre), ("post", post)):
+            if t is None:
+                setattr(io, name, None)
+                setattr(io, name + "_kind", L.SSFFT_MUL_NONE)
+                continue
+            if not (_is_cuda_tensor(t) and t.is_contiguous()):
+                raise TypeError(f"{name} must be a contiguous CUDA tensor")
+            if t.dtype not in (self._t_real, self._t_cplx):
+                raise TypeError(f"{name}: expected {self._t_real} (window) or {self._t_cplx} (filter), got {t.dtype}")
+            setattr(io, name, t.data_ptr())
+            setattr(io, name + "_kind", L.SSFFT_MUL_COMPLEX if t.is_complex() else L.SSFFT_MUL_REAL)
+        return io
+
+    def _flat(self, t, dtype, what):
+        if not _is_cuda_tensor(t):
+            raise TypeError(f"{what} must be a CUDA tensor (the extended calls are device-only)")
+        if t.dtype != dtype:
+            raise TypeError(f"{what}: expected {dtype}, got {t.dtype}")
+        if not t.is_contiguous():
+            raise ValueError(f"{what} must be contiguous (the layout is given by the stride / dist arguments)")
+        return t
+
+    @staticmethod
+    def _span(batch, length, stride, dist):
+        return 0 if batch == 0 or length == 0 else (batch - 1) * (dist or length) + (length - 1) * (stride or 1) + 1
+
     def _host(self, op, x, out, in_dt, in_last, out_dt, out_last):
         if torch is not None and isinstance(x, torch.Tensor):
             x = x.numpy()
@@ -179,6 +212,31 @@ class FFT(_PlanOwner):
     def ifft(self, input, output):
         return self._run(input, output, L.SSFFT_INVERSE)
 
+    def _run_ex(self, x, out, batch, direction, in_stride, in_dist, out_stride, out_dist, pre, post, pre_dist, post_dist):
+        n = self._size
+        self._flat(x, self._t_cplx, "input")
+        self._flat(out, self._t_cplx, "output")
+        if x.numel() < self._span(batch, n, in_stride, in_dist) or out.numel() < self._span(batch, n, out_stride, out_dist):
+            raise ValueError("buffer too small for the requested layout")
+        io = self._io(False, False, in_stride, in_dist, out_stride, out_dist, pre, post, pre_dist, post_dist)
+        L.check(self._lib.ssfft_exec_c2c_ex(self._plan, x.data_ptr(), out.data_ptr(), batch, direction, ctypes.byref(io),
+                                            self._stream(x)), "ssfft_exec_c2c_ex")
+        return out
+
+    def fft_ex(self, input, output, batch, *, in_stride=1, in_dist=0, out_stride=1, out_dist=0, pre=None, post=None,
+               pre_dist=0, post_dist=0):
+        """Forward transforms with explicit layouts: sample e of transform b is read at ``input[b*in_dist + e*in_stride]``
+        (times ``pre``) and bin k written to ``output[b*out_dist + k*out_stride]`` (times ``post``); ssfft_exec_c2c_ex.
+        ``in_stride=cols, in_dist=1`` walks the columns of a row-major matrix (second pass of a 2-D transform)."""
+        return self._run_ex(input, output, batch, L.SSFFT_FORWARD, in_stride, in_dist, out_stride, out_dist, pre, post,
+                            pre_dist, post_dist)
+
+    def ifft_ex(self, input, output, batch, *, in_stride=1, in_dist=0, out_stride=1, out_dist=0, pre=None, post=None,
+                pre_dist=0, post_dist=0):
+        """Inverse counterpart of :meth:`fft_ex`; ``pre`` = a complex filter gives ``ifft(spectrum * filter)`` in one pass."""
+        return self._run_ex(input, output, batch, L.SSFFT_INVERSE, in_stride, in_dist, out_stride, out_dist, pre, post,
+                            pre_dist, post_dist)
+
 
 class RealFFT(_PlanOwner):
     """signalsmith::RealFFT<V> -- even-length real transform, (DC, Nyquist) packed into bin 0 (:393-503)."""
@@ -240,6 +298,49 @@ class RealFFT(_PlanOwner):
                                              self._stream(input)), "ssfft_exec_c2r")
             return output
         return self._host(3, input, output, self._np_cplx, h, self._np_real, n)
+
+
+    def fft_ex(self, input, output, batch, *, in_stride=1, in_dist=0, out_stride=1, out_dist=0, pre=None, post=None,
+               pre_dist=0, post_dist=0):
+        """RealFFT::fft with explicit layouts (ssfft_exec_r2c_ex).  Input side counts REALS: ``in_dist = hop < N`` reads
+        overlapping frames straight out of a signal, ``pre`` = a real window of N samples is applied on load; the output
+        side counts complex bins, ``post`` = a complex filter multiplies the packed half spectrum on store."""
+        n, h = self.size(), self._half
+        self._flat(input, self._t_real, "input")
+        self._flat(output, self._t_cplx, "output")
+        if input.numel() < self._span(batch, n, in_stride, in_dist) or output.numel() < self._span(batch, h, out_stride, out_dist):
+            raise ValueError("buffer too small for the requested layout")
+        io = self._io(True, False, in_stride, in_dist, out_stride, out_dist, pre, post, pre_dist, post_dist)
+        L.check(self._lib.ssfft_exec_r2c_ex(self._plan, input.data_ptr(), output.data_ptr(), batch, ctypes.byref(io),
+                                            self._stream(input)), "ssfft_exec_r2c_ex")
+        return output
+
+    def ifft_ex(self, input, output, batch, *, in_stride=1, in_dist=0, out_stride=1, out_dist=0, pre=None, post=None,
+                pre_dist=0, post_dist=0):
+        """RealFFT::ifft with explicit layouts (ssfft_exec_c2r_ex): ``pre`` = complex filter on the packed half spectrum,
+        ``post`` = real synthesis window on the N output samples.  Outputs of different transforms must not overlap."""
+        n, h = self.size(), self._half
+        self._flat(input, self._t_cplx, "input")
+        self._flat(output, self._t_real, "output")
+        if input.numel() < self._span(batch, h, in_stride, in_dist) or output.numel() < self._span(batch, n, out_stride, out_dist):
+            raise ValueError("buffer too small for the requested layout")
+        io = self._io(False, True, in_stride, in_dist, out_stride, out_dist, pre, post, pre_dist, post_dist)
+        L.check(self._lib.ssfft_exec_c2r_ex(self._plan, input.data_ptr(), output.data_ptr(), batch, ctypes.byref(io),
+                                            self._stream(input)), "ssfft_exec_c2r_ex")
+        return output
+
+    def stft(self, signal, hop, window=None, output=None):
+        """Short-time transform of a 1-D CUDA signal in ONE launch: frame b = ``signal[b*hop : b*hop + N] * window``,
+        ``frames = (len - N) // hop + 1``; returns ``[frames, N/2]`` packed half spectra.  No frame matrix is ever
+        written to HBM (overlapping frames are read through L2)."""
+        n, h = self.size(), self._half
+        self._flat(signal, self._t_real, "signal")
+        if signal.dim() != 1 or signal.numel() < n or hop < 1:
+            raise ValueError("signal must be 1-D with at least N samples, hop >= 1")
+        frames = (signal.numel() - n) // hop + 1
+        if output is None:
+            output = torch.empty((frames, h), dtype=self._t_cplx, device=signal.device)
+        return self.fft_ex(signal, output, frames, in_dist=hop, pre=window)
 
 
 class ModifiedRealFFT(RealFFT):

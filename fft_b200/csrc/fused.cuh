@@ -78,6 +78,26 @@ struct FusedCfg {
     static_assert(TX_ >= 1 && TX_ <= N_, "bad thread count");
 };
 
+// Same configuration without input staging: the extended-I/O instantiation (EX) gathers its input with plain loads
+// (frames may overlap, be strided or be only 4-byte aligned, none of which a bulk copy of a whole group can express).
+template <typename Cfg>
+using NoStaging = FusedCfg<typename Cfg::T, Cfg::N, Cfg::radix(0), Cfg::radix(1), Cfg::radix(2), Cfg::radix(3), Cfg::TX, Cfg::FPB,
+                           (Cfg::MINB > 2 ? Cfg::MINB - 1 : Cfg::MINB), Cfg::PADSHIFT, 0>;
+
+// Extended I/O of the EX instantiation (ssfft_exec_*_ex, include/ssfft.h): layouts other than "contiguous batch" and
+// pointwise multipliers fused into the first load / last store.  "Elements" are reals on the real side of a RealFFT
+// (R2C input, C2R output) and complex values everywhere else.
+enum { FUSED_MUL_NONE = 0, FUSED_MUL_REAL = 1, FUSED_MUL_COMPLEX = 2 };
+template <typename T>
+struct FusedIo {
+    long long in_dist, in_stride;    // elements between transforms / between samples of one transform
+    long long out_dist, out_stride;
+    const T *pre, *post;             // multiplier tables (real or interleaved complex), nullptr = none
+    long long pre_dist, post_dist;   // elements between the multipliers of consecutive transforms (0: shared by all)
+    int pre_kind, post_kind;         // FUSED_MUL_*
+    int in_vec, out_vec;             // real side: sample pairs (2i, 2i+1) may be accessed as one aligned vector
+};
+
 #ifdef __CUDACC__
 
 template <typename T> struct vec2;
@@ -147,14 +167,63 @@ __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, u
 }
 #endif  // SSFFT_EMUL
 
+// ---- extended I/O (EX instantiation): what the first pass loads and the last pass stores.
+// real_side: the buffer holds reals and element idx is the sample pair (2 idx, 2 idx + 1)  (R2C input, C2R output);
+// packed: the buffer is a RealFFT half spectrum whose bin 0 holds (DC, Nyquist): a complex multiplier acts on its two
+// components separately (DC * DC', Nyquist * Nyquist'), which is what multiplying two real signals' spectra means.
+template <typename T>
+__device__ __forceinline__ cx<T> ex_mul(cx<T> v, const T *table, int kind, long long first, int idx, bool real_side, bool packed) {
+    if (kind == FUSED_MUL_REAL) {
+        if (real_side) {
+            const T *w = table + first + 2 * (long long)idx;
+            return mk<T>(v.x * __ldg(w), v.y * __ldg(w + 1));
+        }
+        const T w = __ldg(table + first + idx);
+        return mk<T>(v.x * w, v.y * w);
+    }
+    if (kind == FUSED_MUL_COMPLEX) {
+        const cx<T> w = ld_table(reinterpret_cast<const cx<T> *>(table) + first + idx);
+        return (packed && idx == 0) ? mk<T>(v.x * w.x, v.y * w.y) : cmul(v, w);
+    }
+    return v;
+}
+template <typename T>
+__device__ __forceinline__ cx<T> ex_load(const cx<T> *in, const FusedIo<T> &io, long long tr, int idx, bool real_side, bool packed) {
+    cx<T> v;
+    if (real_side) {
+        const T *x = reinterpret_cast<const T *>(in) + tr * io.in_dist;
+        if (io.in_vec) v = ld_stream(reinterpret_cast<const cx<T> *>(x) + idx);
+        else v = mk<T>(__ldcs(x + (2 * (long long)idx) * io.in_stride), __ldcs(x + (2 * (long long)idx + 1) * io.in_stride));
+    } else {
+        v = ld_stream(in + tr * io.in_dist + (long long)idx * io.in_stride);
+    }
+    return ex_mul(v, io.pre, io.pre_kind, tr * io.pre_dist, idx, real_side, packed);
+}
+template <typename T>
+__device__ __forceinline__ void ex_store(cx<T> *out, const FusedIo<T> &io, long long tr, int k, cx<T> v, bool real_side, bool packed) {
+    v = ex_mul(v, io.post, io.post_kind, tr * io.post_dist, k, real_side, packed);
+    if (real_side) {
+        T *y = reinterpret_cast<T *>(out) + tr * io.out_dist;
+        if (io.out_vec) st_stream(reinterpret_cast<cx<T> *>(y) + k, v);
+        else { __stcs(y + (2 * (long long)k) * io.out_stride, v.x); __stcs(y + (2 * (long long)k + 1) * io.out_stride, v.y); }
+    } else {
+        st_stream(out + tr * io.out_dist + (long long)k * io.out_stride, v);
+    }
+}
+
+// EX: extended I/O (FusedIo, ssfft_exec_*_ex) -- strided / overlapping layouts and fused multipliers behind the same
+// passes; instantiated for NoStaging configurations only, so that the plain kernels carry none of its address
+// arithmetic either.  mode: FUSED_C2C (inverse = 0 / 1), FUSED_R2C, FUSED_C2R (inverse = 1).
 // MOD: the ModifiedRealFFT flavours live in their own instantiation so that the plain kernels carry none of their
 // address arithmetic (with a run-time flag the C2R gather of the unmodified transform lost 7-20 % of roofline).
-template <typename Cfg, bool MOD = false>
+// `io` is read by the EX instantiation only (plain launches pass FusedIo<T>{}).
+template <typename Cfg, bool MOD = false, bool EX = false>
 __global__ void __launch_bounds__(Cfg::TX *Cfg::FPB, Cfg::MINB)
 fused_fft_kernel(const cx<typename Cfg::T> *__restrict__ in, cx<typename Cfg::T> *__restrict__ out,
                  const cx<typename Cfg::T> *__restrict__ tw, const cx<typename Cfg::T> *__restrict__ rtw,
-                 long long batch, int inverse, int mode) {
+                 long long batch, int inverse, int mode, FusedIo<typename Cfg::T> io) {
     using T = typename Cfg::T;
+    static_assert(!EX || (Cfg::PF == 0 && !MOD), "extended I/O: plain loads, unmodified transforms");
     constexpr int N = Cfg::N, TX = Cfg::TX, FPB = Cfg::FPB, E = Cfg::E, NP = Cfg::NP;
     constexpr bool PF = Cfg::PF != 0;
     extern __shared__ __align__(128) unsigned char ssfft_smem[];
@@ -213,9 +282,12 @@ fused_fft_kernel(const cx<typename Cfg::T> *__restrict__ in, cx<typename Cfg::T>
             }
         }
         auto load_in = [&](int idx) -> cx<T> {
-            if constexpr (PF) return stage[idx];
+            if constexpr (EX) return ex_load(in, io, active ? tr : 0, idx, is_r2c, is_c2r);
+            else if constexpr (PF) return stage[idx];
             else return ld_stream(gin + idx);
         };
+        // last-pass store of element k (EX only; the plain kernels store through gout directly)
+        auto store_ex = [&](int k, cx<T> val) { ex_store(out, io, tr, k, val, is_c2r, is_r2c); };
 
         // C2R (RealFFT::ifft :478-492): the pre-twiddle is applied on the fly while gathering pass 0 -- the
         // element buf[i] only needs in[i], in[N-i] and tw[min(i, N-i)], all of which this thread can fetch
@@ -348,12 +420,19 @@ fused_fft_kernel(const cx<typename Cfg::T> *__restrict__ in, cx<typename Cfg::T>
                                 const int i = t + TX * (u0 + k);
                                 if (u0 + k < ITER && i < H2 && (!mod || 2 * i <= N - 1)) {
                                     if (i == 0 && !mod) {
-                                        st_stream(gout, mk<T>(zi[k].x + zi[k].y, zi[k].x - zi[k].y));  // (DC, Nyquist) :459-462
+                                        const cx<T> dcny = mk<T>(zi[k].x + zi[k].y, zi[k].x - zi[k].y);  // (DC, Nyquist) :459-462
+                                        if constexpr (EX) store_ex(0, dcny);
+                                        else st_stream(gout, dcny);
                                     } else {
                                         cx<T> oi, oc;
                                         r2c_pair(zi[k], zc[k], tw_[k], oi, oc);
-                                        st_stream(gout + i, oi);
-                                        st_stream(gout + (mod ? N - 1 - i : N - i), oc);  // self-pair: second write wins
+                                        if constexpr (EX) {
+                                            store_ex(i, oi);
+                                            store_ex(N - i, oc);
+                                        } else {
+                                            st_stream(gout + i, oi);
+                                            st_stream(gout + (mod ? N - 1 - i : N - i), oc);  // self-pair: second write wins
+                                        }
                                     }
                                 }
                             }
@@ -378,13 +457,19 @@ fused_fft_kernel(const cx<typename Cfg::T> *__restrict__ in, cx<typename Cfg::T>
                         for (int u = 0; u < U; ++u)
 #pragma unroll
                             for (int r = 0; r < R; ++r)
-                                if (has(u)) st_stream(gout + t + TX * u + P * r, cswap(v[u * R + r]));
+                                if (has(u)) {
+                                    if constexpr (EX) store_ex(t + TX * u + P * r, cswap(v[u * R + r]));
+                                    else st_stream(gout + t + TX * u + P * r, cswap(v[u * R + r]));
+                                }
                     } else {
 #pragma unroll
                         for (int u = 0; u < U; ++u)
 #pragma unroll
                             for (int r = 0; r < R; ++r)
-                                if (has(u)) st_stream(gout + t + TX * u + P * r, v[u * R + r]);
+                                if (has(u)) {
+                                    if constexpr (EX) store_ex(t + TX * u + P * r, v[u * R + r]);
+                                    else st_stream(gout + t + TX * u + P * r, v[u * R + r]);
+                                }
                     }
                 }
             }
@@ -406,6 +491,9 @@ struct FusedEntry {
     int real_only;  // 1: tuned for the R2C / C2R flavours, picked for real plans only (the C2C entry of the size differs)
     int (*launch)(const void *tw, const void *in, void *out, long long batch, int inverse, int mode, const void *rtw,
                   cudaStream_t s);
+    // extended I/O (strided / overlapping layouts, fused multipliers): io -> host FusedIo<T>; unmodified transforms only
+    int (*launch_ex)(const void *tw, const void *in, void *out, long long batch, int inverse, int mode, const void *rtw,
+                     const void *io, cudaStream_t s);
 };
 
 const std::vector<FusedEntry> &fused_registry();

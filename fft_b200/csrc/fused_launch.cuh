@@ -44,10 +44,52 @@ int launch_cfg(const void *tw, const void *in, void *out, long long batch, int i
     dim3 block(Cfg::TX, Cfg::FPB);
     if (mode >= FUSED_R2C_MOD)
         fused_fft_kernel<Cfg, true><<<(unsigned)grid, block, Cfg::smem_bytes, s>>>(
-            (const cx<T> *)in, (cx<T> *)out, (const cx<T> *)tw, (const cx<T> *)rtw, batch, inverse, mode);
+            (const cx<T> *)in, (cx<T> *)out, (const cx<T> *)tw, (const cx<T> *)rtw, batch, inverse, mode, FusedIo<T>{});
     else
         fused_fft_kernel<Cfg, false><<<(unsigned)grid, block, Cfg::smem_bytes, s>>>(
-            (const cx<T> *)in, (cx<T> *)out, (const cx<T> *)tw, (const cx<T> *)rtw, batch, inverse, mode);
+            (const cx<T> *)in, (cx<T> *)out, (const cx<T> *)tw, (const cx<T> *)rtw, batch, inverse, mode, FusedIo<T>{});
+    return cudaGetLastError() == cudaSuccess ? 0 : 2;
+}
+
+// Extended I/O (ssfft_exec_*_ex): the NoStaging twin of the configuration behind strided / overlapping loads and stores
+// with fused multipliers.  `io` points at a host FusedIo<T>.
+template <typename Cfg>
+int launch_cfg_ex(const void *tw, const void *in, void *out, long long batch, int inverse, int mode, const void *rtw,
+                  const void *io, cudaStream_t s) {
+    using T = typename Cfg::T;
+    using X = NoStaging<Cfg>;
+    static int ready_mask = 0;
+    static int resident[64] = {0};
+    static std::mutex setup_mutex;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 2;
+    if (dev < 0 || dev >= 32) return 1;
+    std::unique_lock<std::mutex> lock(setup_mutex);
+    if (!(ready_mask & (1 << dev))) {
+        if (X::smem_bytes > 48 * 1024 &&
+            cudaFuncSetAttribute(fused_fft_kernel<X, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)X::smem_bytes) != cudaSuccess)
+            return 2;
+        int per_sm = 0, sms = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fused_fft_kernel<X, false, true>, X::TX * X::FPB,
+                                                          X::smem_bytes) != cudaSuccess)
+            return 2;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (per_sm < 1) per_sm = 1;
+        resident[dev] = per_sm * sms;
+        ready_mask |= 1 << dev;
+    }
+    const int resident_dev = resident[dev];
+    lock.unlock();
+    const long long groups = (batch + X::FPB - 1) / X::FPB;
+    if (groups <= 0) return 0;
+    long long grid = groups;
+    const long long cap = (long long)resident_dev * fused_waves();
+    if (cap > 0 && grid > cap) grid = cap;
+    dim3 block(X::TX, X::FPB);
+    fused_fft_kernel<X, false, true><<<(unsigned)grid, block, X::smem_bytes, s>>>(
+        (const cx<T> *)in, (cx<T> *)out, (const cx<T> *)tw, (const cx<T> *)rtw, batch, inverse, mode,
+        *static_cast<const FusedIo<T> *>(io));
     return cudaGetLastError() == cudaSuccess ? 0 : 2;
 }
 
@@ -62,6 +104,7 @@ FusedEntry make_entry(const char *name) {
     for (int i = 0; i < 4; ++i) e.radix[i] = Cfg::radix(i);
     e.real_only = 0;
     e.launch = &launch_cfg<Cfg>;
+    e.launch_ex = &launch_cfg_ex<Cfg>;
     return e;
 }
 

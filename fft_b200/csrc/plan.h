@@ -74,5 +74,9 @@ struct ssfft_plan {
     size_t stage_in_bytes = 0, stage_out_bytes = 0;
     cudaStream_t host_stream = nullptr;
 
+    // extended execution (ssfft_exec_*_ex) without a fused kernel: gather / scatter workspaces (grow-only)
+    void *d_ex_in = nullptr, *d_ex_out = nullptr;
+    size_t ex_in_bytes = 0, ex_out_bytes = 0;
+
     std::string desc;
 };

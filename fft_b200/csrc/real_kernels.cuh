@@ -102,6 +102,44 @@ __global__ void rotate_kernel(cx<T> *__restrict__ dst, const cx<T> *__restrict__
     dst[idx] = conj_rot ? cmulc(v, r) : cmul(v, r);
 }
 
+// ---- unfused form of the extended I/O (ssfft_exec_*_ex) for plans without a fused EX kernel ----
+// dst[b * dst_dist + e * dst_stride] = src[b * src_dist + e * src_stride] * mul[b * mul_dist + e],  e < len, b < batch.
+// E is the element type of the side: T on the real side of a real plan, cx<T> elsewhere.  mul_kind 1: real table,
+// 2: complex table (E = cx<T> only); packed0: the row is a RealFFT half spectrum, element 0 = (DC, Nyquist) is
+// multiplied component by component.  Consecutive threads take consecutive e: the contiguous side is coalesced.
+template <typename T>
+SSFFT_HD T ex_apply_mul_real(T v, const T *mul, int mul_kind, long long at) { return mul_kind == 1 ? v * mul[at] : v; }
+template <typename T>
+SSFFT_HD cx<T> ex_apply_mul_cx(cx<T> v, const T *mul, int mul_kind, long long at, bool first_packed) {
+    if (mul_kind == 1) return mk<T>(v.x * mul[at], v.y * mul[at]);
+    if (mul_kind == 2) {
+        const cx<T> w = reinterpret_cast<const cx<T> *>(mul)[at];
+        return first_packed ? mk<T>(v.x * w.x, v.y * w.y) : cmul(v, w);
+    }
+    return v;
+}
+#ifdef __CUDACC__
+template <typename T, bool REAL_SIDE>
+__global__ void ex_copy_kernel(const void *__restrict__ src_, void *__restrict__ dst_, long long len, long long batch,
+                               long long src_dist, long long src_stride, long long dst_dist, long long dst_stride,
+                               const T *__restrict__ mul, int mul_kind, long long mul_dist, int packed0) {
+    const long long total = len * batch;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const long long b = idx / len, e = idx - b * len;
+        if constexpr (REAL_SIDE) {
+            const T *src = static_cast<const T *>(src_);
+            T *dst = static_cast<T *>(dst_);
+            dst[b * dst_dist + e * dst_stride] = ex_apply_mul_real<T>(src[b * src_dist + e * src_stride], mul, mul_kind, b * mul_dist + e);
+        } else {
+            const cx<T> *src = static_cast<const cx<T> *>(src_);
+            cx<T> *dst = static_cast<cx<T> *>(dst_);
+            dst[b * dst_dist + e * dst_stride] =
+                ex_apply_mul_cx<T>(src[b * src_dist + e * src_stride], mul, mul_kind, b * mul_dist + e, packed0 && e == 0);
+        }
+    }
+}
+#endif
+
 // ---- local building blocks of the distributed four-step (fft_b200/dist.py) ----
 // out[b][c][r] = in[b][r][c] * W_N^((row0 + r) * c)^(+-1)   (twiddle optional: n_total == 0 -> plain transpose)
 // 32x32 tiles through shared memory, both sides coalesced.  The twiddle phase is evaluated in double

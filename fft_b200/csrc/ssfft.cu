@@ -561,6 +561,158 @@ int exec_c2r_typed(ssfft_plan *pl, const void *in, void *out, long long batch, c
     return SSFFT_OK;
 }
 
+// =============================================================================================
+// extended execution (ssfft_exec_*_ex): strided / overlapping layouts and fused multipliers
+// =============================================================================================
+enum { EX_C2C = 0, EX_R2C = 1, EX_C2R = 2 };
+
+struct ExRequest {  // a validated ssfft_io with the defaults filled in; "elements" as in include/ssfft.h
+    bool in_real = false, out_real = false;  // the side holds reals (R2C input, C2R output)
+    long long in_len = 0, out_len = 0;       // elements per transform
+    long long is = 1, id = 0, os = 1, od = 0;
+    const void *pre = nullptr, *post = nullptr;
+    int pre_kind = SSFFT_MUL_NONE, post_kind = SSFFT_MUL_NONE;
+    long long pre_dist = 0, post_dist = 0;
+    bool in_plain = true, out_plain = true;  // contiguous batch, no multiplier: nothing to do on that side
+    bool packed = false;                     // the complex side is a RealFFT half spectrum (bin 0 = DC, Nyquist)
+};
+
+int ex_validate(const ssfft_plan *pl, int op, const ssfft_io *io, long long batch, const void *in, const void *out,
+                ExRequest &x) {
+    x.in_real = op == EX_R2C;
+    x.out_real = op == EX_C2R;
+    x.in_len = x.in_real ? (long long)pl->n_real : (long long)pl->n;
+    x.out_len = x.out_real ? (long long)pl->n_real : (long long)pl->n;
+    x.packed = pl->kind == SSFFT_REAL;  // the half-bin-shifted spectrum of a modified plan has no (DC, Nyquist) bin
+    if (io->in_stride < 0 || io->in_dist < 0 || io->out_stride < 0 || io->out_dist < 0 || io->pre_dist < 0 || io->post_dist < 0)
+        return SSFFT_ERR_INVALID;
+    x.is = io->in_stride ? io->in_stride : 1;
+    x.id = io->in_dist ? io->in_dist : x.in_len;
+    x.os = io->out_stride ? io->out_stride : 1;
+    x.od = io->out_dist ? io->out_dist : x.out_len;
+    x.pre = io->pre; x.post = io->post;
+    x.pre_kind = io->pre ? io->pre_kind : SSFFT_MUL_NONE;
+    x.post_kind = io->post ? io->post_kind : SSFFT_MUL_NONE;
+    x.pre_dist = io->pre_dist; x.post_dist = io->post_dist;
+    if (io->pre && x.pre_kind != SSFFT_MUL_REAL && x.pre_kind != SSFFT_MUL_COMPLEX) return SSFFT_ERR_INVALID;
+    if (io->post && x.post_kind != SSFFT_MUL_REAL && x.post_kind != SSFFT_MUL_COMPLEX) return SSFFT_ERR_INVALID;
+    if ((x.in_real && x.pre_kind == SSFFT_MUL_COMPLEX) || (x.out_real && x.post_kind == SSFFT_MUL_COMPLEX)) return SSFFT_ERR_INVALID;
+    // vector accesses: complex buffers and complex tables must be aligned to a whole complex value
+    const size_t cplx = pl->elem, real = pl->elem / 2;
+    if ((uintptr_t)in % (x.in_real ? real : cplx) || (uintptr_t)out % (x.out_real ? real : cplx)) return SSFFT_ERR_INVALID;
+    if ((uintptr_t)x.pre % (x.pre_kind == SSFFT_MUL_COMPLEX ? cplx : real) || (uintptr_t)x.post % (x.post_kind == SSFFT_MUL_COMPLEX ? cplx : real))
+        return SSFFT_ERR_INVALID;
+    // the outputs of different transforms must not overlap: rows one after the other, or interleaved columns
+    auto disjoint = [&](long long len, long long stride, long long dist) {
+        return batch <= 1 || dist >= (len - 1) * stride + 1 || stride >= (batch - 1) * dist + 1;
+    };
+    if (!disjoint(x.out_len, x.os, x.od)) return SSFFT_ERR_INVALID;
+    x.in_plain = x.is == 1 && x.id == x.in_len && !x.pre;
+    x.out_plain = x.os == 1 && x.od == x.out_len && !x.post;
+    if (in == out) {
+        // in place: every transform is read completely before it is written, so it is enough that transform b's output
+        // covers transform b's input bytes and nobody else's
+        const long long in_sc = x.in_real ? 1 : 2, out_sc = x.out_real ? 1 : 2;
+        const bool same_bytes = x.is == 1 && x.os == 1 && x.id * in_sc == x.od * out_sc && x.in_len * in_sc == x.out_len * out_sc;
+        const bool same_layout = op == EX_C2C && x.is == x.os && x.id == x.od;
+        if (!same_bytes && !same_layout) return SSFFT_ERR_INVALID;
+    }
+    return SSFFT_OK;
+}
+
+int ex_workspace(void **ptr, size_t *have, size_t need) {
+    if (*have >= need) return SSFFT_OK;
+    if (*ptr) {
+        CU(cudaDeviceSynchronize());  // an earlier extended call may still be using the old workspace
+        cudaFree(*ptr);
+    }
+    *ptr = nullptr; *have = 0;
+    CU(cudaMalloc(ptr, need));
+    *have = need;
+    return SSFFT_OK;
+}
+
+template <typename T>
+int launch_ex_copy(bool real_side, const void *src, void *dst, long long len, long long batch, long long src_dist,
+                   long long src_stride, long long dst_dist, long long dst_stride, const void *mul, int mul_kind,
+                   long long mul_dist, bool packed, cudaStream_t s) {
+    const long long total = len * batch;
+    if (total <= 0) return SSFFT_OK;
+    long long blocks = (total + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    if (real_side)
+        ex_copy_kernel<T, true><<<(unsigned)blocks, 256, 0, s>>>(src, dst, len, batch, src_dist, src_stride, dst_dist, dst_stride,
+                                                                  (const T *)mul, mul_kind, mul_dist, 0);
+    else
+        ex_copy_kernel<T, false><<<(unsigned)blocks, 256, 0, s>>>(src, dst, len, batch, src_dist, src_stride, dst_dist, dst_stride,
+                                                                   (const T *)mul, mul_kind, mul_dist, packed ? 1 : 0);
+    ++g_launches;
+    CU(cudaGetLastError());
+    return SSFFT_OK;
+}
+
+template <typename T>
+int exec_plain(ssfft_plan *pl, int op, const void *in, void *out, long long batch, int inverse, cudaStream_t s) {
+    if (op == EX_C2C) return exec_complex<T>(pl, in, out, batch, inverse, s);
+    if (op == EX_R2C) return exec_r2c_typed<T>(pl, in, out, batch, s);
+    return exec_c2r_typed<T>(pl, in, out, batch, s);
+}
+
+template <typename T>
+int exec_ex_typed(ssfft_plan *pl, int op, const void *in, void *out, long long batch, int inverse, const ExRequest &x,
+                  cudaStream_t s) {
+    if (x.in_plain && x.out_plain) return exec_plain<T>(pl, op, in, out, batch, inverse, s);
+    const bool fused = !pl->four_step && !pl->tiled && !pl->clustered && pl->fused.id >= 0 && pl->kind != SSFFT_REAL_MODIFIED &&
+                       fused_registry()[pl->fused.id].launch_ex && !env_int("SSFFT_EX_UNFUSED", 0);
+    if (fused) {
+        // ONE launch: the layouts and multipliers ride on the first load and the last store of the fused kernel
+        FusedIo<T> f;
+        f.in_dist = x.id; f.in_stride = x.is; f.out_dist = x.od; f.out_stride = x.os;
+        f.pre = (const T *)x.pre; f.post = (const T *)x.post;
+        f.pre_dist = x.pre_dist; f.post_dist = x.post_dist;
+        f.pre_kind = x.pre_kind; f.post_kind = x.post_kind;
+        // real side: the sample pair (2i, 2i+1) is one aligned vector when every frame starts on an even sample
+        f.in_vec = x.in_real && x.is == 1 && x.id % 2 == 0 && (uintptr_t)in % sizeof(cx<T>) == 0;
+        f.out_vec = x.out_real && x.os == 1 && x.od % 2 == 0 && (uintptr_t)out % sizeof(cx<T>) == 0;
+        const int mode = op == EX_C2C ? FUSED_C2C : op == EX_R2C ? FUSED_R2C : FUSED_C2R;
+        int rc = fused_registry()[pl->fused.id].launch_ex(pl->fused.d_twiddles, in, out, batch, op == EX_C2R ? 1 : inverse, mode,
+                                                          pl->d_rtw, &f, s);
+        ++g_launches;
+        if (rc) return cuda_fail(cudaGetLastError(), "fused_fft_kernel<EX> launch");
+        return SSFFT_OK;
+    }
+    // no fused kernel for this plan: gather pass -> plain transform -> scatter pass through the plan's workspaces
+    const size_t bytes = (size_t)batch * pl->n * pl->elem;  // one contiguous batch (N reals == N/2 complex values)
+    const void *src = in;
+    void *dst = out;
+    int rc;
+    if (!x.in_plain) {
+        if ((rc = ex_workspace(&pl->d_ex_in, &pl->ex_in_bytes, bytes))) return rc;
+        rc = launch_ex_copy<T>(x.in_real, in, pl->d_ex_in, x.in_len, batch, x.id, x.is, x.in_len, 1, x.pre, x.pre_kind, x.pre_dist,
+                               x.packed && !x.in_real, s);
+        if (rc) return rc;
+        src = pl->d_ex_in;
+    }
+    if (!x.out_plain) {
+        if ((rc = ex_workspace(&pl->d_ex_out, &pl->ex_out_bytes, bytes))) return rc;
+        dst = pl->d_ex_out;
+    }
+    if ((rc = exec_plain<T>(pl, op, src, dst, batch, inverse, s))) return rc;
+    if (!x.out_plain)
+        rc = launch_ex_copy<T>(x.out_real, dst, out, x.out_len, batch, x.out_len, 1, x.od, x.os, x.post, x.post_kind, x.post_dist,
+                               x.packed && !x.out_real, s);
+    return rc;
+}
+
+int exec_ex(ssfft_plan *pl, int op, const void *d_in, void *d_out, size_t batch, int inverse, const ssfft_io *io, void *stream) {
+    ExRequest x;
+    int rc = ex_validate(pl, op, io, (long long)batch, d_in, d_out, x);
+    if (rc) return rc;
+    DeviceGuard guard(pl->device);
+    return pl->prec == SSFFT_F32 ? exec_ex_typed<float>(pl, op, d_in, d_out, (long long)batch, inverse, x, (cudaStream_t)stream)
+                                 : exec_ex_typed<double>(pl, op, d_in, d_out, (long long)batch, inverse, x, (cudaStream_t)stream);
+}
+
 void free_stage(GenericStage &st) {
     if (st.d_roots) cudaFree(st.d_roots);
     st.d_roots = nullptr;
@@ -618,7 +770,7 @@ int ssfft_plan_destroy(ssfft_plan *pl) {
     free_stage(pl->direct); free_stage(pl->col); free_stage(pl->row);
     void *ptrs[] = {pl->fused.d_twiddles, pl->fused_col.d_twiddles, pl->fused_row.d_twiddles, pl->d_ep_lo, pl->d_ep_hi,
                     pl->d_scratch, pl->d_rtw, pl->d_rot, pl->d_stage_in, pl->d_stage_out, pl->d_tile_tw_a, pl->d_tile_tw_b,
-                    pl->d_tw4, pl->d_fs_ctr};
+                    pl->d_tw4, pl->d_fs_ctr, pl->d_ex_in, pl->d_ex_out};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     for (int k = 0; k < 3; ++k) {
@@ -671,6 +823,32 @@ int ssfft_exec_c2r(ssfft_plan *pl, const void *d_in, void *d_out, size_t batch, 
     DeviceGuard guard(pl->device);
     return pl->prec == SSFFT_F32 ? exec_c2r_typed<float>(pl, d_in, d_out, (long long)batch, (cudaStream_t)stream)
                                  : exec_c2r_typed<double>(pl, d_in, d_out, (long long)batch, (cudaStream_t)stream);
+}
+
+int ssfft_exec_c2c_ex(ssfft_plan *pl, const void *d_in, void *d_out, size_t batch, int direction, const ssfft_io *io,
+                      void *stream) {
+    if (!io) return ssfft_exec_c2c(pl, d_in, d_out, batch, direction, stream);
+    if (!pl || pl->kind != SSFFT_C2C) return SSFFT_ERR_INVALID;
+    if (direction != SSFFT_FORWARD && direction != SSFFT_INVERSE) return SSFFT_ERR_INVALID;
+    if (batch == 0 || pl->n == 0) return SSFFT_OK;
+    if (!d_in || !d_out) return SSFFT_ERR_INVALID;
+    return exec_ex(pl, EX_C2C, d_in, d_out, batch, direction == SSFFT_INVERSE, io, stream);
+}
+
+int ssfft_exec_r2c_ex(ssfft_plan *pl, const void *d_in, void *d_out, size_t batch, const ssfft_io *io, void *stream) {
+    if (!io) return ssfft_exec_r2c(pl, d_in, d_out, batch, stream);
+    if (!pl || pl->kind == SSFFT_C2C) return SSFFT_ERR_INVALID;
+    if (batch == 0 || pl->n == 0) return SSFFT_OK;
+    if (!d_in || !d_out) return SSFFT_ERR_INVALID;
+    return exec_ex(pl, EX_R2C, d_in, d_out, batch, 0, io, stream);
+}
+
+int ssfft_exec_c2r_ex(ssfft_plan *pl, const void *d_in, void *d_out, size_t batch, const ssfft_io *io, void *stream) {
+    if (!io) return ssfft_exec_c2r(pl, d_in, d_out, batch, stream);
+    if (!pl || pl->kind == SSFFT_C2C) return SSFFT_ERR_INVALID;
+    if (batch == 0 || pl->n == 0) return SSFFT_OK;
+    if (!d_in || !d_out) return SSFFT_ERR_INVALID;
+    return exec_ex(pl, EX_C2R, d_in, d_out, batch, 1, io, stream);
 }
 
 int ssfft_exec_host(ssfft_plan *pl, int op, const void *h_in, void *h_out, size_t batch) {

@@ -85,6 +85,43 @@ SSFFT_API int ssfft_exec_r2c(ssfft_plan *plan, const void *d_real_in, void *d_cp
 SSFFT_API int ssfft_exec_c2r(ssfft_plan *plan, const void *d_cplx_in, void *d_real_out, size_t batch,
                              void *stream);
 
+/* ---- extended execution: the callers either side of the transform ----
+ * The reference has no counterpart: its users write these loops on the host around fft() / ifft() -- cut a signal into
+ * overlapping frames and multiply by a window before RealFFT::fft (STFT), multiply a spectrum by a filter before
+ * ifft (fast convolution), walk the columns of a matrix (2-D transforms).  On a GPU each such loop is one more trip
+ * through HBM, so the same layouts and multipliers are applied inside the transform's first load and last store.
+ *
+ * "Elements" are REALS on the real side of a real plan (input of r2c, output of c2r) and COMPLEX values everywhere
+ * else; strides, distances and multiplier tables all count in elements of their side.  A zero field means "default".
+ * Every table lives in device memory.  Sizes with a fused kernel run these calls in ONE launch; every other plan runs
+ * a gather pass, the plain transform and a scatter pass through a workspace owned by the plan (grown on demand:
+ * one extended call in flight per plan). */
+enum { SSFFT_MUL_NONE = 0, SSFFT_MUL_REAL = 1, SSFFT_MUL_COMPLEX = 2 };
+typedef struct ssfft_io {
+    int64_t in_stride;   /* elements between consecutive samples of one transform (0 or 1: contiguous) */
+    int64_t in_dist;     /* elements between the first samples of consecutive transforms (0: the transform's length).
+                            May be SMALLER than the length: overlapping STFT frames with hop = in_dist */
+    int64_t out_stride;  /* same on the output side; the outputs of different transforms must not overlap */
+    int64_t out_dist;
+    const void *pre;     /* multiplier applied to every input element as it is loaded, NULL = none */
+    int32_t pre_kind;    /* SSFFT_MUL_REAL: one real per element (a window; on a complex side it scales re and im);
+                            SSFFT_MUL_COMPLEX: one complex per element, complex sides only (a filter).  On the half
+                            spectrum of a real plan, bin 0 packs (DC, Nyquist) and is multiplied component by component,
+                            which is what the product of two such spectra means */
+    int32_t post_kind;
+    int64_t pre_dist;    /* elements between the multipliers of consecutive transforms, 0 = one table shared by all */
+    const void *post;    /* multiplier applied to every output element as it is stored, NULL = none */
+    int64_t post_dist;
+} ssfft_io;
+/* io == NULL behaves exactly like the plain call.  in == out is accepted when both sides have the same byte layout.
+ * SSFFT_ERR_INVALID: negative field, overlapping outputs, a complex multiplier on a real side, unknown kind. */
+SSFFT_API int ssfft_exec_c2c_ex(ssfft_plan *plan, const void *d_in, void *d_out, size_t batch, int direction,
+                                const ssfft_io *io, void *stream);
+SSFFT_API int ssfft_exec_r2c_ex(ssfft_plan *plan, const void *d_real_in, void *d_cplx_out, size_t batch,
+                                const ssfft_io *io, void *stream);
+SSFFT_API int ssfft_exec_c2r_ex(ssfft_plan *plan, const void *d_cplx_in, void *d_real_out, size_t batch,
+                                const ssfft_io *io, void *stream);
+
 /* ---- execution on HOST pointers: the call a reference user makes (fft(in, out) on host containers).
  * Stages host -> device (pinned staging buffers owned by the plan), runs the device path above, copies
  * back, and returns when `h_out` is complete.  kind-specific meaning of in/out as for the device calls:

@@ -6,6 +6,7 @@
 #include <cmath>
 #include <cstddef>
 #include <cstdint>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 
@@ -36,10 +37,14 @@ typedef struct simt_stream_st *cudaStream_t;
 typedef int cudaError_t;
 enum { cudaSuccess = 0 };
 
-// cache-hinted accesses are plain accesses on the host
-template <typename V> inline V __ldcs(const V *p) { return *p; }
-template <typename V> inline V __ldg(const V *p) { return *p; }
-template <typename V> inline void __stcs(V *p, V v) { *p = v; }
+// cache-hinted accesses are plain accesses on the host -- but a misaligned vector access, which x86 tolerates and
+// the GPU does not, aborts
+inline void simt_check_aligned(const void *p, size_t size) {
+    if ((uintptr_t)p % size) { fprintf(stderr, "simt: misaligned %zu-byte access at %p\n", size, p); abort(); }
+}
+template <typename V> inline V __ldcs(const V *p) { simt_check_aligned(p, sizeof(V)); return *p; }
+template <typename V> inline V __ldg(const V *p) { simt_check_aligned(p, sizeof(V)); return *p; }
+template <typename V> inline void __stcs(V *p, V v) { simt_check_aligned(p, sizeof(V)); *p = v; }
 
 void __syncthreads();  // yields to the block scheduler (simt_emul.h)
 inline long long clock64() { return 0; }

@@ -77,3 +77,26 @@ def test_product_never_imports_the_oracle():
                 if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
                     text = open(os.path.join(dirpath, f)).read()
                     assert "liboracle" not in text and "import oracle" not in text and "from oracle" not in text, f
+
+
+def test_ssfft_io_layout_matches_the_ctypes_mirror(tmp_path):
+    """struct ssfft_io as gcc lays it out (plain C, include/ssfft.h) == fft_b200._lib.SsfftIo field by field."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    fields = [name for name, _ in L.SsfftIo._fields_]
+    src = tmp_path / "layout.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "ssfft.h"\nint main(void) {\n'
+                   '  printf("%zu", sizeof(ssfft_io));\n' +
+                   "".join(f'  printf(" %zu", offsetof(ssfft_io, {f}));\n' for f in fields) + "  return 0;\n}\n")
+    exe = tmp_path / "layout"
+    import subprocess
+    subprocess.run(["gcc", "-std=c99", "-pedantic-errors", "-I" + os.path.join(root, "include"), str(src), "-o", str(exe)], check=True)
+    got = [int(v) for v in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
+    assert got[0] == ctypes.sizeof(L.SsfftIo)
+    assert got[1:] == [getattr(L.SsfftIo, f).offset for f in fields]
+
+
+def test_extended_calls_reject_bad_handles(lib):
+    io = L.SsfftIo()
+    assert lib.ssfft_exec_c2c_ex(None, None, None, 1, L.SSFFT_FORWARD, ctypes.byref(io), None) == L.SSFFT_ERR_INVALID
+    assert lib.ssfft_exec_r2c_ex(None, None, None, 1, ctypes.byref(io), None) == L.SSFFT_ERR_INVALID
+    assert lib.ssfft_exec_c2r_ex(None, None, None, 1, None, None) == L.SSFFT_ERR_INVALID

@@ -7,6 +7,9 @@ The configuration list is read from the registry sources (fused_f*.cu), so a new
 touching this test.  Each configuration runs C2C forward / inverse / in place / from pointers that are only 8-byte
 aligned, R2C, C2R and both ModifiedRealFFT flavours on a batch that makes CTAs loop and ends in a ragged group, and is
 compared with the oracle within the tolerance of the GPU parity tests (1e-6 log2 N float, 1e-14 log2 N double).
+The extended-I/O instantiation (ssfft_exec_*_ex: strided / overlapping layouts, fused windows and filters) runs ten
+layouts per configuration, checked for values AND for stray writes outside the requested layout; a misaligned vector
+access (which x86 would tolerate and the GPU would not) aborts.
 
 This is a check of index logic, barriers and staging hazards -- the GPU tests (-m gpu) remain the parity tests proper.
 """
@@ -67,6 +70,7 @@ def test_every_fused_kernel_runs_on_cpu(tmp_path, oracle):
         inc.write_text("".join("CFG(" + ", ".join(c) + ")\n" for c in chunks[i]))
         exe = str(tmp_path / f"fused_emul_{i}")
         cmd = ["g++", "-std=c++17", "-O1", "-D__CUDACC__", "-DSSFFT_EMUL", f'-DFUSED_CFG_INC="{inc}"',
+               *(["-DEMUL_EX_COPY"] if i == 0 else []),
                "-I" + os.path.join(HOST, "simt"), os.path.join(HOST, "fused_emul.cpp"),
                "-L" + os.path.join(ROOT, "oracle"), "-loracle", "-Wl,-rpath," + os.path.join(ROOT, "oracle"), "-o", exe]
         subprocess.run(cmd, check=True, capture_output=True, timeout=900)
@@ -78,4 +82,5 @@ def test_every_fused_kernel_runs_on_cpu(tmp_path, oracle):
     for res in results:
         assert res.returncode == 0 and "FUSED-EMUL-OK" in res.stdout, res.stdout[-4000:] + res.stderr[-2000:]
         runs += int(res.stdout.split(" runs over")[0].split()[-1])
-    assert runs >= 8 * len(cfgs)
+    # per configuration: 8 plain runs (x2 when it prefetches: both TMA timings) + 10 extended-I/O layouts; + ex_copy_kernel
+    assert runs >= 18 * len(cfgs) + 12

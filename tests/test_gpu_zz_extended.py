@@ -1,0 +1,202 @@
+"""GPU parity tests (-m gpu) of the extended execution calls (ssfft_exec_*_ex):
+strided / overlapping layouts and multipliers fused into the transform's first load and last store.
+
+The reference has no such call -- its users write these loops on the host around fft() / ifft() -- so the expected
+values are the ORACLE applied to explicitly gathered-and-multiplied inputs, followed by an explicit multiply-and-scatter
+(same precision, tolerance 2 x the parity bar because of the two extra roundings).  Sizes cover the three execution
+routes: fused single-launch kernels, the generic kernel and the four-step kernels (gather / transform / scatter passes).
+"""
+import math
+import os
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+import fft_b200  # noqa: E402
+from fft_b200 import _lib as L  # noqa: E402
+
+SEED = 9
+
+
+def tol(n, prec):
+    return 2.0 * (1e-6 if prec == "float32" else 1e-14) * max(1.0, math.log2(max(n, 2)))
+
+
+def dts(prec):
+    return (np.float32, np.complex64, torch.float32, torch.complex64) if prec == "float32" else \
+        (np.float64, np.complex128, torch.float64, torch.complex128)
+
+
+def around_one(oracle, count, seed, dtype):
+    """multipliers in [0.5, 1.5): keeps the comparison well conditioned"""
+    return (oracle.uniform(count, seed, dtype) + 1).astype(dtype)
+
+
+def packed_mul(spec, h):
+    """product of two RealFFT half spectra: bin 0 = (DC, Nyquist) multiplies component by component"""
+    out = spec * h
+    out[..., 0] = spec[..., 0].real * h[..., 0].real + 1j * spec[..., 0].imag * h[..., 0].imag
+    return out.astype(spec.dtype)
+
+
+# real lengths: fused (256 ... 8192), fast size 2^k*3, mixed radix with / without a fused kernel, generic, four-step
+STFT_SIZES = [128, 256, 1024, 4096, 8192, 1536, 2000, 1100, 2 ** 16]
+
+
+@pytest.mark.parametrize("prec", ["float32", "float64"])
+@pytest.mark.parametrize("n", STFT_SIZES)
+def test_stft_overlapping_frames_with_window(oracle, cuda_device, prec, n):
+    rdt, cdt, trdt, tcdt = dts(prec)
+    for hop in (n // 4, n // 4 + 1):  # even hop: vector loads; odd hop: frames start on odd samples
+        frames = 9
+        sig = oracle.uniform((frames - 1) * hop + n, SEED, rdt)
+        win = around_one(oracle, n, SEED + 1, rdt)
+        ref = oracle.run(oracle.KIND_R2C, np.stack([sig[b * hop:b * hop + n] * win for b in range(frames)]), n, threads=4)[0]
+        rfft = fft_b200.RealFFT(n, dtype=prec)
+        launches = fft_b200.launch_count()
+        spec = rfft.stft(torch.from_numpy(sig).cuda(), hop, torch.from_numpy(win).cuda())
+        torch.cuda.synchronize()
+        launches = fft_b200.launch_count() - launches
+        assert spec.shape == (frames, n // 2)
+        err = oracle.rel_l2(spec.cpu().numpy(), ref)
+        assert err <= tol(n, prec), (n, hop, err, rfft.describe())
+        if "fused" in rfft.describe():
+            assert launches == 1, (launches, rfft.describe())  # framing + window + transform + packing in ONE kernel
+
+
+@pytest.mark.parametrize("prec", ["float32", "float64"])
+@pytest.mark.parametrize("n", [256, 2048, 6000, 1100, 2 ** 16])
+def test_fast_convolution_filter_and_synthesis_window(oracle, cuda_device, prec, n):
+    """ifft(spectrum * filter) * window, padded output rows -- and the forward direction with the filter on the store."""
+    rdt, cdt, trdt, tcdt = dts(prec)
+    h, batch = n // 2, 7
+    spec = oracle.uniform_complex((batch, h), SEED, cdt)
+    filt = (oracle.uniform_complex((batch, h), SEED + 1, cdt) + 1).astype(cdt)
+    win = around_one(oracle, n, SEED + 2, rdt)
+    rfft = fft_b200.RealFFT(n, dtype=prec)
+    # inverse: per-transform filter on load, shared window on store, odd output pitch (scalar stores)
+    pitch = n + 3
+    ref = oracle.run(oracle.KIND_C2R, packed_mul(spec, filt), n, threads=4)[0] * win
+    out = torch.full((batch * pitch,), float("nan"), dtype=trdt, device="cuda")
+    rfft.ifft_ex(torch.from_numpy(spec).cuda().reshape(-1), out, batch, out_dist=pitch, pre=torch.from_numpy(filt).cuda(),
+                 pre_dist=h, post=torch.from_numpy(win).cuda())
+    torch.cuda.synchronize()
+    got = out.cpu().numpy().reshape(batch, pitch)
+    assert oracle.rel_l2(got[:, :n], ref.astype(rdt)) <= tol(n, prec), (n, rfft.describe())
+    assert np.isnan(got[:, n:]).all(), "wrote outside the requested layout"
+    # forward: shared filter applied to the packed half spectrum on store
+    x = oracle.uniform(batch * n, SEED + 3, rdt).reshape(batch, n)
+    ref = packed_mul(oracle.run(oracle.KIND_R2C, x, n, threads=4)[0], filt[:1])
+    outc = torch.empty((batch, h), dtype=tcdt, device="cuda")
+    rfft.fft_ex(torch.from_numpy(x).cuda().reshape(-1), outc.reshape(-1), batch, post=torch.from_numpy(filt[0]).cuda())
+    torch.cuda.synchronize()
+    assert oracle.rel_l2(outc.cpu().numpy(), ref) <= tol(n, prec), (n, rfft.describe())
+
+
+@pytest.mark.parametrize("prec", ["float32", "float64"])
+@pytest.mark.parametrize("rows,cols", [(64, 48), (256, 100), (1000, 33), (4096, 12), (1100, 8), (2 ** 15, 5)])
+def test_column_transforms_of_a_matrix(oracle, cuda_device, prec, rows, cols):
+    """2-D building block: length-`rows` transforms down the columns of a row-major [rows, cols] matrix, out of place
+    into a second matrix, in place, and into a transposed (row-per-transform) result."""
+    rdt, cdt, trdt, tcdt = dts(prec)
+    m = oracle.uniform_complex((rows, cols), SEED, cdt)
+    fft = fft_b200.FFT(rows, dtype=prec)
+    for inverse in (False, True):
+        ref = oracle.run(oracle.KIND_C2C_INV if inverse else oracle.KIND_C2C_FWD, np.ascontiguousarray(m.T), rows, threads=4)[0]
+        run = fft.ifft_ex if inverse else fft.fft_ex
+        d = torch.from_numpy(m).cuda()
+        out = torch.empty_like(d)
+        run(d.reshape(-1), out.reshape(-1), cols, in_stride=cols, in_dist=1, out_stride=cols, out_dist=1)
+        outT = torch.empty((cols, rows), dtype=tcdt, device="cuda")
+        run(d.reshape(-1), outT.reshape(-1), cols, in_stride=cols, in_dist=1)
+        run(d.reshape(-1), d.reshape(-1), cols, in_stride=cols, in_dist=1, out_stride=cols, out_dist=1)  # in place
+        torch.cuda.synchronize()
+        for got in (out.cpu().numpy().T, outT.cpu().numpy(), d.cpu().numpy().T):
+            assert oracle.rel_l2(np.ascontiguousarray(got), ref) <= tol(rows, prec), (rows, cols, inverse, fft.describe())
+
+
+@pytest.mark.parametrize("n", [512, 3125, 4096])
+def test_complex_multipliers_and_real_scales(oracle, cuda_device, n):
+    """C2C with every multiplier kind: real window on load, complex per-transform filter on store, and the reverse."""
+    prec = "float32"
+    rdt, cdt, trdt, tcdt = dts(prec)
+    batch = 11
+    x = oracle.uniform_complex((batch, n), SEED, cdt)
+    win = around_one(oracle, n, SEED + 1, rdt)
+    filt = (oracle.uniform_complex((batch, n), SEED + 2, cdt) + 1).astype(cdt)
+    fft = fft_b200.FFT(n, dtype=prec)
+    d, dw, df = torch.from_numpy(x).cuda(), torch.from_numpy(win).cuda(), torch.from_numpy(filt).cuda()
+    out = torch.empty_like(d)
+    fft.fft_ex(d.reshape(-1), out.reshape(-1), batch, pre=dw, post=df, post_dist=n)
+    torch.cuda.synchronize()
+    ref = (oracle.run(oracle.KIND_C2C_FWD, (x * win).astype(cdt), n, threads=4)[0] * filt).astype(cdt)
+    assert oracle.rel_l2(out.cpu().numpy(), ref) <= tol(n, prec)
+    fft.ifft_ex(d.reshape(-1), out.reshape(-1), batch, pre=df, pre_dist=n, post=dw)
+    torch.cuda.synchronize()
+    ref = (oracle.run(oracle.KIND_C2C_INV, (x * filt).astype(cdt), n, threads=4)[0] * win).astype(cdt)
+    assert oracle.rel_l2(out.cpu().numpy(), ref) <= tol(n, prec)
+
+
+@pytest.mark.parametrize("n", [1024, 4096])
+def test_fused_and_unfused_routes_agree(oracle, cuda_device, n):
+    """The single-launch kernel and the gather / transform / scatter passes implement the same request."""
+    prec = "float32"
+    rdt, cdt, trdt, tcdt = dts(prec)
+    hop, frames = n // 2 + 1, 13
+    sig = torch.from_numpy(oracle.uniform((frames - 1) * hop + n, SEED, rdt)).cuda()
+    win = torch.from_numpy(around_one(oracle, n, SEED + 1, rdt)).cuda()
+    rfft = fft_b200.RealFFT(n, dtype=prec)
+    a = rfft.stft(sig, hop, win)
+    l0 = fft_b200.launch_count()
+    os.environ["SSFFT_EX_UNFUSED"] = "1"
+    try:
+        b = rfft.stft(sig, hop, win)
+    finally:
+        del os.environ["SSFFT_EX_UNFUSED"]
+    torch.cuda.synchronize()
+    assert fft_b200.launch_count() - l0 == 2  # gather pass + fused transform (the output side is plain)
+    assert oracle.rel_l2(a.cpu().numpy(), b.cpu().numpy()) <= 1e-6
+
+
+def test_modified_real_plans_take_the_unfused_route(oracle, cuda_device):
+    prec, n, hop, frames = "float32", 1024, 300, 6
+    rdt, cdt, trdt, tcdt = dts(prec)
+    sig = oracle.uniform((frames - 1) * hop + n, SEED, rdt)
+    win = around_one(oracle, n, SEED + 1, rdt)
+    ref = oracle.run(oracle.KIND_MR2C, np.stack([sig[b * hop:b * hop + n] * win for b in range(frames)]), n, threads=2)[0]
+    mfft = fft_b200.ModifiedRealFFT(n, dtype=prec)
+    got = mfft.stft(torch.from_numpy(sig).cuda(), hop, torch.from_numpy(win).cuda())
+    torch.cuda.synchronize()
+    assert oracle.rel_l2(got.cpu().numpy(), ref) <= tol(n, prec)
+
+
+def test_null_io_is_the_plain_call_and_invalid_requests_are_rejected(oracle, cuda_device):
+    import ctypes
+    n, batch = 256, 4
+    fft = fft_b200.FFT(n)
+    x = torch.from_numpy(oracle.uniform_complex((batch, n), SEED, np.complex64)).cuda()
+    a, b = torch.empty_like(x), torch.empty_like(x)
+    fft.fft(x, a)
+    lib = L.load()
+    stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    assert lib.ssfft_exec_c2c_ex(fft._plan, x.data_ptr(), b.data_ptr(), batch, L.SSFFT_FORWARD, None, stream) == L.SSFFT_OK
+    torch.cuda.synchronize()
+    assert torch.equal(a, b)
+    with pytest.raises(fft_b200.SsfftError):  # outputs of different transforms overlap
+        fft.fft_ex(x.reshape(-1), b.reshape(-1), batch, out_dist=n // 2)
+    with pytest.raises(fft_b200.SsfftError):  # negative stride
+        fft.fft_ex(x.reshape(-1), b.reshape(-1), batch, in_stride=-1)
+    with pytest.raises(fft_b200.SsfftError):  # in place with different layouts
+        fft.fft_ex(x.reshape(-1), x.reshape(-1), batch, in_stride=batch, in_dist=1)
+    rfft = fft_b200.RealFFT(2 * n)
+    sig = torch.zeros(batch * 2 * n, device="cuda")
+    spec = torch.empty(batch * n, dtype=torch.complex64, device="cuda")
+    with pytest.raises(fft_b200.SsfftError):  # a complex multiplier cannot act on the real side
+        rfft.fft_ex(sig, spec, batch, pre=torch.ones(2 * n, dtype=torch.complex64, device="cuda"))
+    # overlapping INPUT frames are fine (that is the STFT); empty batches are no-ops
+    rfft.fft_ex(sig, spec, batch, in_dist=n)
+    rfft.fft_ex(sig, spec, 0, in_dist=n)
+    torch.cuda.synchronize()
