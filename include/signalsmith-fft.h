@@ -12,7 +12,9 @@
 //   1. the reference's way -- host containers or iterators:   fft.fft(input, output);
 //      data is staged through the device (one transform), results are identical in layout and scaling;
 //   2. NEW batched device-pointer overloads:                   fft.fft(d_in, d_out, batch, stream);
-//      `batch` contiguous transforms, asynchronous on `stream` (a cudaStream_t passed as void*).
+//      `batch` contiguous transforms, asynchronous on `stream` (a cudaStream_t passed as void*);
+//   3. NEW extended overloads:                                 fft.fft(d_in, d_out, batch, io, stream);
+//      strided / overlapping layouts and window / filter multipliers fused into the transform (struct ssfft_io).
 //
 // Conventions kept from the reference: unnormalised in both directions (ifft(fft(x)) == N*x); RealFFT
 // packs DC into output[0].real() and Nyquist into output[0].imag() and writes only N/2 bins;
@@ -126,6 +128,15 @@ public:
     void ifft(const complex *d_in, complex *d_out, std::size_t batch, void *stream = nullptr) {
         if (_size) b200_detail::check(ssfft_exec_c2c(plan.get(), d_in, d_out, batch, SSFFT_INVERSE, stream), "ssfft_exec_c2c");
     }
+    // ---- extended overloads (new): explicit layouts and fused multipliers, see struct ssfft_io in ssfft.h.
+    // e.g. the column pass of a 2-D transform over a row-major [rows][cols] matrix, in place:
+    //     ssfft_io io{}; io.in_stride = io.out_stride = cols; io.in_dist = io.out_dist = 1;  fft.fft(d, d, cols, io);
+    void fft(const complex *d_in, complex *d_out, std::size_t batch, const ssfft_io &io, void *stream = nullptr) {
+        if (_size) b200_detail::check(ssfft_exec_c2c_ex(plan.get(), d_in, d_out, batch, SSFFT_FORWARD, &io, stream), "ssfft_exec_c2c_ex");
+    }
+    void ifft(const complex *d_in, complex *d_out, std::size_t batch, const ssfft_io &io, void *stream = nullptr) {
+        if (_size) b200_detail::check(ssfft_exec_c2c_ex(plan.get(), d_in, d_out, batch, SSFFT_INVERSE, &io, stream), "ssfft_exec_c2c_ex");
+    }
     // batched HOST buffers in one call (H2D, kernels and D2H overlap inside the library)
     void fftHostBatch(const complex *h_in, complex *h_out, std::size_t batch) {
         if (_size) b200_detail::check(ssfft_exec_host(plan.get(), 0, h_in, h_out, batch), "ssfft_exec_host");
@@ -200,6 +211,14 @@ public:
     }
     void ifft(const complex *d_in, V *d_out, std::size_t batch, void *stream = nullptr) {
         if (halfSize) b200_detail::check(ssfft_exec_c2r(plan.get(), d_in, d_out, batch, stream), "ssfft_exec_c2r");
+    }
+    // extended overloads (new): e.g. an STFT straight out of a signal, window applied on load --
+    //     ssfft_io io{}; io.in_dist = hop; io.pre = d_window; io.pre_kind = SSFFT_MUL_REAL;  rfft.fft(d_signal, d_spectra, frames, io);
+    void fft(const V *d_in, complex *d_out, std::size_t batch, const ssfft_io &io, void *stream = nullptr) {
+        if (halfSize) b200_detail::check(ssfft_exec_r2c_ex(plan.get(), d_in, d_out, batch, &io, stream), "ssfft_exec_r2c_ex");
+    }
+    void ifft(const complex *d_in, V *d_out, std::size_t batch, const ssfft_io &io, void *stream = nullptr) {
+        if (halfSize) b200_detail::check(ssfft_exec_c2r_ex(plan.get(), d_in, d_out, batch, &io, stream), "ssfft_exec_c2r_ex");
     }
     std::string describe() const {
         char buf[1024] = "empty";

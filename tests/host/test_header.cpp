@@ -105,6 +105,54 @@ void testType(const char *name) {
         Oracle<V>::rfft(nr, x.data(), mref.data(), 1);
         CHECK(relL2(mspec.data(), mref.data(), nr / 2) <= Oracle<V>::tol(nr), "%s modified real n=%zu", name, nr);
     }
+    // extended overloads: an STFT straight out of a signal (overlapping frames, window applied on load) ...
+    {
+        const size_t nr = 1024, hop = 257, frames = 21, len = (frames - 1) * hop + nr;
+        std::vector<V> sig(len), win(nr), frame(nr);
+        Oracle<V>::fill(sig.data(), len, 21);
+        Oracle<V>::fill(win.data(), nr, 22);
+        for (auto &w : win) w += V(1);
+        std::vector<cplx> spec(frames * nr / 2), sref(nr / 2);
+        void *dSig = nullptr, *dWin = nullptr, *dSpec = nullptr;
+        ssfft_malloc(&dSig, len * sizeof(V)); ssfft_malloc(&dWin, nr * sizeof(V)); ssfft_malloc(&dSpec, spec.size() * sizeof(cplx));
+        ssfft_memcpy_h2d(dSig, sig.data(), len * sizeof(V), nullptr);
+        ssfft_memcpy_h2d(dWin, win.data(), nr * sizeof(V), nullptr);
+        ssfft_io io = ssfft_io();
+        io.in_dist = (int64_t)hop; io.pre = dWin; io.pre_kind = SSFFT_MUL_REAL;
+        signalsmith::RealFFT<V> r(nr);
+        r.fft((const V *)dSig, (cplx *)dSpec, frames, io);
+        ssfft_memcpy_d2h(spec.data(), dSpec, spec.size() * sizeof(cplx), nullptr);
+        ssfft_stream_synchronize(nullptr);
+        for (size_t f : {size_t(0), size_t(10), frames - 1}) {
+            for (size_t i = 0; i < nr; ++i) frame[i] = sig[f * hop + i] * win[i];
+            Oracle<V>::rfft(nr, frame.data(), sref.data(), 0);
+            CHECK(relL2(spec.data() + f * nr / 2, sref.data(), nr / 2) <= 2 * Oracle<V>::tol(nr), "%s stft frame %zu", name, f);
+        }
+        // ... and the column pass of a 2-D transform, in place on a row-major [rows][cols] matrix
+        const size_t rows = 256, cols = 24;
+        std::vector<cplx> m(rows * cols), mOut(rows * cols), col(rows), cref(rows);
+        Oracle<V>::fill((V *)m.data(), 2 * rows * cols, 23);
+        void *dM = nullptr;
+        ssfft_malloc(&dM, m.size() * sizeof(cplx));
+        ssfft_memcpy_h2d(dM, m.data(), m.size() * sizeof(cplx), nullptr);
+        ssfft_io cio = ssfft_io();
+        cio.in_stride = cio.out_stride = (int64_t)cols; cio.in_dist = cio.out_dist = 1;
+        signalsmith::FFT<V> cfft(rows);
+        cfft.fft((const cplx *)dM, (cplx *)dM, cols, cio);
+        ssfft_memcpy_d2h(mOut.data(), dM, m.size() * sizeof(cplx), nullptr);
+        ssfft_stream_synchronize(nullptr);
+        for (size_t c : {size_t(0), size_t(11), cols - 1}) {
+            for (size_t i = 0; i < rows; ++i) col[i] = m[i * cols + c];
+            Oracle<V>::fft(rows, col.data(), cref.data(), 0);
+            for (size_t i = 0; i < rows; ++i) col[i] = mOut[i * cols + c];
+            CHECK(relL2(col.data(), cref.data(), rows) <= Oracle<V>::tol(rows), "%s column %zu", name, c);
+        }
+        bool threw = false;
+        cio.out_dist = 0; cio.out_stride = 1;  // in place with a different output layout: rejected
+        try { cfft.fft((const cplx *)dM, (cplx *)dM, cols, cio); } catch (const std::runtime_error &) { threw = true; }
+        CHECK(threw, "invalid extended request must throw");
+        ssfft_free(dSig); ssfft_free(dWin); ssfft_free(dSpec); ssfft_free(dM);
+    }
     CHECK(signalsmith::RealFFT<V>(7).size() == 6, "odd real size truncates");
     CHECK(signalsmith::RealFFT<V>::sizeMinimum(256) == 258 && signalsmith::RealFFT<V>::sizeMaximum(1000) == 1024, "RealFFT size helper quirks");
 }
