@@ -78,11 +78,11 @@ struct FusedCfg {
     static_assert(TX_ >= 1 && TX_ <= N_, "bad thread count");
 };
 
-// Same configuration without input staging: the extended-I/O instantiation (EX) gathers its input with plain loads
-// (frames may overlap, be strided or be only 4-byte aligned, none of which a bulk copy of a whole group can express).
+// Same configuration without TMA staging: the extended-I/O instantiation (EX) stages its input with a cooperative copy
+// loop (frames may overlap, be strided or be only 4-byte aligned, none of which a bulk copy of a whole group can express).
 template <typename Cfg>
 using NoStaging = FusedCfg<typename Cfg::T, Cfg::N, Cfg::radix(0), Cfg::radix(1), Cfg::radix(2), Cfg::radix(3), Cfg::TX, Cfg::FPB,
-                           (Cfg::MINB > 2 ? Cfg::MINB - 1 : Cfg::MINB), Cfg::PADSHIFT, 0>;
+                           Cfg::MINB, Cfg::PADSHIFT, 0>;
 
 // Extended I/O of the EX instantiation (ssfft_exec_*_ex, include/ssfft.h): layouts other than "contiguous batch" and
 // pointwise multipliers fused into the first load / last store.  "Elements" are reals on the real side of a RealFFT
@@ -167,47 +167,67 @@ __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, u
 }
 #endif  // SSFFT_EMUL
 
-// ---- extended I/O (EX instantiation): what the first pass loads and the last pass stores.
-// real_side: the buffer holds reals and element idx is the sample pair (2 idx, 2 idx + 1)  (R2C input, C2R output);
-// packed: the buffer is a RealFFT half spectrum whose bin 0 holds (DC, Nyquist): a complex multiplier acts on its two
-// components separately (DC * DC', Nyquist * Nyquist'), which is what multiplying two real signals' spectra means.
-template <typename T>
-__device__ __forceinline__ cx<T> ex_mul(cx<T> v, const T *table, int kind, long long first, int idx, bool real_side, bool packed) {
-    if (kind == FUSED_MUL_REAL) {
-        if (real_side) {
+// ---- extended I/O (EX instantiation): cooperative, rolled copy loops between HBM and the shared-memory image of a
+// group of transforms apply the layout and the multipliers; the passes in between are the plain kernel's.
+// SIDE: 0 = complex elements, 1 = real samples accessed one by one, 2 = real samples whose pairs (2i, 2i+1) are one
+// aligned vector.  KIND: FUSED_MUL_*.  packed: the buffer is a RealFFT half spectrum whose bin 0 holds (DC, Nyquist):
+// a complex multiplier acts on its two components separately (DC * DC', Nyquist * Nyquist'), which is what
+// multiplying two such spectra means.  SIDE and KIND are compile-time so that each copy loop is branch-free and its
+// loads can be batched; ex_dispatch picks the instantiation once per group.
+template <int N> struct ic { static constexpr int value = N; };
+template <int SIDE, int KIND, typename T>
+__device__ __forceinline__ cx<T> ex_mul(cx<T> v, const T *table, long long first, int idx, bool packed) {
+    if constexpr (KIND == FUSED_MUL_REAL) {
+        if constexpr (SIDE != 0) {
             const T *w = table + first + 2 * (long long)idx;
             return mk<T>(v.x * __ldg(w), v.y * __ldg(w + 1));
+        } else {
+            const T w = __ldg(table + first + idx);
+            return mk<T>(v.x * w, v.y * w);
         }
-        const T w = __ldg(table + first + idx);
-        return mk<T>(v.x * w, v.y * w);
-    }
-    if (kind == FUSED_MUL_COMPLEX) {
+    } else if constexpr (KIND == FUSED_MUL_COMPLEX) {
         const cx<T> w = ld_table(reinterpret_cast<const cx<T> *>(table) + first + idx);
         return (packed && idx == 0) ? mk<T>(v.x * w.x, v.y * w.y) : cmul(v, w);
+    } else {
+        return v;
     }
-    return v;
 }
-template <typename T>
-__device__ __forceinline__ cx<T> ex_load(const cx<T> *in, const FusedIo<T> &io, long long tr, int idx, bool real_side, bool packed) {
+template <int SIDE, int KIND, typename T>
+__device__ __forceinline__ cx<T> ex_load(const cx<T> *in, const FusedIo<T> &io, long long tr, int idx, bool packed) {
     cx<T> v;
-    if (real_side) {
-        const T *x = reinterpret_cast<const T *>(in) + tr * io.in_dist;
-        if (io.in_vec) v = ld_stream(reinterpret_cast<const cx<T> *>(x) + idx);
-        else v = mk<T>(__ldcs(x + (2 * (long long)idx) * io.in_stride), __ldcs(x + (2 * (long long)idx + 1) * io.in_stride));
-    } else {
+    if constexpr (SIDE == 0) {
         v = ld_stream(in + tr * io.in_dist + (long long)idx * io.in_stride);
-    }
-    return ex_mul(v, io.pre, io.pre_kind, tr * io.pre_dist, idx, real_side, packed);
-}
-template <typename T>
-__device__ __forceinline__ void ex_store(cx<T> *out, const FusedIo<T> &io, long long tr, int k, cx<T> v, bool real_side, bool packed) {
-    v = ex_mul(v, io.post, io.post_kind, tr * io.post_dist, k, real_side, packed);
-    if (real_side) {
-        T *y = reinterpret_cast<T *>(out) + tr * io.out_dist;
-        if (io.out_vec) st_stream(reinterpret_cast<cx<T> *>(y) + k, v);
-        else { __stcs(y + (2 * (long long)k) * io.out_stride, v.x); __stcs(y + (2 * (long long)k + 1) * io.out_stride, v.y); }
     } else {
+        const T *x = reinterpret_cast<const T *>(in) + tr * io.in_dist;
+        if constexpr (SIDE == 2) v = ld_stream(reinterpret_cast<const cx<T> *>(x) + idx);
+        else v = mk<T>(__ldcs(x + (2 * (long long)idx) * io.in_stride), __ldcs(x + (2 * (long long)idx + 1) * io.in_stride));
+    }
+    return ex_mul<SIDE, KIND>(v, io.pre, tr * io.pre_dist, idx, packed);
+}
+template <int SIDE, int KIND, typename T>
+__device__ __forceinline__ void ex_store(cx<T> *out, const FusedIo<T> &io, long long tr, int k, cx<T> v, bool packed) {
+    v = ex_mul<SIDE, KIND>(v, io.post, tr * io.post_dist, k, packed);
+    if constexpr (SIDE == 0) {
         st_stream(out + tr * io.out_dist + (long long)k * io.out_stride, v);
+    } else {
+        T *y = reinterpret_cast<T *>(out) + tr * io.out_dist;
+        if constexpr (SIDE == 2) st_stream(reinterpret_cast<cx<T> *>(y) + k, v);
+        else { __stcs(y + (2 * (long long)k) * io.out_stride, v.x); __stcs(y + (2 * (long long)k + 1) * io.out_stride, v.y); }
+    }
+}
+// body(ic<SIDE>, ic<KIND>) for the run-time (side, kind); a complex multiplier on a real side is rejected by the host
+template <typename F>
+__device__ __forceinline__ void ex_dispatch(int side, int kind, F &&body) {
+    if (side == 0) {
+        if (kind == FUSED_MUL_REAL) body(ic<0>{}, ic<FUSED_MUL_REAL>{});
+        else if (kind == FUSED_MUL_COMPLEX) body(ic<0>{}, ic<FUSED_MUL_COMPLEX>{});
+        else body(ic<0>{}, ic<FUSED_MUL_NONE>{});
+    } else if (side == 1) {
+        if (kind == FUSED_MUL_REAL) body(ic<1>{}, ic<FUSED_MUL_REAL>{});
+        else body(ic<1>{}, ic<FUSED_MUL_NONE>{});
+    } else {
+        if (kind == FUSED_MUL_REAL) body(ic<2>{}, ic<FUSED_MUL_REAL>{});
+        else body(ic<2>{}, ic<FUSED_MUL_NONE>{});
     }
 }
 
@@ -223,14 +243,15 @@ fused_fft_kernel(const cx<typename Cfg::T> *__restrict__ in, cx<typename Cfg::T>
                  const cx<typename Cfg::T> *__restrict__ tw, const cx<typename Cfg::T> *__restrict__ rtw,
                  long long batch, int inverse, int mode, FusedIo<typename Cfg::T> io) {
     using T = typename Cfg::T;
-    static_assert(!EX || (Cfg::PF == 0 && !MOD), "extended I/O: plain loads, unmodified transforms");
+    static_assert(!EX || (Cfg::PF == 0 && !MOD), "extended I/O: no TMA staging, unmodified transforms");
+    constexpr bool STAGED = (Cfg::PF != 0) || EX;  // the first pass reads its input from a dense shared-memory image
     constexpr int N = Cfg::N, TX = Cfg::TX, FPB = Cfg::FPB, E = Cfg::E, NP = Cfg::NP;
     constexpr bool PF = Cfg::PF != 0;
     extern __shared__ __align__(128) unsigned char ssfft_smem[];
     __shared__ __align__(8) unsigned long long mbar;
     const int t = threadIdx.x, f = threadIdx.y;
     cx<T> *sm = reinterpret_cast<cx<T> *>(ssfft_smem) + (size_t)f * Cfg::SM_STRIDE;
-    const cx<T> *stage_all = reinterpret_cast<const cx<T> *>(Cfg::PF == 2 ? ssfft_smem : ssfft_smem + Cfg::xchg_bytes);
+    const cx<T> *stage_all = reinterpret_cast<const cx<T> *>((Cfg::PF == 2 || EX) ? ssfft_smem : ssfft_smem + Cfg::xchg_bytes);
     const cx<T> *stage = stage_all + (size_t)f * N;
     const long long groups = (batch + FPB - 1) / FPB;
     const bool leader = (t == 0 && f == 0);
@@ -281,13 +302,24 @@ fused_fft_kernel(const cx<typename Cfg::T> *__restrict__ in, cx<typename Cfg::T>
                 __syncthreads();
             }
         }
+        // EX: transforms of this group, and the cooperative gather of their inputs -- layout and pre-multiplier are
+        // applied on the way into the dense shared-memory image the first pass reads (as with PF = 2, minus the TMA)
+        const int ex_cnt = (int)((batch - g * FPB < FPB) ? (batch - g * FPB) : FPB);
+        if constexpr (EX) {
+            cx<T> *st = const_cast<cx<T> *>(stage_all);
+            ex_dispatch(is_r2c ? (io.in_vec ? 2 : 1) : 0, io.pre_kind, [&](auto side, auto kind) {
+#pragma unroll 8
+                for (int i = f * TX + t; i < ex_cnt * N; i += TX * FPB) {
+                    const int ff = i / N, idx = i - ff * N;
+                    st[i] = ex_load<decltype(side)::value, decltype(kind)::value>(in, io, g * FPB + ff, idx, is_c2r);
+                }
+            });
+            __syncthreads();
+        }
         auto load_in = [&](int idx) -> cx<T> {
-            if constexpr (EX) return ex_load(in, io, active ? tr : 0, idx, is_r2c, is_c2r);
-            else if constexpr (PF) return stage[idx];
+            if constexpr (STAGED) return stage[idx];
             else return ld_stream(gin + idx);
         };
-        // last-pass store of element k (EX only; the plain kernels store through gout directly)
-        auto store_ex = [&](int k, cx<T> val) { ex_store(out, io, tr, k, val, is_c2r, is_r2c); };
 
         // C2R (RealFFT::ifft :478-492): the pre-twiddle is applied on the fly while gathering pass 0 -- the
         // element buf[i] only needs in[i], in[N-i] and tw[min(i, N-i)], all of which this thread can fetch
@@ -301,7 +333,7 @@ fused_fft_kernel(const cx<typename Cfg::T> *__restrict__ in, cx<typename Cfg::T>
             // ---- gather inputs
             if constexpr (first) {
                 if (is_c2r) {
-                    if (PF || active) {
+                    if (STAGED || active) {
 #pragma unroll
                         for (int u = 0; u < U; ++u)
 #pragma unroll
@@ -320,7 +352,7 @@ fused_fft_kernel(const cx<typename Cfg::T> *__restrict__ in, cx<typename Cfg::T>
                             }
                     }
                 } else if (mod && mode == FUSED_R2C_MOD) {
-                    if (PF || active) {
+                    if (STAGED || active) {
 #pragma unroll
                         for (int u = 0; u < U; ++u)
 #pragma unroll
@@ -330,7 +362,7 @@ fused_fft_kernel(const cx<typename Cfg::T> *__restrict__ in, cx<typename Cfg::T>
                                     v[u * R + j] = cmul(load_in(idx), ld_table(rot + idx));  // pre-rotation :450-452
                                 }
                     }
-                } else if (PF || active) {
+                } else if (STAGED || active) {
                     if (inverse) {
 #pragma unroll
                         for (int u = 0; u < U; ++u)
@@ -353,7 +385,7 @@ fused_fft_kernel(const cx<typename Cfg::T> *__restrict__ in, cx<typename Cfg::T>
                         if (has(u)) v[u * R + j] = sm[Cfg::pad(t + TX * u + NR * j)];
                 __syncthreads();  // everyone has read: the buffer may be overwritten
             }
-            if constexpr (first && Cfg::PF == 2) __syncthreads();  // everyone holds its inputs: the dense image may be overwritten
+            if constexpr (first && (Cfg::PF == 2 || EX)) __syncthreads();  // everyone holds its inputs: the dense image may be overwritten
             if constexpr (last && !first && Cfg::PF == 2) {
                 if (!is_r2c) prefetch(g + gridDim.x);  // the exchange buffer is free from here on (R2C: after its epilogue)
             }
@@ -391,7 +423,48 @@ fused_fft_kernel(const cx<typename Cfg::T> *__restrict__ in, cx<typename Cfg::T>
                 if constexpr (Cfg::PF == 1 && first) prefetch(g + gridDim.x);  // every thread has consumed the staging buffer
             } else {
                 // last pass: P == N/R, m' == 0, racc == b  ->  natural-order index b + P*r
-                if (is_r2c) {
+                if constexpr (EX) {
+                    // results -> shared memory in natural order; ONE cooperative rolled loop per group then applies the
+                    // RealFFT post-twiddle (R2C), the post-multiplier and the output layout
+#pragma unroll
+                    for (int u = 0; u < U; ++u)
+#pragma unroll
+                        for (int r = 0; r < R; ++r)
+                            if (has(u)) sm[Cfg::pad(t + TX * u + P * r)] = inverse ? cswap(v[u * R + r]) : v[u * R + r];
+                    __syncthreads();
+                    const cx<T> *img = reinterpret_cast<const cx<T> *>(ssfft_smem);
+                    if (is_r2c) {
+                        constexpr int H2 = N / 2 + 1;  // pairs (k, N-k), k = 0 .. N/2  (RealFFT::fft :459-472)
+                        ex_dispatch(0, io.post_kind, [&](auto side, auto kind) {
+                            constexpr int SD = decltype(side)::value, KD = decltype(kind)::value;
+#pragma unroll 2
+                            for (int i = f * TX + t; i < ex_cnt * H2; i += TX * FPB) {
+                                const int ff = i / H2, k = i - ff * H2;
+                                const cx<T> *row = img + (size_t)ff * Cfg::SM_STRIDE;
+                                const cx<T> zi = row[Cfg::pad(k)], zc = row[Cfg::pad(k ? N - k : 0)];
+                                const long long trk = g * FPB + ff;
+                                if (k == 0) {
+                                    ex_store<SD, KD>(out, io, trk, 0, mk<T>(zi.x + zi.y, zi.x - zi.y), true);  // (DC, Nyquist)
+                                } else {
+                                    cx<T> oi, oc;
+                                    r2c_pair(zi, zc, ld_table(rtw + k), oi, oc);
+                                    ex_store<SD, KD>(out, io, trk, k, oi, true);
+                                    ex_store<SD, KD>(out, io, trk, N - k, oc, true);  // self-pair: second write wins
+                                }
+                            }
+                        });
+                    } else {
+                        ex_dispatch(is_c2r ? (io.out_vec ? 2 : 1) : 0, io.post_kind, [&](auto side, auto kind) {
+#pragma unroll 4
+                            for (int i = f * TX + t; i < ex_cnt * N; i += TX * FPB) {
+                                const int ff = i / N, k = i - ff * N;
+                                ex_store<decltype(side)::value, decltype(kind)::value>(out, io, g * FPB + ff, k,
+                                                                                       img[(size_t)ff * Cfg::SM_STRIDE + Cfg::pad(k)], false);
+                            }
+                        });
+                    }
+                    __syncthreads();  // the next group's gather overwrites the image
+                } else if (is_r2c) {
 #pragma unroll
                     for (int u = 0; u < U; ++u)
 #pragma unroll
@@ -420,19 +493,12 @@ fused_fft_kernel(const cx<typename Cfg::T> *__restrict__ in, cx<typename Cfg::T>
                                 const int i = t + TX * (u0 + k);
                                 if (u0 + k < ITER && i < H2 && (!mod || 2 * i <= N - 1)) {
                                     if (i == 0 && !mod) {
-                                        const cx<T> dcny = mk<T>(zi[k].x + zi[k].y, zi[k].x - zi[k].y);  // (DC, Nyquist) :459-462
-                                        if constexpr (EX) store_ex(0, dcny);
-                                        else st_stream(gout, dcny);
+                                        st_stream(gout, mk<T>(zi[k].x + zi[k].y, zi[k].x - zi[k].y));  // (DC, Nyquist) :459-462
                                     } else {
                                         cx<T> oi, oc;
                                         r2c_pair(zi[k], zc[k], tw_[k], oi, oc);
-                                        if constexpr (EX) {
-                                            store_ex(i, oi);
-                                            store_ex(N - i, oc);
-                                        } else {
-                                            st_stream(gout + i, oi);
-                                            st_stream(gout + (mod ? N - 1 - i : N - i), oc);  // self-pair: second write wins
-                                        }
+                                        st_stream(gout + i, oi);
+                                        st_stream(gout + (mod ? N - 1 - i : N - i), oc);  // self-pair: second write wins
                                     }
                                 }
                             }
@@ -457,19 +523,13 @@ fused_fft_kernel(const cx<typename Cfg::T> *__restrict__ in, cx<typename Cfg::T>
                         for (int u = 0; u < U; ++u)
 #pragma unroll
                             for (int r = 0; r < R; ++r)
-                                if (has(u)) {
-                                    if constexpr (EX) store_ex(t + TX * u + P * r, cswap(v[u * R + r]));
-                                    else st_stream(gout + t + TX * u + P * r, cswap(v[u * R + r]));
-                                }
+                                if (has(u)) st_stream(gout + t + TX * u + P * r, cswap(v[u * R + r]));
                     } else {
 #pragma unroll
                         for (int u = 0; u < U; ++u)
 #pragma unroll
                             for (int r = 0; r < R; ++r)
-                                if (has(u)) {
-                                    if constexpr (EX) store_ex(t + TX * u + P * r, v[u * R + r]);
-                                    else st_stream(gout + t + TX * u + P * r, v[u * R + r]);
-                                }
+                                if (has(u)) st_stream(gout + t + TX * u + P * r, v[u * R + r]);
                     }
                 }
             }

@@ -124,8 +124,13 @@ __global__ void ex_copy_kernel(const void *__restrict__ src_, void *__restrict__
                                long long src_dist, long long src_stride, long long dst_dist, long long dst_stride,
                                const T *__restrict__ mul, int mul_kind, long long mul_dist, int packed0) {
     const long long total = len * batch;
-    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
-        const long long b = idx / len, e = idx - b * len;
+    // (b, e) advance incrementally: a 64-bit division per element would make this copy instruction-bound
+    const long long step = (long long)gridDim.x * blockDim.x, step_b = step / len, step_e = step - step_b * len;
+    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    long long b = idx / len, e = idx - b * len;
+#pragma unroll 4
+    for (; idx < total; idx += step, b += step_b, e += step_e) {
+        if (e >= len) { e -= len; ++b; }
         if constexpr (REAL_SIDE) {
             const T *src = static_cast<const T *>(src_);
             T *dst = static_cast<T *>(dst_);
