@@ -96,7 +96,27 @@ struct FusedIo {
     long long pre_dist, post_dist;   // elements between the multipliers of consecutive transforms (0: shared by all)
     int pre_kind, post_kind;         // FUSED_MUL_*
     int in_vec, out_vec;             // real side: sample pairs (2i, 2i+1) may be accessed as one aligned vector
+    // "lite" sides need no staging through shared memory: the first pass gathers straight from HBM like the plain kernel
+    // (unit stride, real window or none -- overlapping frames only move the base pointer), the last pass stores
+    // straight from registers (unit stride, no multiplier).  Set by fused_io_finalize().
+    int lite_in, lite_out;
 };
+
+// Derived flags of an extended-I/O request (host side; the CPU emulation of the kernels uses the same function).
+// mode: FUSED_C2C / FUSED_R2C / FUSED_C2R.  Strides and distances must already hold their defaults.
+template <typename T>
+inline void fused_io_finalize(FusedIo<T> &io, int mode, const void *in, const void *out) {
+    const bool in_real = mode == 1 /* FUSED_R2C */, out_real = mode == 2 /* FUSED_C2R */;
+    const size_t vec = 2 * sizeof(T);
+    // real side: the sample pair (2i, 2i+1) is one aligned vector when every frame starts on an even sample
+    io.in_vec = in_real && io.in_stride == 1 && io.in_dist % 2 == 0 && reinterpret_cast<size_t>(in) % vec == 0;
+    io.out_vec = out_real && io.out_stride == 1 && io.out_dist % 2 == 0 && reinterpret_cast<size_t>(out) % vec == 0;
+    const bool window_ok = io.pre_kind == FUSED_MUL_NONE ||
+                           (io.pre_kind == FUSED_MUL_REAL &&
+                            (!in_real || (reinterpret_cast<size_t>(io.pre) % vec == 0 && io.pre_dist % 2 == 0)));
+    io.lite_in = mode != 2 && window_ok && (in_real ? io.in_vec != 0 : io.in_stride == 1);
+    io.lite_out = io.post_kind == FUSED_MUL_NONE && (out_real ? io.out_vec != 0 : io.out_stride == 1);
+}
 
 #ifdef __CUDACC__
 
@@ -289,6 +309,10 @@ fused_fft_kernel(const cx<typename Cfg::T> *__restrict__ in, cx<typename Cfg::T>
         const bool active = tr < batch;
         const cx<T> *gin = in + (active ? tr : 0) * N;
         cx<T> *gout = out + (active ? tr : 0) * N;
+        if constexpr (EX) {  // lite sides: the transform's own base pointer (distances count reals on a real side)
+            gin = reinterpret_cast<const cx<T> *>(reinterpret_cast<const T *>(in) + (active ? tr : 0) * io.in_dist * (is_r2c ? 1 : 2));
+            gout = reinterpret_cast<cx<T> *>(reinterpret_cast<T *>(out) + (active ? tr : 0) * io.out_dist * (is_c2r ? 1 : 2));
+        }
         cx<T> v[E];
         if constexpr (PF) {
             const unsigned bytes = group_bytes(g);
@@ -305,7 +329,9 @@ fused_fft_kernel(const cx<typename Cfg::T> *__restrict__ in, cx<typename Cfg::T>
         // EX: transforms of this group, and the cooperative gather of their inputs -- layout and pre-multiplier are
         // applied on the way into the dense shared-memory image the first pass reads (as with PF = 2, minus the TMA)
         const int ex_cnt = (int)((batch - g * FPB < FPB) ? (batch - g * FPB) : FPB);
-        if constexpr (EX) {
+        bool ex_lite_in = false, ex_lite_out = false;
+        if constexpr (EX) { ex_lite_in = io.lite_in != 0; ex_lite_out = io.lite_out != 0; }
+        if constexpr (EX) if (!ex_lite_in) {
             cx<T> *st = const_cast<cx<T> *>(stage_all);
             ex_dispatch(is_r2c ? (io.in_vec ? 2 : 1) : 0, io.pre_kind, [&](auto side, auto kind) {
 #pragma unroll 8
@@ -332,7 +358,38 @@ fused_fft_kernel(const cx<typename Cfg::T> *__restrict__ in, cx<typename Cfg::T>
             auto has = [&](int u) { return !ragged || (t + TX * u) < NR; };
             // ---- gather inputs
             if constexpr (first) {
-                if (is_c2r) {
+                if (EX && ex_lite_in) {
+                    // extended I/O, lite input: gather straight from HBM as the plain kernel does; the window (if any)
+                    // is one more L1-resident load per element.  R2C: element idx = samples (2 idx, 2 idx + 1).
+                    if constexpr (EX) {
+                        if (active) {
+                            const T *wtab = io.pre + tr * io.pre_dist;
+                            auto gather = [&](auto kind) {
+                                constexpr int KD = decltype(kind)::value;
+#pragma unroll
+                                for (int u = 0; u < U; ++u)
+#pragma unroll
+                                    for (int j = 0; j < R; ++j)
+                                        if (has(u)) {
+                                            const int idx = t + TX * u + NR * j;
+                                            cx<T> x = ld_stream(gin + idx);
+                                            if constexpr (KD == FUSED_MUL_REAL) {
+                                                if (is_r2c) {
+                                                    const cx<T> w = ld_table(reinterpret_cast<const cx<T> *>(wtab) + idx);
+                                                    x = mk<T>(x.x * w.x, x.y * w.y);
+                                                } else {
+                                                    const T w = __ldg(wtab + idx);
+                                                    x = mk<T>(x.x * w, x.y * w);
+                                                }
+                                            }
+                                            v[u * R + j] = inverse ? cswap(x) : x;
+                                        }
+                            };
+                            if (io.pre_kind == FUSED_MUL_REAL) gather(ic<FUSED_MUL_REAL>{});
+                            else gather(ic<FUSED_MUL_NONE>{});
+                        }
+                    }
+                } else if (is_c2r) {
                     if (STAGED || active) {
 #pragma unroll
                         for (int u = 0; u < U; ++u)
@@ -385,7 +442,8 @@ fused_fft_kernel(const cx<typename Cfg::T> *__restrict__ in, cx<typename Cfg::T>
                         if (has(u)) v[u * R + j] = sm[Cfg::pad(t + TX * u + NR * j)];
                 __syncthreads();  // everyone has read: the buffer may be overwritten
             }
-            if constexpr (first && (Cfg::PF == 2 || EX)) __syncthreads();  // everyone holds its inputs: the dense image may be overwritten
+            if constexpr (first && Cfg::PF == 2) __syncthreads();  // everyone holds its inputs: the dense image may be overwritten
+            if constexpr (first && EX) { if (!ex_lite_in) __syncthreads(); }
             if constexpr (last && !first && Cfg::PF == 2) {
                 if (!is_r2c) prefetch(g + gridDim.x);  // the exchange buffer is free from here on (R2C: after its epilogue)
             }
@@ -423,7 +481,9 @@ fused_fft_kernel(const cx<typename Cfg::T> *__restrict__ in, cx<typename Cfg::T>
                 if constexpr (Cfg::PF == 1 && first) prefetch(g + gridDim.x);  // every thread has consumed the staging buffer
             } else {
                 // last pass: P == N/R, m' == 0, racc == b  ->  natural-order index b + P*r
-                if constexpr (EX) {
+                bool stored = false;
+                if constexpr (EX) if (!ex_lite_out) {
+                    stored = true;
                     // results -> shared memory in natural order; ONE cooperative rolled loop per group then applies the
                     // RealFFT post-twiddle (R2C), the post-multiplier and the output layout
 #pragma unroll
@@ -464,6 +524,9 @@ fused_fft_kernel(const cx<typename Cfg::T> *__restrict__ in, cx<typename Cfg::T>
                         });
                     }
                     __syncthreads();  // the next group's gather overwrites the image
+                }
+                if (stored) {
+                    // extended I/O: done above
                 } else if (is_r2c) {
 #pragma unroll
                     for (int u = 0; u < U; ++u)

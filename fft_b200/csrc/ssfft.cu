@@ -671,10 +671,8 @@ int exec_ex_typed(ssfft_plan *pl, int op, const void *in, void *out, long long b
         f.pre = (const T *)x.pre; f.post = (const T *)x.post;
         f.pre_dist = x.pre_dist; f.post_dist = x.post_dist;
         f.pre_kind = x.pre_kind; f.post_kind = x.post_kind;
-        // real side: the sample pair (2i, 2i+1) is one aligned vector when every frame starts on an even sample
-        f.in_vec = x.in_real && x.is == 1 && x.id % 2 == 0 && (uintptr_t)in % sizeof(cx<T>) == 0;
-        f.out_vec = x.out_real && x.os == 1 && x.od % 2 == 0 && (uintptr_t)out % sizeof(cx<T>) == 0;
         const int mode = op == EX_C2C ? FUSED_C2C : op == EX_R2C ? FUSED_R2C : FUSED_C2R;
+        fused_io_finalize(f, mode, in, out);  // vector accesses on the real side, sides that need no staging
         int rc = fused_registry()[pl->fused.id].launch_ex(pl->fused.d_twiddles, in, out, batch, op == EX_C2R ? 1 : inverse, mode,
                                                           pl->d_rtw, &f, s);
         ++g_launches;

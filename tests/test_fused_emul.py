@@ -7,8 +7,8 @@ The configuration list is read from the registry sources (fused_f*.cu), so a new
 touching this test.  Each configuration runs C2C forward / inverse / in place / from pointers that are only 8-byte
 aligned, R2C, C2R and both ModifiedRealFFT flavours on a batch that makes CTAs loop and ends in a ragged group, and is
 compared with the oracle within the tolerance of the GPU parity tests (1e-6 log2 N float, 1e-14 log2 N double).
-The extended-I/O instantiation (ssfft_exec_*_ex: strided / overlapping layouts, fused windows and filters) runs ten
-layouts per configuration, checked for values AND for stray writes outside the requested layout; a misaligned vector
+The extended-I/O instantiation (ssfft_exec_*_ex: strided / overlapping layouts, fused windows and filters) runs fifteen
+layouts per configuration (staged through shared memory and "lite" sides), checked for values AND for stray writes outside the requested layout; a misaligned vector
 access (which x86 would tolerate and the GPU would not) aborts.
 
 This is a check of index logic, barriers and staging hazards -- the GPU tests (-m gpu) remain the parity tests proper.
@@ -82,5 +82,5 @@ def test_every_fused_kernel_runs_on_cpu(tmp_path, oracle):
     for res in results:
         assert res.returncode == 0 and "FUSED-EMUL-OK" in res.stdout, res.stdout[-4000:] + res.stderr[-2000:]
         runs += int(res.stdout.split(" runs over")[0].split()[-1])
-    # per configuration: 8 plain runs (x2 when it prefetches: both TMA timings) + 10 extended-I/O layouts; + ex_copy_kernel
-    assert runs >= 18 * len(cfgs) + 12
+    # per configuration: 8 plain runs (x2 when it prefetches: both TMA timings) + 15 extended-I/O layouts; + ex_copy_kernel
+    assert runs >= 23 * len(cfgs) + 12
