@@ -272,7 +272,10 @@ fused_fft_kernel(const cx<typename Cfg::T> *__restrict__ in, cx<typename Cfg::T>
     const int t = threadIdx.x, f = threadIdx.y;
     cx<T> *sm = reinterpret_cast<cx<T> *>(ssfft_smem) + (size_t)f * Cfg::SM_STRIDE;
     const cx<T> *stage_all = reinterpret_cast<const cx<T> *>((Cfg::PF == 2 || EX) ? ssfft_smem : ssfft_smem + Cfg::xchg_bytes);
-    const cx<T> *stage = stage_all + (size_t)f * N;
+    // EX: images one element apart from a multiple of N, so that a copy loop running over the transforms of a group
+    // (column layouts) does not put all of them on the same shared-memory bank
+    constexpr int STAGE_STRIDE = EX ? N + 1 : N;
+    const cx<T> *stage = stage_all + (size_t)f * STAGE_STRIDE;
     const long long groups = (batch + FPB - 1) / FPB;
     const bool leader = (t == 0 && f == 0);
     constexpr bool mod = MOD;                                             // half-bin-shifted real transform
@@ -333,11 +336,14 @@ fused_fft_kernel(const cx<typename Cfg::T> *__restrict__ in, cx<typename Cfg::T>
         if constexpr (EX) { ex_lite_in = io.lite_in != 0; ex_lite_out = io.lite_out != 0; }
         if constexpr (EX) if (!ex_lite_in) {
             cx<T> *st = const_cast<cx<T> *>(stage_all);
+            // consecutive threads take consecutive samples of a transform -- or, when the transforms of the group are
+            // closer together in memory than the samples of one transform (columns of a matrix), consecutive transforms
+            const bool tr_fastest = FPB > 1 && ex_cnt == FPB && io.in_dist < io.in_stride;
             ex_dispatch(is_r2c ? (io.in_vec ? 2 : 1) : 0, io.pre_kind, [&](auto side, auto kind) {
 #pragma unroll 8
                 for (int i = f * TX + t; i < ex_cnt * N; i += TX * FPB) {
-                    const int ff = i / N, idx = i - ff * N;
-                    st[i] = ex_load<decltype(side)::value, decltype(kind)::value>(in, io, g * FPB + ff, idx, is_c2r);
+                    const int ff = tr_fastest ? i % FPB : i / N, idx = tr_fastest ? i / FPB : i - ff * N;
+                    st[ff * STAGE_STRIDE + idx] = ex_load<decltype(side)::value, decltype(kind)::value>(in, io, g * FPB + ff, idx, is_c2r);
                 }
             });
             __syncthreads();
@@ -493,13 +499,14 @@ fused_fft_kernel(const cx<typename Cfg::T> *__restrict__ in, cx<typename Cfg::T>
                             if (has(u)) sm[Cfg::pad(t + TX * u + P * r)] = inverse ? cswap(v[u * R + r]) : v[u * R + r];
                     __syncthreads();
                     const cx<T> *img = reinterpret_cast<const cx<T> *>(ssfft_smem);
+                    const bool tr_fastest = FPB > 1 && ex_cnt == FPB && io.out_dist < io.out_stride;  // as in the gather
                     if (is_r2c) {
                         constexpr int H2 = N / 2 + 1;  // pairs (k, N-k), k = 0 .. N/2  (RealFFT::fft :459-472)
                         ex_dispatch(0, io.post_kind, [&](auto side, auto kind) {
                             constexpr int SD = decltype(side)::value, KD = decltype(kind)::value;
 #pragma unroll 2
                             for (int i = f * TX + t; i < ex_cnt * H2; i += TX * FPB) {
-                                const int ff = i / H2, k = i - ff * H2;
+                                const int ff = tr_fastest ? i % FPB : i / H2, k = tr_fastest ? i / FPB : i - ff * H2;
                                 const cx<T> *row = img + (size_t)ff * Cfg::SM_STRIDE;
                                 const cx<T> zi = row[Cfg::pad(k)], zc = row[Cfg::pad(k ? N - k : 0)];
                                 const long long trk = g * FPB + ff;
@@ -517,7 +524,7 @@ fused_fft_kernel(const cx<typename Cfg::T> *__restrict__ in, cx<typename Cfg::T>
                         ex_dispatch(is_c2r ? (io.out_vec ? 2 : 1) : 0, io.post_kind, [&](auto side, auto kind) {
 #pragma unroll 4
                             for (int i = f * TX + t; i < ex_cnt * N; i += TX * FPB) {
-                                const int ff = i / N, k = i - ff * N;
+                                const int ff = tr_fastest ? i % FPB : i / N, k = tr_fastest ? i / FPB : i - ff * N;
                                 ex_store<decltype(side)::value, decltype(kind)::value>(out, io, g * FPB + ff, k,
                                                                                        img[(size_t)ff * Cfg::SM_STRIDE + Cfg::pad(k)], false);
                             }
