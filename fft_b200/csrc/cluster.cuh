@@ -370,7 +370,7 @@ template <typename Cfg, int KIND>
 __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINB)
 cluster_fft_kernel(ClusterParams<typename Cfg::T> q, const __grid_constant__ CUtensorMap tmap) {
     using T = typename Cfg::T;
-    extern __shared__ __align__(128) unsigned char ssfft_smem[];
+    SSFFT_DYNAMIC_SMEM(ssfft_smem);
     __shared__ __align__(8) unsigned long long bars[2];  // [0] "bufB full" (peers' st.async)   [1] input tile (TMA)
     cx<T> *bufA = reinterpret_cast<cx<T> *>(ssfft_smem);
     cx<T> *bufB = bufA + Cfg::BUFA;

@@ -9,6 +9,14 @@
 
 #define SSFFT_HD __host__ __device__ __forceinline__
 
+// The dynamic shared memory of a CTA.  Under SSFFT_EMUL (CPU execution of the kernels, tests/host/simt/) several CTAs
+// of a cluster are alive at once, so the name is a pointer to the current CTA's buffer instead of one array.
+#ifdef SSFFT_EMUL
+#define SSFFT_DYNAMIC_SMEM(name) unsigned char *name = simt::dynamic_smem()
+#else
+#define SSFFT_DYNAMIC_SMEM(name) extern __shared__ __align__(128) unsigned char name[]
+#endif
+
 namespace ssfft {
 
 template <typename T>

@@ -146,6 +146,7 @@ __device__ __forceinline__ cx<T> ld_table(const cx<T> *p) {
 
 #ifdef SSFFT_EMUL
 // Host emulation of the kernels (tests/host/simt/simt_emul.h, CPU tests only): same call sites, hooks instead of PTX.
+inline unsigned smem_u32(const void *p) { return (unsigned)reinterpret_cast<size_t>(p); }
 inline void mbar_init(unsigned long long *, unsigned) { simt::mbar_init(); }
 inline void mbar_expect_tx(unsigned long long *, unsigned bytes) { simt::mbar_expect_tx(bytes); }
 inline void mbar_wait(unsigned long long *, unsigned parity) { simt::mbar_wait(parity); }
@@ -267,7 +268,7 @@ fused_fft_kernel(const cx<typename Cfg::T> *__restrict__ in, cx<typename Cfg::T>
     constexpr bool STAGED = (Cfg::PF != 0) || EX;  // the first pass reads its input from a dense shared-memory image
     constexpr int N = Cfg::N, TX = Cfg::TX, FPB = Cfg::FPB, E = Cfg::E, NP = Cfg::NP;
     constexpr bool PF = Cfg::PF != 0;
-    extern __shared__ __align__(128) unsigned char ssfft_smem[];
+    SSFFT_DYNAMIC_SMEM(ssfft_smem);
     __shared__ __align__(8) unsigned long long mbar;
     const int t = threadIdx.x, f = threadIdx.y;
     cx<T> *sm = reinterpret_cast<cx<T> *>(ssfft_smem) + (size_t)f * Cfg::SM_STRIDE;

@@ -141,7 +141,7 @@ SSFFT_HD void run_pass(int R, int n, int P, const cx<T> *roots, const Src &src, 
 // blockDim = (TX, FPB): threadIdx.x strides over butterflies, threadIdx.y picks the transform in the block.
 template <typename T>
 __global__ void generic_fft_kernel(const cx<T> *__restrict__ in, cx<T> *__restrict__ out, GenericParams<T> p) {
-    extern __shared__ __align__(128) unsigned char ssfft_smem[];
+    SSFFT_DYNAMIC_SMEM(ssfft_smem);
     cx<T> *bufA = reinterpret_cast<cx<T> *>(ssfft_smem) + (size_t)threadIdx.y * 2 * p.smem_stride;
     cx<T> *bufB = bufA + p.smem_stride;
     const int tx = threadIdx.x, TX = blockDim.x;

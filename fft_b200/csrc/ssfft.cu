@@ -184,17 +184,8 @@ int setup_tiled(ssfft_plan *pl, size_t total, bool real, bool *ok) {
     int ctb_log2 = 0;
     while (((size_t)1 << ctb_log2) < ctb) ++ctb_log2;
     pl->ctb_log2 = ctb_log2;
-    const size_t rows_live = real ? n1 / 2 + 1 : n1;
-    const size_t rows = (rows_live + ctb - 1) / ctb * ctb;
-    std::vector<T> h(2 * rows * n2, (T)0);
-    for (size_t k1 = 0; k1 < rows_live; ++k1)
-        for (size_t c = 0; c < n2; ++c) {
-            unsigned long long q = (unsigned long long)k1 * c % total;
-            long double a = 2.0L * 3.14159265358979323846264338327950288L * (long double)q / (long double)total;
-            const size_t o = (k1 / ctb) * (ctb * n2) + c * ctb + (k1 % ctb);
-            h[2 * o] = (T)cosl(a);
-            h[2 * o + 1] = (T)(-sinl(a));
-        }
+    std::vector<T> h;
+    const size_t rows = fill_fourstep_twiddles<T>(h, total, n1, n2, ctb, real);
     CU(cudaMalloc(&pl->d_tw4, h.size() * sizeof(T)));
     CU(cudaMemcpy(pl->d_tw4, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
     pl->scratch_per = rows * n2;

@@ -408,7 +408,7 @@ __device__ __forceinline__ void tile_body(const TileParams<typename Cfg::T> &p, 
 template <typename Cfg, int FLAVOR>
 __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINB) tile_fft_kernel(TileParams<typename Cfg::T> p) {
     using T = typename Cfg::T;
-    extern __shared__ __align__(128) unsigned char ssfft_smem[];
+    SSFFT_DYNAMIC_SMEM(ssfft_smem);
     cx<T> *sm = reinterpret_cast<cx<T> *>(ssfft_smem);
     const int width = tile_width<FLAVOR>(p.n1, p.n2);
     const int tiles = (width + Cfg::CT - 1) / Cfg::CT;
@@ -448,6 +448,13 @@ struct FourStepParams {
     int use_tma;          // the tensor map passed next to these parameters is valid (set by the launcher)
 };
 
+#ifdef SSFFT_EMUL  // CPU execution of the kernels (tests/host/simt/simt_emul.h): hooks instead of PTX
+inline unsigned cluster_ctarank() { return simt::cluster_ctarank(); }
+inline unsigned cluster_nctarank() { return simt::cluster_nctarank(); }
+inline void cluster_barrier() { simt::cluster_barrier(); }
+inline unsigned ld_acquire_gpu(const unsigned *p) { simt::spin_yield(); return *p; }
+inline void discard_l2_line(const void *a) { memset(const_cast<void *>(a), 0xff, 128); }  // poison: nobody may read it again
+#else
 __device__ __forceinline__ unsigned cluster_ctarank() {
     unsigned r;
     asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
@@ -461,6 +468,13 @@ __device__ __forceinline__ unsigned cluster_nctarank() {
 __device__ __forceinline__ void cluster_barrier() {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+__device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned *p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void discard_l2_line(const void *a) { asm volatile("discard.global.L2 [%0], 128;" ::"l"(a) : "memory"); }
+#endif
 
 // Barrier over the CTAs of a group (all co-resident: the launch is cooperative / sized to residency).  The counter
 // only grows; `target` is the value it reaches when every CTA of the group has arrived for this barrier.
@@ -472,8 +486,7 @@ __device__ __forceinline__ void group_barrier(unsigned *ctr, unsigned target) {
         atomicAdd(ctr, 1u);
         const long long t0 = clock64();
         for (;;) {
-            unsigned v;
-            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
+            const unsigned v = ld_acquire_gpu(ctr);
             if (v >= target) break;
             __nanosleep(40);
             if (clock64() - t0 > 4000000000LL) __trap();
@@ -491,7 +504,7 @@ __device__ __forceinline__ void discard_lines(const cx<T> *base, long long first
     for (int i = tid; i < count * groups; i += nthreads) {
         const int g = i / count, l = i - g * count;
         const char *a = reinterpret_cast<const char *>(base) + (first_line + (long long)g * stride_lines + l) * 128;
-        asm volatile("discard.global.L2 [%0], 128;" ::"l"(a) : "memory");
+        discard_l2_line(a);
     }
 }
 
@@ -531,7 +544,7 @@ __global__ void __launch_bounds__(CfgA::THREADS, (fourstep_minb<CfgA, CfgB>()))
 fourstep_cluster_kernel(FourStepParams<typename CfgA::T> q, const __grid_constant__ CUtensorMap tmap) {
     using T = typename CfgA::T;
     static_assert(CfgA::THREADS == CfgB::THREADS, "both stages must use the same CTA size");
-    extern __shared__ __align__(128) unsigned char ssfft_smem[];
+    SSFFT_DYNAMIC_SMEM(ssfft_smem);
     __shared__ __align__(8) unsigned long long stage_bar;
     cx<T> *sm = reinterpret_cast<cx<T> *>(ssfft_smem);
     const int crank = (int)cluster_ctarank(), csize0 = (int)cluster_nctarank();
@@ -777,6 +790,25 @@ inline int find_tile(size_t len) {
     for (size_t i = 0; i < reg.size(); ++i)
         if (reg[i].prec == prec && (size_t)reg[i].len == len) return (int)i;
     return -1;
+}
+
+// Four-step twiddles W_total^(k1 * c), rows k1 < n1 (real transforms: k1 <= n1/2), columns c < n2, in the tile-major
+// layout of the scratch (see tm_off): blocks of `ctb` rows, [c][k1 % ctb] inside a block; rows padded to whole blocks.
+// Returns the padded row count (scratch elements per transform = rows * n2).
+template <typename T>
+inline size_t fill_fourstep_twiddles(std::vector<T> &h, size_t total, size_t n1, size_t n2, size_t ctb, bool real) {
+    const size_t rows_live = real ? n1 / 2 + 1 : n1;
+    const size_t rows = (rows_live + ctb - 1) / ctb * ctb;
+    h.assign(2 * rows * n2, (T)0);
+    for (size_t k1 = 0; k1 < rows_live; ++k1)
+        for (size_t c = 0; c < n2; ++c) {
+            unsigned long long q = (unsigned long long)k1 * c % total;
+            long double a = 2.0L * 3.14159265358979323846264338327950288L * (long double)q / (long double)total;
+            const size_t o = (k1 / ctb) * (ctb * n2) + c * ctb + (k1 % ctb);
+            h[2 * o] = (T)cosl(a);
+            h[2 * o + 1] = (T)(-sinl(a));
+        }
+    return rows;
 }
 
 template <typename T>

@@ -17,6 +17,7 @@
 #define __launch_bounds__(...)
 #define __align__(n) __attribute__((aligned(n)))
 #define __shared__  // `extern __shared__ T name[]` binds to a host array defined by the test; see simt_emul.h
+#define __grid_constant__
 
 struct uint3 { unsigned x, y, z; };
 struct dim3 {
@@ -44,9 +45,13 @@ inline void simt_check_aligned(const void *p, size_t size) {
 }
 template <typename V> inline V __ldcs(const V *p) { simt_check_aligned(p, sizeof(V)); return *p; }
 template <typename V> inline V __ldg(const V *p) { simt_check_aligned(p, sizeof(V)); return *p; }
+template <typename V> inline V __ldcg(const V *p) { simt_check_aligned(p, sizeof(V)); return *p; }
+inline unsigned atomicAdd(unsigned *p, unsigned v) { const unsigned old = *p; *p += v; return old; }  // fibers never preempt
 template <typename V> inline void __stcs(V *p, V v) { simt_check_aligned(p, sizeof(V)); *p = v; }
 
 void __syncthreads();  // yields to the block scheduler (simt_emul.h)
+inline void __threadfence() {}
+inline void __nanosleep(unsigned) {}
 inline long long clock64() { return 0; }
 [[noreturn]] inline void __trap() { abort(); }
 inline size_t __cvta_generic_to_shared(const void *p) { return (size_t)(uintptr_t)p; }
