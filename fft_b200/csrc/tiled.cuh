@@ -526,6 +526,35 @@ __host__ __device__ constexpr size_t fourstep_smem_bytes() {
     return (CfgA::smem_bytes > CfgB::smem_bytes ? CfgA::smem_bytes : CfgB::smem_bytes) * (fourstep_staged<CfgA, CfgB>() ? 2 : 1);
 }
 
+// L2 prefetch hints for the column stage (complex and R2C): while a CTA transforms one stage-1 tile it asks for the lines
+// of the NEXT stage-1 tile it will work on (same transform, or its first tile of the next transform) with
+// prefetch.global.L2 -- one instruction per 128-byte line, no registers, no shared memory, no wait: the loads of the next
+// tile then hit L2 instead of HBM.  Motivation: 25 % of the stall samples of the 65536 kernel sit on the first use of
+// the tile loads (profiles/c2c65536_fourstep_cluster_r01b_stalls.txt) and the two schemes that HOLD the prefetched data
+// (cp.async staging, register double buffer) lost more occupancy than they hid.  Runs on the CPU emulation
+// (tests/test_tiled_emul.py builds it); NOT YET MEASURED on the GPU, hence off by default: NVFLAGS += -DSSFFT_FOURSTEP_L2PF=1.
+#ifndef SSFFT_FOURSTEP_L2PF
+#define SSFFT_FOURSTEP_L2PF 0
+#endif
+#ifdef SSFFT_EMUL
+inline void prefetch_l2(const void *a) { (void)*static_cast<const volatile unsigned char *>(a); }  // must be a readable address
+#else
+__device__ __forceinline__ void prefetch_l2(const void *a) { asm volatile("prefetch.global.L2 [%0];" ::"l"(a)); }
+#endif
+// every 128-byte line the first pass of stage-1 tile `lane0` will read (TILE_A_C2C / TILE_A_R2C: row idx of the tile is
+// CT consecutive elements)
+template <typename Cfg, int FLAVOR, int N1C, int N2C>
+__device__ __forceinline__ void tile_l2_prefetch(const cx<typename Cfg::T> *gin, int lane0, int tid) {
+    using T = typename Cfg::T;
+    static_assert(FLAVOR == TILE_A_C2C || FLAVOR == TILE_A_R2C, "user-buffer column tiles only");
+    constexpr int kPerLine = 128 / (int)sizeof(cx<T>);
+    constexpr int kLines = (Cfg::CT + kPerLine - 1) / kPerLine;  // lines per row of the tile
+    for (int i = tid; i < Cfg::L * kLines; i += Cfg::THREADS) {
+        const int idx = i / kLines, part = i - idx * kLines;
+        prefetch_l2(tile_src<FLAVOR, Cfg::L>(gin, lane0 + part * kPerLine, idx, N1C, N2C, 0));
+    }
+}
+
 #ifndef SSFFT_FOURSTEP_REGPREFETCH
 #define SSFFT_FOURSTEP_REGPREFETCH 0  // measured slower (65536 C2C: 50.6 % -> 43.9 %): 3 CTAs/SM beat 2 CTAs/SM + register prefetch
 #endif
@@ -670,6 +699,12 @@ fourstep_cluster_kernel(FourStepParams<typename CfgA::T> q, const __grid_constan
                         }
                     }
                 };
+                if constexpr (SSFFT_FOURSTEP_L2PF != 0 && KIND != 2) {
+                    // hint the next stage-1 tile of this CTA into L2 while this one is transformed
+                    const int tid = threadIdx.x + threadIdx.y * blockDim.x;
+                    if (next < tiles1) tile_l2_prefetch<Cfg1, F1, CfgA::L, CfgB::L>(uin, next * Cfg1::CT, tid);
+                    else if (Bn < q.batch && rank < tiles1) tile_l2_prefetch<Cfg1, F1, CfgA::L, CfgB::L>(uin_next, rank * Cfg1::CT, tid);
+                }
                 tile_body<Cfg1, F1, CfgA::L, CfgB::L, kCtbLog, kStage>(p1, uin, scr, tile * Cfg1::CT, sm, st, hook);
             }
         }

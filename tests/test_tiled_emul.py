@@ -47,7 +47,12 @@ def test_pair_registry_is_parsed():
 
 
 @pytest.mark.skipif(shutil.which("g++") is None, reason="needs g++")
-def test_every_four_step_kernel_runs_on_cpu(tmp_path, oracle):
+@pytest.mark.parametrize("variant", ["default", "l2_prefetch_hints"])
+def test_every_four_step_kernel_runs_on_cpu(tmp_path, oracle, variant):
+    """variant l2_prefetch_hints: the opt-in build -DSSFFT_FOURSTEP_L2PF=1 (next column tile hinted into L2), kept
+    green here so that it can be measured on the GPU as it is; the emulated prefetch READS the hinted address, so a
+    hint outside the input buffer would fault under a sanitizer."""
+    extra = ["-DSSFFT_FOURSTEP_L2PF=1"] if variant == "l2_prefetch_hints" else []
     pairs = registered_pairs()
     # largest pairs first so the parallel chunks finish together
     pairs.sort(key=lambda p: -int(p[0].split(",")[1]) * int(p[1].split(",")[1]))
@@ -58,7 +63,7 @@ def test_every_four_step_kernel_runs_on_cpu(tmp_path, oracle):
         inc = tmp_path / f"pairs_{i}.inc"
         inc.write_text("".join(f'PAIR(({a}), ({b}), "{n}")\n' for a, b, n in chunks[i]))
         exe = str(tmp_path / f"tiled_emul_{i}")
-        cmd = ["g++", "-std=c++17", "-O1", "-D__CUDACC__", "-DSSFFT_EMUL", f'-DTILED_PAIR_INC="{inc}"',
+        cmd = ["g++", "-std=c++17", "-O1", "-D__CUDACC__", "-DSSFFT_EMUL", *extra, f'-DTILED_PAIR_INC="{inc}"',
                "-I" + os.path.join(HOST, "simt"), os.path.join(HOST, "tiled_emul.cpp"),
                "-L" + os.path.join(ROOT, "oracle"), "-loracle", "-Wl,-rpath," + os.path.join(ROOT, "oracle"), "-o", exe]
         subprocess.run(cmd, check=True, capture_output=True, timeout=900)
