@@ -675,10 +675,19 @@ int exec_ex_typed(ssfft_plan *pl, int op, const void *in, void *out, long long b
     const void *src = in;
     void *dst = out;
     int rc;
+    // the columns of a row-major [N][batch] matrix (stride = batch, dist = 1, no multiplier) move with the tiled
+    // transpose (32 x 32 tiles through shared memory, both sides coalesced) instead of the element-wise copy, whose
+    // strided side touches one element per 32-byte sector
+    const int prec = sizeof(T) == 4 ? SSFFT_F32 : SSFFT_F64;
+    const bool col_in = !x.in_real && !x.pre && x.id == 1 && x.is == batch && batch > 1;
+    const bool col_out = !x.out_real && !x.post && x.od == 1 && x.os == batch && batch > 1;
     if (!x.in_plain) {
         if ((rc = ex_workspace(&pl->d_ex_in, &pl->ex_in_bytes, bytes))) return rc;
-        rc = launch_ex_copy<T>(x.in_real, in, pl->d_ex_in, x.in_len, batch, x.id, x.is, x.in_len, 1, x.pre, x.pre_kind, x.pre_dist,
-                               x.packed && !x.in_real, s);
+        if (col_in)  // ws[c][r] = in[r][c]
+            rc = ssfft_transpose_twiddle(in, pl->d_ex_in, 1, (size_t)x.in_len, (size_t)batch, 0, 0, 0, prec, s);
+        else
+            rc = launch_ex_copy<T>(x.in_real, in, pl->d_ex_in, x.in_len, batch, x.id, x.is, x.in_len, 1, x.pre, x.pre_kind,
+                                   x.pre_dist, x.packed && !x.in_real, s);
         if (rc) return rc;
         src = pl->d_ex_in;
     }
@@ -687,9 +696,13 @@ int exec_ex_typed(ssfft_plan *pl, int op, const void *in, void *out, long long b
         dst = pl->d_ex_out;
     }
     if ((rc = exec_plain<T>(pl, op, src, dst, batch, inverse, s))) return rc;
-    if (!x.out_plain)
-        rc = launch_ex_copy<T>(x.out_real, dst, out, x.out_len, batch, x.out_len, 1, x.od, x.os, x.post, x.post_kind, x.post_dist,
-                               x.packed && !x.out_real, s);
+    if (!x.out_plain) {
+        if (col_out)  // out[k][c] = ws[c][k]
+            rc = ssfft_transpose_twiddle(dst, out, 1, (size_t)batch, (size_t)x.out_len, 0, 0, 0, prec, s);
+        else
+            rc = launch_ex_copy<T>(x.out_real, dst, out, x.out_len, batch, x.out_len, 1, x.od, x.os, x.post, x.post_kind,
+                                   x.post_dist, x.packed && !x.out_real, s);
+    }
     return rc;
 }
 

@@ -16,7 +16,9 @@
 #define __forceinline__ inline __attribute__((always_inline))
 #define __launch_bounds__(...)
 #define __align__(n) __attribute__((aligned(n)))
-#define __shared__  // `extern __shared__ T name[]` binds to a host array defined by the test; see simt_emul.h
+// Static shared variables become function-local statics (one copy per kernel instantiation, shared by the fibers of
+// the CTA; kernels that keep several CTAs alive use dynamic shared memory only, which is per CTA: SSFFT_DYNAMIC_SMEM).
+#define __shared__ static
 #define __grid_constant__
 
 struct uint3 { unsigned x, y, z; };
