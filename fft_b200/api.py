@@ -238,6 +238,40 @@ class FFT(_PlanOwner):
                             pre_dist, post_dist)
 
 
+class FFT2:
+    """Two-dimensional complex transform of row-major ``[..., rows, cols]`` CUDA tensors: a batched row pass (contiguous,
+    the plain kernels) followed by a column pass through the extended call (``in_stride = cols, in_dist = 1``, in place
+    on the result of the row pass) -- two launches per matrix batch for fused sizes, no transposed copy of the data in
+    HBM.  Unnormalised in both directions, like the 1-D transforms: ``ifft2(fft2(x)) == rows * cols * x``.
+    (The reference has no 2-D call; its users loop over rows and columns on the host.)"""
+
+    def __init__(self, rows: int, cols: int, dtype="float32", device=None):
+        self.rows, self.cols = int(rows), int(cols)
+        self._row_pass = FFT(self.cols, dtype=dtype, device=device)   # length-cols transforms along each row
+        self._col_pass = FFT(self.rows, dtype=dtype, device=device)   # length-rows transforms down each column
+
+    def _run(self, x, out, inverse):
+        rp, cp = self._row_pass, self._col_pass
+        rp._flat(x, rp._t_cplx, "input")
+        rp._flat(out, rp._t_cplx, "output")
+        if x.shape[-2:] != (self.rows, self.cols) or out.shape != x.shape or out.device != x.device:
+            raise ValueError(f"expected [..., {self.rows}, {self.cols}] tensors of the same shape and device")
+        (rp.ifft if inverse else rp.fft)(x, out)
+        per = self.rows * self.cols
+        flat = out.reshape(-1)
+        run = cp.ifft_ex if inverse else cp.fft_ex
+        for m in range(x.numel() // per if per else 0):   # one column pass per matrix of the batch
+            v = flat[m * per:(m + 1) * per]
+            run(v, v, self.cols, in_stride=self.cols, in_dist=1, out_stride=self.cols, out_dist=1)
+        return out
+
+    def fft2(self, input, output):
+        return self._run(input, output, False)
+
+    def ifft2(self, input, output):
+        return self._run(input, output, True)
+
+
 class RealFFT(_PlanOwner):
     """signalsmith::RealFFT<V> -- even-length real transform, (DC, Nyquist) packed into bin 0 (:393-503)."""
     _kind = L.SSFFT_REAL

@@ -200,3 +200,31 @@ def test_null_io_is_the_plain_call_and_invalid_requests_are_rejected(oracle, cud
     rfft.fft_ex(sig, spec, batch, in_dist=n)
     rfft.fft_ex(sig, spec, 0, in_dist=n)
     torch.cuda.synchronize()
+
+
+@pytest.mark.parametrize("prec", ["float32", "float64"])
+@pytest.mark.parametrize("rows,cols", [(64, 96), (256, 256), (1000, 48), (48, 1000), (2048, 20)])
+def test_two_dimensional_transform(oracle, cuda_device, prec, rows, cols):
+    """FFT2 = row pass (plain) + in-place column pass (extended call), checked against the oracle applied along rows and
+    then along columns, and fft2 -> ifft2 == rows * cols * x on a batch of matrices."""
+    rdt, cdt, trdt, tcdt = dts(prec)
+    batch = 3
+    x = oracle.uniform_complex((batch, rows, cols), SEED, cdt)
+    f2 = fft_b200.FFT2(rows, cols, dtype=prec)
+    d = torch.from_numpy(x).cuda()
+    y = torch.empty_like(d)
+    f2.fft2(d, y)
+    torch.cuda.synchronize()
+    ref = oracle.run(oracle.KIND_C2C_FWD, x, cols, threads=4)[0]                                   # along rows
+    ref = oracle.run(oracle.KIND_C2C_FWD, np.ascontiguousarray(ref.transpose(0, 2, 1)), rows, threads=4)[0]  # along columns
+    ref = np.ascontiguousarray(ref.transpose(0, 2, 1))
+    lim = tol(rows, prec) + tol(cols, prec)
+    got = y.cpu().numpy()
+    for m in range(batch):
+        assert oracle.rel_l2(got[m].reshape(1, -1), ref[m].reshape(1, -1)) <= lim, (rows, cols, m)
+    z = torch.empty_like(d)
+    f2.ifft2(y, z)
+    torch.cuda.synchronize()
+    back = z.cpu().numpy() / (rows * cols)
+    for m in range(batch):
+        assert oracle.rel_l2(back[m].reshape(1, -1), x[m].reshape(1, -1)) <= 2 * lim
