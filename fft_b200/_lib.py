@@ -10,9 +10,7 @@ import re
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-# SSFFT_LIB: load another build of the SAME library (A/B measurements of compile-time experiment switches,
-# tools/ab_variants.sh); never a different implementation -- there is no CPU fallback to select.
-LIB_PATH = os.environ.get("SSFFT_LIB") or os.path.join(_HERE, "libssfft.so")
+LIB_PATH = os.path.join(_HERE, "libssfft.so")
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "ssfft.h")
 
 SSFFT_OK, SSFFT_ERR_INVALID, SSFFT_ERR_CUDA, SSFFT_ERR_UNSUPPORTED, SSFFT_ERR_NO_DEVICE, SSFFT_ERR_ALLOC = range(6)

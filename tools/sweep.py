@@ -14,6 +14,12 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import fft_b200  # noqa: E402
 
+# A/B measurements of compile-time experiment switches (tools/ab_variants.sh): time another BUILD of the same library.
+# The override lives in this development tool, not in the package: the product always loads fft_b200/libssfft.so.
+if os.environ.get("SSFFT_LIB"):
+    from fft_b200 import _lib as _L
+    _L.LIB_PATH = fft_b200.LIB_PATH = os.environ["SSFFT_LIB"]
+
 PEAK = 6528.1
 try:
     PEAK = json.load(open(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")))["hbm_gbs"]
