@@ -100,3 +100,14 @@ def test_extended_calls_reject_bad_handles(lib):
     assert lib.ssfft_exec_c2c_ex(None, None, None, 1, L.SSFFT_FORWARD, ctypes.byref(io), None) == L.SSFFT_ERR_INVALID
     assert lib.ssfft_exec_r2c_ex(None, None, None, 1, ctypes.byref(io), None) == L.SSFFT_ERR_INVALID
     assert lib.ssfft_exec_c2r_ex(None, None, None, 1, None, None) == L.SSFFT_ERR_INVALID
+
+
+def test_extended_request_validation_rules(tmp_path):
+    """ex_validate (fft_b200/csrc/ex_request.h, CUDA-free): defaults, kinds, alignment, overlap and in-place rules."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = tmp_path / "test_ex_request"
+    subprocess.run(["g++", "-std=c++11", "-Wall", "-Werror", os.path.join(root, "tests", "host", "test_ex_request.cpp"), "-o", str(exe)],
+                   check=True)
+    res = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert res.returncode == 0 and "EX-REQUEST-TESTS OK" in res.stdout, res.stdout + res.stderr
