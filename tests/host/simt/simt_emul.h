@@ -7,7 +7,8 @@
 // cluster by default; the whole grid for persistent kernels whose CTAs wait for each other).  __syncthreads() parks a
 // fiber until every fiber of its CTA that has not returned is parked too; the cluster barrier does the same over the
 // CTAs of a cluster; spin-waits on global memory yield (simt::spin_yield).  A state in which nobody can run any more is
-// reported as a deadlock instead of hanging.  Each live CTA has its own dynamic shared memory (SSFFT_DYNAMIC_SMEM in
+// reported as a deadlock instead of hanging.  The resume order can be reversed (State::reverse_order): the tests run
+// every case under both orders, so a result that depends on which thread happens to run first fails.  Each live CTA has its own dynamic shared memory (SSFFT_DYNAMIC_SMEM in
 // the kernels resolves to simt::dynamic_smem()), poisoned with NaN before the CTA starts.
 //
 // TMA bulk copy + mbarrier (fused.cuh, PF = 1 / 2; one mbarrier per CTA is all the kernels use) are emulated at the
@@ -68,6 +69,9 @@ struct State {
     unsigned long long barriers = 0, cluster_barriers = 0, bulk_copies = 0, bulk_bytes = 0;
     bool progress = false;
     bool late_copy = false;
+    // Fibers are resumed in index order, or in reverse when set: code that is only correct because "thread 0 runs
+    // first" (a missing barrier, a flag read before it is written) gives different results under the two orders.
+    bool reverse_order = false;
 };
 inline State &state() { static State s; return s; }
 inline Fiber &self() { State &s = state(); return s.fibers[s.current]; }
@@ -143,7 +147,8 @@ inline bool launch(dim3 grid, dim3 block, const std::function<void()> &body, Lau
         const size_t nf = (size_t)live_ctas * nthreads;
         for (;;) {
             s.progress = false;
-            for (size_t i = 0; i < nf; ++i) {
+            for (size_t k = 0; k < nf; ++k) {
+                const size_t i = s.reverse_order ? nf - 1 - k : k;
                 Fiber &f = s.fibers[i];
                 if (f.st != Fiber::RUNNABLE) continue;
                 s.current = (int)i;
