@@ -21,6 +21,11 @@ run)
     for v in $VARIANTS; do
         name=${v%%:*}
         SSFFT_LIB=$PWD/fft_b200/libssfft_$name.so python tools/sweep.py ab_$name float32 $SIZES
-    done ;;
+        # run-time knobs on top of the variant: CTAs per cluster of the persistent four-step launch
+        for cs in 2 8; do
+            SSFFT_CLUSTER=$cs SSFFT_LIB=$PWD/fft_b200/libssfft_$name.so python tools/sweep.py ab_${name}_cluster$cs float32 $SIZES
+        done
+    done
+    for cs in 2 8; do SSFFT_CLUSTER=$cs python tools/sweep.py ab_default_cluster$cs float32 $SIZES; done ;;
 *) echo "usage: $0 build|run"; exit 2 ;;
 esac
