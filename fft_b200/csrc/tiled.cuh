@@ -529,7 +529,7 @@ __host__ __device__ constexpr size_t fourstep_smem_bytes() {
 // L2 prefetch hints for the column stage (complex and R2C): while a CTA transforms one stage-1 tile it asks for the lines
 // of the NEXT stage-1 tile it will work on (same transform, or its first tile of the next transform) with
 // prefetch.global.L2 -- one instruction per 128-byte line, no registers, no shared memory, no wait: the loads of the next
-// tile then hit L2 instead of HBM.  Motivation: 25 % of the stall samples of the 65536 kernel sit on the first use of
+// tile then hit L2 instead of HBM.  Motivation: about a sixth of the stall samples of the 65536 kernel sit on the first use of
 // the tile loads (profiles/c2c65536_fourstep_cluster_r01b_stalls.txt) and the two schemes that HOLD the prefetched data
 // (cp.async staging, register double buffer) lost more occupancy than they hid.  Runs on the CPU emulation
 // (tests/test_tiled_emul.py builds it); NOT YET MEASURED on the GPU, hence off by default: NVFLAGS += -DSSFFT_FOURSTEP_L2PF=1.
