@@ -526,7 +526,7 @@ __host__ __device__ constexpr size_t fourstep_smem_bytes() {
     return (CfgA::smem_bytes > CfgB::smem_bytes ? CfgA::smem_bytes : CfgB::smem_bytes) * (fourstep_staged<CfgA, CfgB>() ? 2 : 1);
 }
 
-// L2 prefetch hints for the column stage (complex and R2C): while a CTA transforms one stage-1 tile it asks for the lines
+// L2 prefetch hints for the first stage (the one that reads the user buffer from HBM): while a CTA transforms one stage-1 tile it asks for the lines
 // of the NEXT stage-1 tile it will work on (same transform, or its first tile of the next transform) with
 // prefetch.global.L2 -- one instruction per 128-byte line, no registers, no shared memory, no wait: the loads of the next
 // tile then hit L2 instead of HBM.  Motivation: about a sixth of the stall samples of the 65536 kernel sit on the first use of
@@ -541,17 +541,29 @@ inline void prefetch_l2(const void *a) { (void)*static_cast<const volatile unsig
 #else
 __device__ __forceinline__ void prefetch_l2(const void *a) { asm volatile("prefetch.global.L2 [%0];" ::"l"(a)); }
 #endif
-// every 128-byte line the first pass of stage-1 tile `lane0` will read (TILE_A_C2C / TILE_A_R2C: row idx of the tile is
-// CT consecutive elements)
+// every 128-byte line the first pass of stage-1 tile `lane0` will read from the user buffer.  TILE_A_C2C / TILE_A_R2C: row
+// idx of the tile is CT consecutive elements.  TILE_B_C2R (packed half spectrum, Hermitian-extended on the fly): the CT
+// rows k1 of the tile read CT consecutive elements per k2, ascending for k2 < L/2 and descending (mirrored, offset by
+// one element) for k2 >= L/2 -- the addresses of the first, middle and last live lane cover the one or two lines.
 template <typename Cfg, int FLAVOR, int N1C, int N2C>
 __device__ __forceinline__ void tile_l2_prefetch(const cx<typename Cfg::T> *gin, int lane0, int tid) {
     using T = typename Cfg::T;
-    static_assert(FLAVOR == TILE_A_C2C || FLAVOR == TILE_A_R2C, "user-buffer column tiles only");
-    constexpr int kPerLine = 128 / (int)sizeof(cx<T>);
-    constexpr int kLines = (Cfg::CT + kPerLine - 1) / kPerLine;  // lines per row of the tile
-    for (int i = tid; i < Cfg::L * kLines; i += Cfg::THREADS) {
-        const int idx = i / kLines, part = i - idx * kLines;
-        prefetch_l2(tile_src<FLAVOR, Cfg::L>(gin, lane0 + part * kPerLine, idx, N1C, N2C, 0));
+    static_assert(FLAVOR == TILE_A_C2C || FLAVOR == TILE_A_R2C || FLAVOR == TILE_B_C2R, "stage-1 tiles that read the user buffer");
+    if constexpr (FLAVOR == TILE_B_C2R) {
+        constexpr int width = tile_width<FLAVOR>(N1C, N2C);
+        const int last = (lane0 + Cfg::CT - 1 < width ? lane0 + Cfg::CT - 1 : width - 1);
+        for (int i = tid; i < Cfg::L * 3; i += Cfg::THREADS) {
+            const int idx = i / 3, part = i - idx * 3;
+            const int lane = part == 0 ? lane0 : part == 1 ? (lane0 + last) / 2 : last;
+            prefetch_l2(tile_src<FLAVOR, Cfg::L>(gin, lane, idx, N1C, N2C, 0));
+        }
+    } else {
+        constexpr int kPerLine = 128 / (int)sizeof(cx<T>);
+        constexpr int kLines = (Cfg::CT + kPerLine - 1) / kPerLine;  // lines per row of the tile
+        for (int i = tid; i < Cfg::L * kLines; i += Cfg::THREADS) {
+            const int idx = i / kLines, part = i - idx * kLines;
+            prefetch_l2(tile_src<FLAVOR, Cfg::L>(gin, lane0 + part * kPerLine, idx, N1C, N2C, 0));
+        }
     }
 }
 
@@ -699,7 +711,7 @@ fourstep_cluster_kernel(FourStepParams<typename CfgA::T> q, const __grid_constan
                         }
                     }
                 };
-                if constexpr (SSFFT_FOURSTEP_L2PF != 0 && KIND != 2) {
+                if constexpr (SSFFT_FOURSTEP_L2PF != 0) {
                     // hint the next stage-1 tile of this CTA into L2 while this one is transformed
                     const int tid = threadIdx.x + threadIdx.y * blockDim.x;
                     if (next < tiles1) tile_l2_prefetch<Cfg1, F1, CfgA::L, CfgB::L>(uin, next * Cfg1::CT, tid);
