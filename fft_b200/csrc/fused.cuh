@@ -188,6 +188,21 @@ __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, u
 }
 #endif  // SSFFT_EMUL
 
+// prefetch.global.L2 (SASS CCTL.E.PF2): a hint, no register or shared memory is held and nothing waits for it.  The CPU
+// emulation READS the address instead, so a hint outside the buffer faults under a sanitizer.
+#ifdef SSFFT_EMUL
+inline void prefetch_l2(const void *a) { (void)*static_cast<const volatile unsigned char *>(a); }
+#else
+__device__ __forceinline__ void prefetch_l2(const void *a) { asm volatile("prefetch.global.L2 [%0];" ::"l"(a)); }
+#endif
+// Opt-in experiment (NVFLAGS += -DSSFFT_FUSED_L2PF=1, off by default, NOT YET MEASURED): at the top of every iteration a
+// CTA hints the group of transforms it will need next (PF = 1: the one after, its TMA copy is issued early in this
+// iteration) from HBM into L2, one instruction per 128-byte line.  Aimed at the sizes whose staging has a short lead:
+// in-place staging (PF = 2: 2048 ... 16384, 2^k * 3 / 9 above 4608) and the kernels without staging.
+#ifndef SSFFT_FUSED_L2PF
+#define SSFFT_FUSED_L2PF 0
+#endif
+
 // ---- extended I/O (EX instantiation): cooperative, rolled copy loops between HBM and the shared-memory image of a
 // group of transforms apply the layout and the multipliers; the passes in between are the plain kernel's.
 // SIDE: 0 = complex elements, 1 = real samples accessed one by one, 2 = real samples whose pairs (2i, 2i+1) are one
@@ -311,6 +326,14 @@ fused_fft_kernel(const cx<typename Cfg::T> *__restrict__ in, cx<typename Cfg::T>
     for (long long g = blockIdx.x; g < groups; g += gridDim.x) {
         const long long tr = g * FPB + f;
         const bool active = tr < batch;
+        if constexpr (SSFFT_FUSED_L2PF != 0 && !EX) {
+            const long long gp = g + (Cfg::PF == 1 ? 2 : 1) * (long long)gridDim.x;
+            if (gp < groups) {
+                const unsigned bytes = group_bytes(gp);
+                const char *base = reinterpret_cast<const char *>(in + gp * FPB * N);
+                for (unsigned off = (unsigned)(f * TX + t) * 128u; off < bytes; off += (unsigned)(TX * FPB) * 128u) prefetch_l2(base + off);
+            }
+        }
         const cx<T> *gin = in + (active ? tr : 0) * N;
         cx<T> *gout = out + (active ? tr : 0) * N;
         if constexpr (EX) {  // lite sides: the transform's own base pointer (distances count reals on a real side)

@@ -536,11 +536,6 @@ __host__ __device__ constexpr size_t fourstep_smem_bytes() {
 #ifndef SSFFT_FOURSTEP_L2PF
 #define SSFFT_FOURSTEP_L2PF 0
 #endif
-#ifdef SSFFT_EMUL
-inline void prefetch_l2(const void *a) { (void)*static_cast<const volatile unsigned char *>(a); }  // must be a readable address
-#else
-__device__ __forceinline__ void prefetch_l2(const void *a) { asm volatile("prefetch.global.L2 [%0];" ::"l"(a)); }
-#endif
 // every 128-byte line the first pass of stage-1 tile `lane0` will read from the user buffer.  TILE_A_C2C / TILE_A_R2C: row
 // idx of the tile is CT consecutive elements.  TILE_B_C2R (packed half spectrum, Hermitian-extended on the fly): the CT
 // rows k1 of the tile read CT consecutive elements per k2, ascending for k2 < L/2 and descending (mirrored, offset by

@@ -60,7 +60,11 @@ def test_registry_is_parsed():
 
 
 @pytest.mark.skipif(shutil.which("g++") is None, reason="needs g++")
-def test_every_fused_kernel_runs_on_cpu(tmp_path, oracle):
+@pytest.mark.parametrize("variant", ["default", "l2_prefetch_hints"])
+def test_every_fused_kernel_runs_on_cpu(tmp_path, oracle, variant):
+    """variant l2_prefetch_hints: the opt-in build -DSSFFT_FUSED_L2PF=1 (a later group of transforms hinted into L2),
+    kept green so that it can be measured on the GPU as it is; the emulated hint reads the address it names."""
+    extra = ["-DSSFFT_FUSED_L2PF=1"] if variant == "l2_prefetch_hints" else []
     cfgs = registered_configs()
     nchunks = min(8, os.cpu_count() or 1)
     chunks = [cfgs[i::nchunks] for i in range(nchunks)]
@@ -69,7 +73,7 @@ def test_every_fused_kernel_runs_on_cpu(tmp_path, oracle):
         inc = tmp_path / f"cfgs_{i}.inc"
         inc.write_text("".join("CFG(" + ", ".join(c) + ")\n" for c in chunks[i]))
         exe = str(tmp_path / f"fused_emul_{i}")
-        cmd = ["g++", "-std=c++17", "-O1", "-D__CUDACC__", "-DSSFFT_EMUL", f'-DFUSED_CFG_INC="{inc}"',
+        cmd = ["g++", "-std=c++17", "-O1", "-D__CUDACC__", "-DSSFFT_EMUL", *extra, f'-DFUSED_CFG_INC="{inc}"',
                *(["-DEMUL_EX_COPY"] if i == 0 else []),
                "-I" + os.path.join(HOST, "simt"), os.path.join(HOST, "fused_emul.cpp"),
                "-L" + os.path.join(ROOT, "oracle"), "-loracle", "-Wl,-rpath," + os.path.join(ROOT, "oracle"), "-o", exe]

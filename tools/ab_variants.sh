@@ -6,8 +6,8 @@
 # SSFFT_LIB; results land in gpurun_out/sweep_<variant>_float32.json (tools/sweep.py: % of the HBM roofline per size).
 set -e
 cd "$(dirname "$0")/.."
-VARIANTS="l2pf:-DSSFFT_FOURSTEP_L2PF=1"
-SIZES="32768 65536 131072 262144 524288 1048576"
+VARIANTS="l2pf:-DSSFFT_FOURSTEP_L2PF=1 fusedl2pf:-DSSFFT_FUSED_L2PF=1"
+SIZES="2048 4096 8192 16384 6144 9216 32768 65536 131072 262144 524288 1048576"
 case "$1" in
 build)
     for v in $VARIANTS; do
