@@ -19,6 +19,7 @@
 #include "ex_request.h"
 #include "fused.cuh"
 #include "generic.cuh"
+#include "generic_plan.h"
 #include "plan.h"
 #include "planner.h"
 #include "real_kernels.cuh"
@@ -66,36 +67,9 @@ int upload_roots(void **d_out, size_t n, size_t count, size_t step) {
     return SSFFT_OK;
 }
 
-// largest length one CTA can hold in the generic kernel's two padded shared buffers
-size_t generic_limit(size_t elem, int smem_max) {
-    size_t n = (size_t)smem_max / (2 * elem);
-    while (n > 1 && 2 * (size_t)(spad((int)n) + 1) * elem > (size_t)smem_max) --n;
-    return n;
-}
-
 template <typename T>
 int build_generic_stage(GenericStage &st, size_t n, int smem_max) {
-    st.n = (int)n;
-    st.radix = choose_radices(n);
-    st.prod.clear();
-    int P = 1, maxr = 1;
-    for (int r : st.radix) { st.prod.push_back(P); P *= r; if (r > maxr) maxr = r; }
-    if ((int)st.radix.size() > kMaxPasses) return SSFFT_ERR_UNSUPPORTED;
-    st.stage_input = radix_has_codelet(st.radix[0]) ? 0 : 1;
-    st.smem_stride = spad((int)n) + 1;
-    const size_t per = 2 * (size_t)st.smem_stride * sizeof(cx<T>);
-    if (per > (size_t)smem_max) return SSFFT_ERR_UNSUPPORTED;
-    // threads per transform: about one codelet butterfly each, power of two in [1, 256]
-    int want = (int)(n / (size_t)(maxr > 16 ? 1 : maxr));
-    if (!radix_has_codelet(maxr)) want = (int)n;  // any-radix passes parallelise over outputs
-    int tx = 1;
-    while (tx < want && tx < 256) tx *= 2;
-    st.tx = tx;
-    int fpb = 256 / tx;
-    if (fpb < 1) fpb = 1;
-    while (fpb > 1 && per * (size_t)fpb > (size_t)smem_max / 2) fpb /= 2;  // leave room for 2 CTAs/SM
-    st.fpb = fpb;
-    st.smem_bytes = per * (size_t)fpb;
+    if (!plan_generic_stage(st, n, sizeof(cx<T>), smem_max)) return SSFFT_ERR_UNSUPPORTED;
     int rc = upload_roots<T>(&st.d_roots, n, n, 1);
     if (rc) return rc;
     if (st.smem_bytes > 48 * 1024) {
@@ -104,33 +78,14 @@ int build_generic_stage(GenericStage &st, size_t n, int smem_max) {
     return SSFFT_OK;
 }
 
-struct Layout {
-    long long in_outer, in_inner, in_es;
-    int in_cols;
-    long long out_outer, out_inner, out_es;
-    int out_cols;
-};
+using Layout = GenericLayout;
 
 template <typename T>
 int launch_generic(const ssfft_plan *pl, const GenericStage &st, const void *in, void *out, long long batch,
                    const Layout &L, int inverse, bool epilogue, int ep_cols, cudaStream_t s) {
     if (batch <= 0) return SSFFT_OK;
-    GenericParams<T> p;
-    memset(&p, 0, sizeof(p));
-    p.n = st.n;
-    p.npass = (int)st.radix.size();
-    for (int i = 0; i < p.npass; ++i) { p.radix[i] = st.radix[i]; p.prod[i] = st.prod[i]; }
-    p.roots = (const cx<T> *)st.d_roots;
-    p.in_outer = L.in_outer; p.in_inner = L.in_inner; p.in_es = L.in_es; p.in_cols = L.in_cols;
-    p.out_outer = L.out_outer; p.out_inner = L.out_inner; p.out_es = L.out_es; p.out_cols = L.out_cols;
-    p.inverse = inverse;
-    p.ep_lo = epilogue ? (const cx<T> *)pl->d_ep_lo : nullptr;
-    p.ep_hi = epilogue ? (const cx<T> *)pl->d_ep_hi : nullptr;
-    p.ep_shift = pl->ep_shift;
-    p.ep_cols = ep_cols > 0 ? ep_cols : 1;
-    p.batch = batch;
-    p.smem_stride = st.smem_stride;
-    p.stage_input = st.stage_input;
+    const GenericParams<T> p = make_generic_params<T>(st, st.d_roots, batch, L, inverse, epilogue ? pl->d_ep_lo : nullptr,
+                                                      epilogue ? pl->d_ep_hi : nullptr, pl->ep_shift, ep_cols);
     const long long blocks = (batch + st.fpb - 1) / st.fpb;
     if (blocks > 0x7fffffffLL) return SSFFT_ERR_INVALID;
     dim3 grid((unsigned)blocks), block((unsigned)st.tx, (unsigned)st.fpb);
@@ -377,10 +332,10 @@ int exec_complex(ssfft_plan *pl, const void *in, void *out, long long batch, int
         const long long nb = (batch - b0 < (long long)pl->chunk) ? batch - b0 : (long long)pl->chunk;
         const void *cin = src + (size_t)b0 * (size_t)n * pl->elem;
         void *cout = dst + (size_t)b0 * (size_t)n * pl->elem;
-        Layout L1{n, 1, n2, (int)n2, n, 1, n2, (int)n2};
+        const Layout L1 = fourstep_col_layout((size_t)n, (size_t)n2);
         int rc = launch_generic<T>(pl, pl->col, cin, pl->d_scratch, nb * n2, L1, inverse, true, (int)n2, s);
         if (rc) return rc;
-        Layout L2{n, n2, 1, (int)n1, n, 1, n1, (int)n1};
+        const Layout L2 = fourstep_row_layout((size_t)n, (size_t)n1, (size_t)n2);
         rc = launch_generic<T>(pl, pl->row, pl->d_scratch, cout, nb * n1, L2, inverse, false, 1, s);
         if (rc) return rc;
     }
@@ -453,8 +408,9 @@ int build_plan_typed(ssfft_plan *pl) {
                      pl->direct.tx, pl->direct.fpb, pl->direct.smem_bytes);
         pl->desc = buf;
     } else {
-        size_t n1 = 0, n2 = 0;
-        if (!choose_split(n, limit, &n1, &n2)) return SSFFT_ERR_UNSUPPORTED;
+        GenericFourStep fs;
+        if (!plan_generic_fourstep(fs, n, limit)) return SSFFT_ERR_UNSUPPORTED;
+        const size_t n1 = fs.n1, n2 = fs.n2;
         pl->four_step = true;
         pl->n1 = n1; pl->n2 = n2;
         int rc = build_generic_stage<T>(pl->col, n1, smem_max);
@@ -462,13 +418,10 @@ int build_plan_typed(ssfft_plan *pl) {
         rc = build_generic_stage<T>(pl->row, n2, smem_max);
         if (rc) return rc;
         // epilogue twiddle W_n^q, q < n, split q = hi * 2^shift + lo
-        int shift = 0;
-        while ((1ull << (2 * shift)) < n) ++shift;
-        pl->ep_shift = shift;
-        const size_t lo_count = (size_t)1 << shift, hi_count = (n + lo_count - 1) / lo_count;
-        rc = upload_roots<T>(&pl->d_ep_lo, n, lo_count, 1);
+        pl->ep_shift = fs.ep_shift;
+        rc = upload_roots<T>(&pl->d_ep_lo, n, fs.lo_count, 1);
         if (rc) return rc;
-        rc = upload_roots<T>(&pl->d_ep_hi, n, hi_count, lo_count);
+        rc = upload_roots<T>(&pl->d_ep_hi, n, fs.hi_count, fs.lo_count);
         if (rc) return rc;
         // keep the intermediate of one chunk inside L2 (126 MB): 32 MiB of scratch
         size_t per = n * sizeof(cx<T>);
