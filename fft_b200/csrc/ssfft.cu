@@ -577,8 +577,10 @@ int exec_ex_typed(ssfft_plan *pl, int op, const void *in, void *out, long long b
     // transpose (32 x 32 tiles through shared memory, both sides coalesced) instead of the element-wise copy, whose
     // strided side touches one element per 32-byte sector
     const int prec = sizeof(T) == 4 ? SSFFT_F32 : SSFFT_F64;
-    const bool col_in = !x.in_real && !x.pre && x.id == 1 && x.is == batch && batch > 1;
-    const bool col_out = !x.out_real && !x.post && x.od == 1 && x.os == batch && batch > 1;
+    const long long max_rows = 65535LL * 32 * kRowTiles;  // grid.y limit of the transpose launch
+    const bool col_ok = batch > 1 && batch <= max_rows && (long long)pl->n <= max_rows;
+    const bool col_in = col_ok && !x.in_real && !x.pre && x.id == 1 && x.is == batch;
+    const bool col_out = col_ok && !x.out_real && !x.post && x.od == 1 && x.os == batch;
     if (!x.in_plain) {
         if ((rc = ex_workspace(&pl->d_ex_in, &pl->ex_in_bytes, bytes))) return rc;
         if (col_in)  // ws[c][r] = in[r][c]
