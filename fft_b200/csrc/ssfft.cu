@@ -965,6 +965,7 @@ const char *ssfft_error_string(int status) {
 }
 const char *ssfft_last_cuda_error(void) { return g_cuda_err; }
 uint64_t ssfft_launch_count(void) { return g_launches.load(); }
-const char *ssfft_version(void) { return "ssfft-b200 0.2 (sm_100a)";  // 0.2: extended execution (ssfft_exec_*_ex) }
+/* 0.2: extended execution (ssfft_exec_*_ex) */
+const char *ssfft_version(void) { return "ssfft-b200 0.2 (sm_100a)"; }
 
 }  // extern "C"
