@@ -61,3 +61,46 @@ def test_fft2_orchestration(monkeypatch, rows, cols, batch):
     assert (z / (rows * cols) - x).abs().max() < 1e-12  # unnormalised both ways, like the 1-D transforms
     with pytest.raises(ValueError):
         f2.fft2(x, torch.empty(batch, rows, cols + 1, dtype=torch.complex128))
+
+
+def test_span_of_a_layout():
+    span = api._PlanOwner._span
+    assert span(0, 64, 1, 0) == 0 and span(3, 0, 1, 0) == 0
+    assert span(1, 64, 1, 0) == 64                      # one contiguous transform
+    assert span(4, 64, 0, 0) == 256                     # defaults: stride 1, dist = length
+    assert span(5, 64, 1, 16) == 4 * 16 + 64            # overlapping frames, hop 16
+    assert span(10, 64, 10, 1) == 9 + 63 * 10 + 1       # the columns of a [64][10] matrix: exactly the matrix
+    assert span(3, 64, 2, 200) == 2 * 200 + 63 * 2 + 1  # strided rows
+
+
+def test_stft_frames_and_arguments():
+    """RealFFT.stft: frames = (len - N) // hop + 1, hop as the input distance, the window as the pre-multiplier."""
+    seen = {}
+
+    class _FakeReal(api.RealFFT):
+        def __init__(self, n):  # no plan, no library
+            self._half = n // 2
+            self._prec = api.L.SSFFT_F32
+
+        def _flat(self, t, dt, what):
+            assert t.dtype == dt
+            return t
+
+        def fft_ex(self, input, output, batch, **kw):
+            seen.update(batch=batch, out_shape=tuple(output.shape), **kw)
+            return output
+
+        def __del__(self):
+            pass
+
+    r = _FakeReal(256)
+    sig, win = torch.zeros(256 + 7 * 64 + 5), torch.ones(256)
+    out = torch.empty((8, 128), dtype=torch.complex64)
+    assert r.stft(sig, 64, win, out) is out
+    assert seen["batch"] == 8 and seen["in_dist"] == 64 and seen["pre"] is win and seen["out_shape"] == (8, 128)
+    with pytest.raises(ValueError):
+        r.stft(torch.zeros(100), 64)          # shorter than one frame
+    with pytest.raises(ValueError):
+        r.stft(sig, 0)                        # hop must be positive
+    with pytest.raises(ValueError):
+        r.stft(sig.reshape(1, -1), 64)        # 1-D signals only
