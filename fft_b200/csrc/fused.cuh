@@ -84,6 +84,23 @@ template <typename Cfg>
 using NoStaging = FusedCfg<typename Cfg::T, Cfg::N, Cfg::radix(0), Cfg::radix(1), Cfg::radix(2), Cfg::radix(3), Cfg::TX, Cfg::FPB,
                            Cfg::MINB, Cfg::PADSHIFT, 0>;
 
+// Column configuration of a size (opt-in experiment SSFFT_EX_COLCFG=1, NOT YET MEASURED): configurations that hold one
+// or two transforms per CTA walk the columns of a matrix one 8-byte element per 32-byte sector.  With 4 (or 2) transforms
+// per CTA -- same passes and threads per transform, 1 CTA/SM -- the transform-fastest copy loops of the EX instantiation
+// move whole sectors.  column_fpb() = 0: the size has no such configuration (already >= 4 per CTA, or it would not fit).
+template <typename Cfg>
+__host__ __device__ constexpr int column_fpb() {
+    if (Cfg::FPB >= 4 || Cfg::N < 2048) return 0;
+    for (int f = 4; f > Cfg::FPB; f /= 2) {
+        const size_t smem = ((size_t)(Cfg::pad(Cfg::N) + 1) * f * sizeof(cx<typename Cfg::T>) + 127) / 128 * 128;
+        if (Cfg::TX * f <= 1024 && smem <= 227 * 1024) return f;
+    }
+    return 0;
+}
+template <typename Cfg, int FPBX = column_fpb<Cfg>()>
+using ColumnCfg = FusedCfg<typename Cfg::T, Cfg::N, Cfg::radix(0), Cfg::radix(1), Cfg::radix(2), Cfg::radix(3), Cfg::TX,
+                           (FPBX > 0 ? FPBX : Cfg::FPB), 1, Cfg::PADSHIFT, 0>;
+
 // Extended I/O of the EX instantiation (ssfft_exec_*_ex, include/ssfft.h): layouts other than "contiguous batch" and
 // pointwise multipliers fused into the first load / last store.  "Elements" are reals on the real side of a RealFFT
 // (R2C input, C2R output) and complex values everywhere else.
@@ -648,6 +665,9 @@ struct FusedEntry {
     // extended I/O (strided / overlapping layouts, fused multipliers): io -> host FusedIo<T>; unmodified transforms only
     int (*launch_ex)(const void *tw, const void *in, void *out, long long batch, int inverse, int mode, const void *rtw,
                      const void *io, cudaStream_t s);
+    // same through the column configuration of the size (ColumnCfg); null when it has none
+    int (*launch_ex_cols)(const void *tw, const void *in, void *out, long long batch, int inverse, int mode, const void *rtw,
+                          const void *io, cudaStream_t s);
 };
 
 const std::vector<FusedEntry> &fused_registry();

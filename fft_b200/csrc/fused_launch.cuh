@@ -53,11 +53,11 @@ int launch_cfg(const void *tw, const void *in, void *out, long long batch, int i
 
 // Extended I/O (ssfft_exec_*_ex): the NoStaging twin of the configuration behind strided / overlapping loads and stores
 // with fused multipliers.  `io` points at a host FusedIo<T>.
-template <typename Cfg>
-int launch_cfg_ex(const void *tw, const void *in, void *out, long long batch, int inverse, int mode, const void *rtw,
-                  const void *io, cudaStream_t s) {
-    using T = typename Cfg::T;
-    using X = NoStaging<Cfg>;
+// X: the configuration that runs (NoStaging<Cfg>, or the column configuration ColumnCfg<Cfg>)
+template <typename X>
+int launch_ex_as(const void *tw, const void *in, void *out, long long batch, int inverse, int mode, const void *rtw,
+                 const void *io, cudaStream_t s) {
+    using T = typename X::T;
     static int ready_mask = 0;
     static int resident[64] = {0};
     static std::mutex setup_mutex;
@@ -94,6 +94,12 @@ int launch_cfg_ex(const void *tw, const void *in, void *out, long long batch, in
 }
 
 template <typename Cfg>
+int launch_cfg_ex(const void *tw, const void *in, void *out, long long batch, int inverse, int mode, const void *rtw,
+                  const void *io, cudaStream_t s) {
+    return launch_ex_as<NoStaging<Cfg>>(tw, in, out, batch, inverse, mode, rtw, io, s);
+}
+
+template <typename Cfg>
 FusedEntry make_entry(const char *name) {
     FusedEntry e;
     e.prec = sizeof(typename Cfg::T) == 4 ? 0 : 1;
@@ -105,6 +111,8 @@ FusedEntry make_entry(const char *name) {
     e.real_only = 0;
     e.launch = &launch_cfg<Cfg>;
     e.launch_ex = &launch_cfg_ex<Cfg>;
+    e.launch_ex_cols = nullptr;
+    if constexpr (column_fpb<Cfg>() > 0) e.launch_ex_cols = &launch_ex_as<ColumnCfg<Cfg>>;
     return e;
 }
 

@@ -562,8 +562,11 @@ int exec_ex_typed(ssfft_plan *pl, int op, const void *in, void *out, long long b
         f.pre_kind = x.pre_kind; f.post_kind = x.post_kind;
         const int mode = op == EX_C2C ? FUSED_C2C : op == EX_R2C ? FUSED_R2C : FUSED_C2R;
         fused_io_finalize(f, mode, in, out);  // vector accesses on the real side, sides that need no staging
-        int rc = fused_registry()[pl->fused.id].launch_ex(pl->fused.d_twiddles, in, out, batch, op == EX_C2R ? 1 : inverse, mode,
-                                                          pl->d_rtw, &f, s);
+        const FusedEntry &fe = fused_registry()[pl->fused.id];
+        // opt-in experiment: column layouts through the size's column configuration (4 or 2 transforms per CTA)
+        const bool cols = fe.launch_ex_cols && (x.id < x.is || x.od < x.os) && env_int("SSFFT_EX_COLCFG", 0);
+        int rc = (cols ? fe.launch_ex_cols : fe.launch_ex)(pl->fused.d_twiddles, in, out, batch, op == EX_C2R ? 1 : inverse, mode,
+                                                           pl->d_rtw, &f, s);
         ++g_launches;
         if (rc) return cuda_fail(cudaGetLastError(), "fused_fft_kernel<EX> launch");
         return SSFFT_OK;

@@ -121,7 +121,12 @@ def main():
         alg = 2 * m.numel() * 8
         f = lambda: fft.fft_ex(m.reshape(-1), m.reshape(-1), cols, in_stride=cols, in_dist=1, out_stride=cols, out_dist=1)  # noqa: E731
         line(out, "columns", "fused (strided loads / stores inside the kernel)", timed(f), alg, launches_of(f), {"rows": rows, "cols": cols, "plan": fft.describe()})
-        line(out, "columns", "unfused (gather pass + plain C2C + scatter pass)", with_unfused(f), alg, 3)
+        line(out, "columns", "unfused (transpose + plain C2C + transpose)", with_unfused(f), alg, 3)
+        os.environ["SSFFT_EX_COLCFG"] = "1"  # opt-in experiment: 4 transforms per CTA so that column walks move whole sectors
+        try:
+            line(out, "columns", "fused, column configuration (SSFFT_EX_COLCFG=1)", timed(f), alg, launches_of(f))
+        finally:
+            del os.environ["SSFFT_EX_COLCFG"]
 
 
 if __name__ == "__main__":
