@@ -86,6 +86,6 @@ def test_every_fused_kernel_runs_on_cpu(tmp_path, oracle, variant):
     for res in results:
         assert res.returncode == 0 and "FUSED-EMUL-OK" in res.stdout, res.stdout[-4000:] + res.stderr[-2000:]
         runs += int(res.stdout.split(" runs over")[0].split()[-1])
-    # per configuration: 8 plain runs x 2 (both fiber orders; prefetching kernels: both TMA timings) + 15 extended-I/O
+    # per configuration: (8 plain runs + 2 launch shapes) x 2 (both fiber orders; prefetching kernels: both TMA timings) + 15 extended-I/O
     # layouts; + ex_copy_kernel and the column transposes
-    assert runs >= 31 * len(cfgs) + 12 + 18
+    assert runs >= 35 * len(cfgs) + 12 + 18
