@@ -164,11 +164,11 @@ __device__ __forceinline__ cx<T> ld_table(const cx<T> *p) {
 #ifdef SSFFT_EMUL
 // Host emulation of the kernels (tests/host/simt/simt_emul.h, CPU tests only): same call sites, hooks instead of PTX.
 inline unsigned smem_u32(const void *p) { return (unsigned)reinterpret_cast<size_t>(p); }
-inline void mbar_init(unsigned long long *, unsigned) { simt::mbar_init(); }
-inline void mbar_expect_tx(unsigned long long *, unsigned bytes) { simt::mbar_expect_tx(bytes); }
-inline void mbar_wait(unsigned long long *, unsigned parity) { simt::mbar_wait(parity); }
-inline void bulk_g2s(void *dst_smem, const void *src_gmem, unsigned bytes, unsigned long long *) {
-    simt::bulk_g2s(dst_smem, src_gmem, bytes);
+inline void mbar_init(unsigned long long *bar, unsigned) { simt::mbar_init(bar); }
+inline void mbar_expect_tx(unsigned long long *bar, unsigned bytes) { simt::mbar_expect_tx(bar, bytes); }
+inline void mbar_wait(unsigned long long *bar, unsigned parity) { simt::mbar_wait(bar, parity); }
+inline void bulk_g2s(void *dst_smem, const void *src_gmem, unsigned bytes, unsigned long long *bar) {
+    simt::bulk_g2s(dst_smem, src_gmem, bytes, bar);
 }
 #else
 // ---- TMA bulk copy + mbarrier (sm_90+/sm_100a PTX; SASS: UBLKCP / SYNCS)

@@ -22,6 +22,7 @@
 
 #include <cstdio>
 #include <functional>
+#include <map>
 #include <memory>
 #include <vector>
 
@@ -46,15 +47,20 @@ struct Fiber {
     size_t stack_bytes = 0;
     uint3 tid, bid;
     unsigned cta = 0;  // index among the resident CTAs
-    enum { RUNNABLE, AT_BARRIER, AT_CLUSTER_BARRIER, DONE } st = RUNNABLE;
+    enum { RUNNABLE, AT_BARRIER, DONE } st = RUNNABLE;
+    unsigned cl_waits = 0;  // cluster-barrier phases this thread has waited for
 };
 
-struct Mbar {  // emulated mbarrier of one CTA
+struct Mbar {  // emulated mbarrier (arrival count 1 + transaction bytes); a CTA's mbarriers are told apart by address
     unsigned phase = 0;
-    long long pending_tx = 0;
+    long long pending_tx = 0;  // may go negative: transactions can complete before the expect-tx of their phase
     bool armed = false;
-    struct Pending { void *dst; const void *src; unsigned bytes; };
+    struct Pending { void *dst; const void *src; unsigned bytes; unsigned char value[16]; };  // src == nullptr: `value`
     std::vector<Pending> pending;
+};
+struct ClusterBar {  // split-phase hardware cluster barrier: arrive ... wait
+    size_t arrived = 0;
+    unsigned phase = 0;
 };
 
 struct State {
@@ -64,8 +70,9 @@ struct State {
     const std::function<void()> *body = nullptr;
     std::vector<unsigned char *> smem;  // per resident CTA, 128-byte aligned
     std::vector<std::unique_ptr<unsigned char[]>> smem_store;
-    std::vector<Mbar> mbar;             // per resident CTA
-    unsigned cluster = 1;
+    std::vector<std::map<const void *, Mbar>> mbar;  // per resident CTA
+    std::vector<ClusterBar> cbar;       // per resident cluster
+    unsigned cluster = 1, nthreads = 0;
     unsigned long long barriers = 0, cluster_barriers = 0, bulk_copies = 0, bulk_bytes = 0;
     bool progress = false;
     bool late_copy = false;
@@ -79,6 +86,9 @@ inline Fiber &self() { State &s = state(); return s.fibers[s.current]; }
 inline unsigned char *dynamic_smem() { State &s = state(); return s.smem[self().cta]; }
 inline unsigned cluster_ctarank() { return self().cta % state().cluster; }
 inline unsigned cluster_nctarank() { return state().cluster; }
+inline unsigned cta_of_rank(unsigned rank) { State &s = state(); return self().cta / s.cluster * s.cluster + rank; }
+// the dynamic shared memory of CTA `rank` of my cluster (what mapa.shared::cluster addresses)
+inline unsigned char *peer_smem(unsigned rank) { return state().smem[cta_of_rank(rank)]; }
 
 inline void fiber_entry() {
     State &s = state();
@@ -96,13 +106,31 @@ inline void yield_to_scheduler() {
     blockIdx = s.fibers[me].bid;
 }
 inline void spin_yield() { yield_to_scheduler(); }  // a polling loop lets everybody else run before it looks again
-inline void cluster_barrier() {
+// barrier.cluster.arrive / barrier.cluster.wait: the phase completes when every thread of the cluster that has not
+// returned has arrived; a thread may do other work between its arrive and its wait.
+inline void cluster_check(unsigned cl) {
     State &s = state();
-    ++s.cluster_barriers;
-    s.progress = true;
-    self().st = Fiber::AT_CLUSTER_BARRIER;
-    yield_to_scheduler();
+    size_t live = 0;
+    for (size_t i = (size_t)cl * s.cluster * s.nthreads; i < (size_t)(cl + 1) * s.cluster * s.nthreads; ++i) live += s.fibers[i].st != Fiber::DONE;
+    ClusterBar &b = s.cbar[cl];
+    if (b.arrived && b.arrived >= live) { b.arrived = 0; ++b.phase; s.progress = true; }
 }
+inline void cluster_arrive() {
+    State &s = state();
+    const unsigned cl = self().cta / s.cluster;
+    ++s.cbar[cl].arrived;
+    s.progress = true;
+    cluster_check(cl);
+}
+inline void cluster_wait() {
+    State &s = state();
+    const unsigned cl = self().cta / s.cluster;
+    ++s.cluster_barriers;
+    while (s.cbar[cl].phase <= self().cl_waits) yield_to_scheduler();
+    ++self().cl_waits;
+    s.progress = true;
+}
+inline void cluster_barrier() { cluster_arrive(); cluster_wait(); }
 
 // Runs `body` for every thread of every CTA.  Returns false on deadlock.
 inline bool launch(dim3 grid, dim3 block, const std::function<void()> &body, Launch cfg = Launch()) {
@@ -115,6 +143,7 @@ inline bool launch(dim3 grid, dim3 block, const std::function<void()> &body, Lau
     if (resident > nctas) resident = nctas;
     if (nctas % cluster || resident % cluster) { fprintf(stderr, "simt: grid / resident CTAs must be multiples of the cluster size\n"); return false; }
     s.cluster = cluster;
+    s.nthreads = nthreads;
     s.body = &body;
     s.fibers.resize((size_t)resident * nthreads);
     for (auto &f : s.fibers)
@@ -124,16 +153,19 @@ inline bool launch(dim3 grid, dim3 block, const std::function<void()> &body, Lau
         unsigned char *p = s.smem_store.back().get();
         s.smem.push_back(p + (128 - reinterpret_cast<uintptr_t>(p) % 128) % 128);
     }
-    s.mbar.assign(resident, Mbar());
+    s.mbar.assign(resident, std::map<const void *, Mbar>());
+    s.cbar.assign(resident / cluster, ClusterBar());
     for (unsigned first = 0; first < nctas; first += resident) {
         const unsigned live_ctas = nctas - first < resident ? nctas - first : resident;
         for (unsigned c = 0; c < live_ctas; ++c) {
             const unsigned b = first + c;
             memset(s.smem[c], 0xff, kSmemBytes);  // NaN pattern: reads of unwritten shared memory show up
-            s.mbar[c] = Mbar();
+            s.mbar[c].clear();
+            s.cbar[c / cluster] = ClusterBar();
             for (unsigned i = 0; i < nthreads; ++i) {
                 Fiber &f = s.fibers[(size_t)c * nthreads + i];
                 f.st = Fiber::RUNNABLE;
+                f.cl_waits = 0;
                 f.cta = c;
                 f.tid = uint3{i % block.x, (i / block.x) % block.y, i / (block.x * block.y)};
                 f.bid = uint3{b % grid.x, (b / grid.x) % grid.y, b / (grid.x * grid.y)};
@@ -163,7 +195,7 @@ inline bool launch(dim3 grid, dim3 block, const std::function<void()> &body, Lau
                 for (unsigned i = 0; i < nthreads; ++i) {
                     const Fiber &f = s.fibers[(size_t)c * nthreads + i];
                     at += f.st == Fiber::AT_BARRIER;
-                    run += f.st == Fiber::RUNNABLE || f.st == Fiber::AT_CLUSTER_BARRIER;
+                    run += f.st == Fiber::RUNNABLE;
                 }
                 if (at && !run) {
                     for (unsigned i = 0; i < nthreads; ++i) {
@@ -173,21 +205,10 @@ inline bool launch(dim3 grid, dim3 block, const std::function<void()> &body, Lau
                     s.progress = true;
                 }
             }
-            for (unsigned c0 = 0; c0 < live_ctas; c0 += cluster) {
-                size_t at = 0, other = 0;
-                for (size_t i = (size_t)c0 * nthreads; i < (size_t)(c0 + cluster) * nthreads; ++i) {
-                    at += s.fibers[i].st == Fiber::AT_CLUSTER_BARRIER;
-                    other += s.fibers[i].st == Fiber::RUNNABLE || s.fibers[i].st == Fiber::AT_BARRIER;
-                }
-                if (at && !other) {
-                    for (size_t i = (size_t)c0 * nthreads; i < (size_t)(c0 + cluster) * nthreads; ++i)
-                        if (s.fibers[i].st == Fiber::AT_CLUSTER_BARRIER) s.fibers[i].st = Fiber::RUNNABLE;
-                    s.progress = true;
-                }
-            }
+            for (unsigned cl = 0; cl < live_ctas / cluster; ++cl) cluster_check(cl);  // threads that returned no longer count
             for (size_t i = 0; i < nf; ++i) {
                 runnable += s.fibers[i].st == Fiber::RUNNABLE;
-                parked += s.fibers[i].st == Fiber::AT_BARRIER || s.fibers[i].st == Fiber::AT_CLUSTER_BARRIER;
+                parked += s.fibers[i].st == Fiber::AT_BARRIER;
             }
             if (!runnable && !parked) break;  // every thread returned
             if (!s.progress) {
@@ -201,37 +222,55 @@ inline bool launch(dim3 grid, dim3 block, const std::function<void()> &body, Lau
 }
 
 // ---- hooks called by the kernels' PTX wrappers when SSFFT_EMUL is defined
-inline Mbar &my_mbar() { return state().mbar[self().cta]; }
+inline Mbar &mbar_of(unsigned cta, const void *bar) { return state().mbar[cta][bar]; }
 inline void mbar_complete_if_ready(Mbar &m) {
     if (m.armed && m.pending_tx == 0) { m.armed = false; ++m.phase; state().progress = true; }
 }
-inline void mbar_init() { my_mbar() = Mbar(); }
-inline void mbar_expect_tx(unsigned bytes) {  // arrive (count 1) + expect-tx
-    Mbar &m = my_mbar();
+inline void mbar_init(const void *bar) { mbar_of(self().cta, bar) = Mbar(); }
+inline void mbar_expect_tx(const void *bar, unsigned bytes) {  // arrive (count 1) + expect-tx
+    Mbar &m = mbar_of(self().cta, bar);
     m.pending_tx += bytes;
     m.armed = true;
     mbar_complete_if_ready(m);
 }
-inline void bulk_g2s(void *dst, const void *src, unsigned bytes) {
+inline void land(Mbar &m, const Mbar::Pending &c) {
+    memcpy(c.dst, c.src ? c.src : (const void *)c.value, c.bytes);
+    m.pending_tx -= c.bytes;
+}
+inline void bulk_g2s(void *dst, const void *src, unsigned bytes, const void *bar) {
     State &s = state();
-    Mbar &m = my_mbar();
+    Mbar &m = mbar_of(self().cta, bar);
     if (bytes % 16 || ((uintptr_t)dst & 15) || ((uintptr_t)src & 15)) {
         fprintf(stderr, "simt: cp.async.bulk needs 16-byte aligned addresses and sizes (dst %p src %p bytes %u)\n", dst, src, bytes);
         abort();
     }
     ++s.bulk_copies; s.bulk_bytes += bytes;
-    if (s.late_copy) { m.pending.push_back({dst, src, bytes}); return; }
-    memcpy(dst, src, bytes);
-    m.pending_tx -= bytes;
+    Mbar::Pending c{dst, src, bytes, {0}};
+    if (s.late_copy) { m.pending.push_back(c); return; }
+    land(m, c);
     mbar_complete_if_ready(m);
 }
-inline void mbar_wait(unsigned parity) {
+// st.async to CTA `rank` of my cluster: the value lands in the peer's shared memory and completes `bytes` of the PEER's
+// mbarrier at the same shared-memory offset as `bar` (now, or -- late_copy -- when the peer waits for it)
+inline void remote_store_tx(unsigned rank, void *peer_dst, const void *value, unsigned bytes, const void *bar) {
     State &s = state();
-    Mbar &m = my_mbar();
-    for (auto &c : m.pending) { memcpy(c.dst, c.src, c.bytes); m.pending_tx -= c.bytes; }
-    m.pending.clear();
+    Mbar &m = mbar_of(cta_of_rank(rank), bar);
+    Mbar::Pending c{peer_dst, nullptr, bytes, {0}};
+    memcpy(c.value, value, bytes);
+    if (s.late_copy) { m.pending.push_back(c); return; }
+    land(m, c);
     mbar_complete_if_ready(m);
-    while ((m.phase & 1u) == parity) yield_to_scheduler();  // the phase with this parity has not completed yet
+}
+inline void mbar_wait(const void *bar, unsigned parity) {
+    State &s = state();
+    Mbar &m = mbar_of(self().cta, bar);
+    for (;;) {
+        for (auto &c : m.pending) land(m, c);  // late mode: whatever has been sent so far lands when somebody waits
+        m.pending.clear();
+        mbar_complete_if_ready(m);
+        if ((m.phase & 1u) != parity) break;   // the phase with this parity has completed
+        yield_to_scheduler();
+    }
     s.progress = true;
 }
 
