@@ -314,6 +314,27 @@ SSFFT_HD void cl_r2c_epilogue(Env &env, int tid, int rank, const cx<typename Cfg
 
 #ifdef __CUDACC__
 
+#ifdef SSFFT_EMUL
+// CPU execution of the kernel (tests/host/simt/simt_emul.h): hooks instead of PTX.  The all-to-all store lands in the
+// peer CTA's shared memory and completes bytes of the peer's "bufB full" mbarrier, as st.async does.
+inline unsigned cl_ctarank() { return simt::cluster_ctarank(); }
+inline void cl_arrive_release() { simt::cluster_arrive(); }
+inline void cl_arrive_relaxed() { simt::cluster_arrive(); }
+inline void cl_wait() { simt::cluster_wait(); }
+inline void mbar_wait_cluster(unsigned long long *bar, unsigned parity) { simt::mbar_wait(bar, parity); }
+template <typename T>
+struct ClusterDevEnv {
+    size_t bufb_off;            // offset of bufB in the dynamic shared memory (the same in every CTA of the cluster)
+    unsigned long long *bar;    // this CTA's "bufB full" mbarrier (the peers' is at the same place)
+    cx<T> ld_in(const cx<T> *p) const { return ld_stream(p); }
+    void st_out(cx<T> *p, cx<T> v) const { st_stream(p, v); }
+    cx<T> ld_tab(const cx<T> *p) const { return ld_table(p); }
+    void remote_store(int owner, int idx, cx<T> v) const {
+        cx<T> *peer = reinterpret_cast<cx<T> *>(simt::peer_smem((unsigned)owner) + bufb_off) + idx;
+        simt::remote_store_tx((unsigned)owner, peer, &v, (unsigned)sizeof(cx<T>), bar);
+    }
+};
+#else
 __device__ __forceinline__ unsigned cl_ctarank() {
     unsigned r;
     asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
@@ -365,6 +386,7 @@ struct ClusterDevEnv {
                          : "memory");
     }
 };
+#endif  // SSFFT_EMUL
 
 template <typename Cfg, int KIND>
 __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINB)
@@ -392,15 +414,26 @@ cluster_fft_kernel(ClusterParams<typename Cfg::T> q, const __grid_constant__ CUt
     __syncthreads();
     cl_arrive_release();  // every CTA's mbarriers are initialised before a peer may signal them
     cl_wait();
+#ifdef SSFFT_EMUL
+    ClusterDevEnv<T> env{(size_t)(reinterpret_cast<unsigned char *>(bufB) - ssfft_smem), &bars[0]};
+#else
     ClusterDevEnv<T> env{smem_u32(bufB), smem_u32(&bars[0])};
+#endif
     auto prefetch = [&](long long Bn) {
         if (Bn < q.batch && tid == 0) {
             mbar_expect_tx(&bars[1], kTileBytes);
+#ifdef SSFFT_EMUL
+            // the box [N1][CT1] at (x = rank * CT1, y = 0, z = Bn) of the (batch, N1, N2) tensor, one bulk copy per row
+            for (int r = 0; r < Cfg::N1; ++r)
+                bulk_g2s(bufB + r * Cfg::CT1, q.in + Bn * Cfg::N + (long long)r * Cfg::N2 + rank * Cfg::CT1,
+                         (unsigned)(Cfg::CT1 * sizeof(cx<T>)), &bars[1]);
+#else
             asm volatile(
                 "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
                     smem_u32(bufB)),
                 "l"(reinterpret_cast<unsigned long long>(&tmap)), "r"(rank * Cfg::CT1), "r"(0), "r"((int)Bn), "r"(smem_u32(&bars[1]))
                 : "memory");
+#endif
         }
     };
     if (PF) prefetch(cid);

@@ -79,6 +79,11 @@ struct State {
     // Fibers are resumed in index order, or in reverse when set: code that is only correct because "thread 0 runs
     // first" (a missing barrier, a flag read before it is written) gives different results under the two orders.
     bool reverse_order = false;
+    // Skew between CTAs.  0: every runnable fiber of every resident CTA runs once per round (CTAs advance together).
+    // 1 / 2: the lowest / highest-numbered CTA that can make progress runs alone until it blocks on another CTA, so
+    // one CTA races as far ahead of its peers as the synchronisation allows -- a missing cross-CTA wait (a peer's
+    // store landing in a buffer its owner is still reading) shows up.
+    int cta_priority = 0;
 };
 inline State &state() { static State s; return s; }
 inline Fiber &self() { State &s = state(); return s.fibers[s.current]; }
@@ -177,10 +182,9 @@ inline bool launch(dim3 grid, dim3 block, const std::function<void()> &body, Lau
             }
         }
         const size_t nf = (size_t)live_ctas * nthreads;
-        for (;;) {
-            s.progress = false;
-            for (size_t k = 0; k < nf; ++k) {
-                const size_t i = s.reverse_order ? nf - 1 - k : k;
+        auto run_cta = [&](unsigned c) {  // resume every runnable fiber of CTA c once
+            for (unsigned k = 0; k < nthreads; ++k) {
+                const size_t i = (size_t)c * nthreads + (s.reverse_order ? nthreads - 1 - k : k);
                 Fiber &f = s.fibers[i];
                 if (f.st != Fiber::RUNNABLE) continue;
                 s.current = (int)i;
@@ -188,8 +192,8 @@ inline bool launch(dim3 grid, dim3 block, const std::function<void()> &body, Lau
                 blockIdx = f.bid;
                 swapcontext(&s.sched, &f.ctx);
             }
-            // release the barriers every participant has reached
-            size_t runnable = 0, parked = 0;
+        };
+        auto release_barriers = [&]() {  // release the block barriers every participant has reached; cluster phases
             for (unsigned c = 0; c < live_ctas; ++c) {
                 size_t at = 0, run = 0;
                 for (unsigned i = 0; i < nthreads; ++i) {
@@ -206,6 +210,22 @@ inline bool launch(dim3 grid, dim3 block, const std::function<void()> &body, Lau
                 }
             }
             for (unsigned cl = 0; cl < live_ctas / cluster; ++cl) cluster_check(cl);  // threads that returned no longer count
+        };
+        for (;;) {
+            s.progress = false;
+            if (s.cta_priority == 0) {
+                for (unsigned k = 0; k < live_ctas; ++k) run_cta(s.reverse_order ? live_ctas - 1 - k : k);
+            } else {
+                for (unsigned k = 0; k < live_ctas; ++k) {
+                    const unsigned c = s.cta_priority == 1 ? k : live_ctas - 1 - k;
+                    s.progress = false;
+                    release_barriers();     // so that a favoured CTA parked at its own block barrier goes on at once
+                    run_cta(c);
+                    if (s.progress) break;  // this CTA got somewhere: keep favouring it
+                }
+            }
+            release_barriers();
+            size_t runnable = 0, parked = 0;
             for (size_t i = 0; i < nf; ++i) {
                 runnable += s.fibers[i].st == Fiber::RUNNABLE;
                 parked += s.fibers[i].st == Fiber::AT_BARRIER;
