@@ -248,3 +248,21 @@ def test_lengths_with_a_large_prime_factor_are_checked_against_the_exact_transfo
     ref = oracle.rel_l2(oracle.fft(x).astype(np.complex128), exact)
     assert ours <= 1e-6 * math.log2(n), (n, ours, fft.describe())
     assert ours <= ref * 1.5, (n, ours, ref)
+
+
+@pytest.mark.parametrize("rows,cols", [(2048, 20), (4096, 12), (8192, 6)])
+def test_column_configuration_opt_in(oracle, cuda_device, rows, cols):
+    """SSFFT_EX_COLCFG=1 (experiment): column layouts of sizes >= 2048 through the size's column configuration
+    (4 or 2 transforms per CTA); must give the same transform as the tuned configuration."""
+    m = oracle.uniform_complex((rows, cols), SEED, np.complex64)
+    ref = oracle.run(oracle.KIND_C2C_FWD, np.ascontiguousarray(m.T), rows, threads=4)[0]
+    fft = fft_b200.FFT(rows)
+    d = torch.from_numpy(m).cuda()
+    out = torch.empty_like(d)
+    os.environ["SSFFT_EX_COLCFG"] = "1"
+    try:
+        fft.fft_ex(d.reshape(-1), out.reshape(-1), cols, in_stride=cols, in_dist=1, out_stride=cols, out_dist=1)
+        torch.cuda.synchronize()
+    finally:
+        del os.environ["SSFFT_EX_COLCFG"]
+    assert oracle.rel_l2(np.ascontiguousarray(out.cpu().numpy().T), ref) <= tol(rows, "float32"), fft.describe()
