@@ -110,9 +110,12 @@ FusedEntry make_entry(const char *name) {
     for (int i = 0; i < 4; ++i) e.radix[i] = Cfg::radix(i);
     e.real_only = 0;
     e.launch = &launch_cfg<Cfg>;
-    e.launch_ex = &launch_cfg_ex<Cfg>;
+    e.launch_ex = nullptr;
     e.launch_ex_cols = nullptr;
+#ifndef SSFFT_NO_EX_KERNELS  // tools/kbench.cu times hundreds of plain variants: no extended-I/O instantiations there
+    e.launch_ex = &launch_cfg_ex<Cfg>;
     if constexpr (column_fpb<Cfg>() > 0) e.launch_ex_cols = &launch_ex_as<ColumnCfg<Cfg>>;
+#endif
     return e;
 }
 

@@ -6,6 +6,7 @@
 // g_mode selects C2C / R2C / C2R.  Every variant of a size must reproduce the first variant's output (maxdiff column).
 // Sections tune2 ... tune11 are the rounds whose outputs are kept under profiles/kbench_*_r01.txt; the earliest
 // sections (4096, c4, pow2, real, tune2-4) compile only with -DKBENCH_ALL.
+#define SSFFT_NO_EX_KERNELS 1  // plain kernels only (compile time)
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
