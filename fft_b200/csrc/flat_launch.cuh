@@ -1,0 +1,70 @@
+// flat_launch.cuh -- host launchers for the ticket-queue four-step kernels (flat.cuh).
+#pragma once
+#include <cstring>
+#include <mutex>
+
+#include "flat.cuh"
+#include "tma_host.cuh"
+
+namespace ssfft {
+
+template <typename CfgA, typename CfgB, int INV, int NSTAGE, int MINB>
+int flat_max_ctas() {
+    using Lay = FlatLayout<CfgA, CfgB, NSTAGE>;
+    auto kern = fourstep_flat_kernel<CfgA, CfgB, INV, NSTAGE, MINB>;
+    static int cached[32] = {0};
+    static std::mutex m;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 32) return -1;
+    std::lock_guard<std::mutex> lock(m);
+    if (cached[dev]) return cached[dev];
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Lay::smem_bytes) != cudaSuccess) {
+        cudaGetLastError();
+        return -1;
+    }
+    int per_sm = 0, sms = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, CfgA::THREADS + 32, Lay::smem_bytes) != cudaSuccess) {
+        cudaGetLastError();
+        return -1;
+    }
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cached[dev] = per_sm * sms > 0 ? per_sm * sms : -1;
+    return cached[dev];
+}
+
+// returns 0 on success, 2 on a launch error, 3 when the input cannot be described by a tensor map (caller falls back)
+template <typename CfgA, typename CfgB, int INV, int NSTAGE, int MINB>
+int launch_flat(const void *params, int ctas, cudaStream_t s) {
+    using T = typename CfgA::T;
+    using Lay = FlatLayout<CfgA, CfgB, NSTAGE>;
+    const FlatParams<T> &q = *reinterpret_cast<const FlatParams<T> *>(params);
+    if (q.batch <= 0) return 0;
+    if (flat_max_ctas<CfgA, CfgB, INV, NSTAGE, MINB>() < 1) return 2;  // also sets the shared-memory attribute
+    CUtensorMap tmap;
+    memset(&tmap, 0, sizeof(tmap));
+    constexpr int kBoxRows = CfgA::L > 256 ? 256 : CfgA::L;
+    if (!encode_tensor_map_3d(&tmap, q.in, q.batch, CfgA::L, CfgB::L, kBoxRows, CfgA::CT)) return 3;
+    fourstep_flat_kernel<CfgA, CfgB, INV, NSTAGE, MINB><<<(unsigned)ctas, CfgA::THREADS + 32, Lay::smem_bytes, s>>>(q, tmap);
+    return cudaGetLastError() == cudaSuccess ? 0 : 2;
+}
+
+template <typename CfgA, typename CfgB, int NSTAGE, int MINB>
+FlatEntry make_flat_entry(const char *name) {
+    using Lay = FlatLayout<CfgA, CfgB, NSTAGE>;
+    FlatEntry e;
+    e.prec = sizeof(typename CfgA::T) == 4 ? 0 : 1;
+    e.n1 = CfgA::L; e.n2 = CfgB::L; e.name = name;
+    e.ra0 = CfgA::radix(0); e.ra1 = CfgA::radix(1); e.cta = CfgA::CT; e.ctb = CfgB::CT;
+    e.threads = CfgA::THREADS + 32; e.nstage = NSTAGE; e.minb = MINB;
+    e.smem_bytes = Lay::smem_bytes;
+    e.tile_b_tw = CfgB::tw_total;
+    e.nb_passes = CfgB::NP;
+    for (int i = 0; i < 3; ++i) e.rb[i] = CfgB::radix(i);
+    e.launch[0] = &launch_flat<CfgA, CfgB, 0, NSTAGE, MINB>;
+    e.launch[1] = &launch_flat<CfgA, CfgB, 1, NSTAGE, MINB>;
+    e.max_ctas[0] = &flat_max_ctas<CfgA, CfgB, 0, NSTAGE, MINB>;
+    e.max_ctas[1] = &flat_max_ctas<CfgA, CfgB, 1, NSTAGE, MINB>;
+    return e;
+}
+
+}  // namespace ssfft

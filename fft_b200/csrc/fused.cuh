@@ -164,7 +164,7 @@ __device__ __forceinline__ cx<T> ld_table(const cx<T> *p) {
 #ifdef SSFFT_EMUL
 // Host emulation of the kernels (tests/host/simt/simt_emul.h, CPU tests only): same call sites, hooks instead of PTX.
 inline unsigned smem_u32(const void *p) { return (unsigned)reinterpret_cast<size_t>(p); }
-inline void mbar_init(unsigned long long *bar, unsigned) { simt::mbar_init(bar); }
+inline void mbar_init(unsigned long long *bar, unsigned count) { simt::mbar_init(bar, count); }
 inline void mbar_expect_tx(unsigned long long *bar, unsigned bytes) { simt::mbar_expect_tx(bar, bytes); }
 inline void mbar_wait(unsigned long long *bar, unsigned parity) { simt::mbar_wait(bar, parity); }
 inline void bulk_g2s(void *dst_smem, const void *src_gmem, unsigned bytes, unsigned long long *bar) {

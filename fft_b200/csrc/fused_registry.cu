@@ -4,6 +4,7 @@
 #include "fused.cuh"
 #include "cluster.cuh"
 #include "tiled.cuh"
+#include "flat.cuh"
 namespace ssfft {
 void register_fused_f32_a(std::vector<FusedEntry> &);
 void register_fused_f32_b(std::vector<FusedEntry> &);
@@ -78,6 +79,22 @@ int fourstep_cluster_size() {
         return (v < 1 || v > 16) ? 4 : v;
     }();
     return c;
+}
+
+void register_flat_f32_a(std::vector<FlatEntry> &);
+void register_flat_f32_b(std::vector<FlatEntry> &);
+
+const std::vector<FlatEntry> &flat_registry() {
+    static const std::vector<FlatEntry> reg = [] {
+        std::vector<FlatEntry> v;
+        const char *off = getenv("SSFFT_DISABLE_FLAT");  // fall back to the cluster kernels of tiled.cuh / cluster.cuh
+        const char *off2 = getenv("SSFFT_DISABLE_TILED");
+        if ((off && off[0] == '1') || (off2 && off2[0] == '1')) return v;
+        register_flat_f32_a(v);
+        register_flat_f32_b(v);
+        return v;
+    }();
+    return reg;
 }
 
 void register_cluster_f32_a(std::vector<ClusterEntry> &);

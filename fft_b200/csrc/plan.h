@@ -58,6 +58,14 @@ struct ssfft_plan {
     void *d_scratch = nullptr;  // four-step intermediate, chunk transforms
     size_t chunk = 0;
 
+    // ticket-queue four-step (flat.cuh): registry id, -1 = not used.  Complex transforms only for now.
+    int flat_id = -1;
+    int flat_ctas = 0;                     // co-resident CTAs of the persistent launch
+    int flat_slots = 0;                    // scratch slots (transforms) allocated
+    void *d_flat_ga = nullptr, *d_flat_gb = nullptr, *d_flat_s4 = nullptr, *d_flat_twb = nullptr;
+    void *d_flat_scratch = nullptr, *d_flat_ctrl = nullptr;
+    long long flat_cap = 0;                // transforms per launch the dependency counters cover
+
     // cluster-resident four-step (cluster.cuh): registry id per kind (C2C / R2C / C2R), -1 = not used
     bool clustered = false;
     int cl_id[3] = {-1, -1, -1};

@@ -17,6 +17,7 @@
 
 #include "cluster.cuh"
 #include "ex_request.h"
+#include "flat.cuh"
 #include "fused.cuh"
 #include "generic.cuh"
 #include "generic_plan.h"
@@ -256,6 +257,84 @@ int exec_tiled(ssfft_plan *pl, int kind, const void *in, void *out, long long ba
     return SSFFT_OK;
 }
 
+// Ticket-queue four-step (flat.cuh), complex transforms: tables, scratch slots and dependency counters.  *ok = false
+// leaves the plan on its other paths (which stay set up as the fallback for inputs a tensor map cannot describe).
+int flat_span(int ctas, int tickets_per_phase) {  // phases that are in flight at once, with head-room
+    const int v = (3 * ctas + 2 * tickets_per_phase - 1) / (2 * tickets_per_phase);
+    return v < 1 ? 1 : v;
+}
+template <typename T>
+int setup_flat(ssfft_plan *pl, bool *ok) {
+    *ok = false;
+    const size_t n = pl->n;
+    if (pl->kind != SSFFT_C2C || n == 0 || (n & (n - 1))) return SSFFT_OK;
+    int lg = 0;
+    while (((size_t)1 << lg) < n) ++lg;
+    if (lg < env_int("SSFFT_FLAT_MIN_LOG2", 15)) return SSFFT_OK;
+    const size_t n1 = (size_t)1 << (lg / 2), n2 = n / n1;
+    const int id = find_flat<T>(n1, n2);
+    if (id < 0) return SSFFT_OK;
+    const FlatEntry &e = flat_registry()[id];
+    int ctas = e.max_ctas[0]();
+    const int ctas_inv = e.max_ctas[1]();
+    if (ctas_inv < ctas) ctas = ctas_inv;
+    if (ctas < 1) return SSFFT_OK;
+    std::vector<T> ga, gb, s4, twb;
+    fill_flat_tables<T>(ga, gb, s4, n1, n2, e.ra0, e.ra1);
+    fill_flat_row_twiddles<T>(twb, e.n2, e.rb, e.nb_passes, e.tile_b_tw);
+    auto up = [&](void **d, const std::vector<T> &h) -> int {
+        CU(cudaMalloc(d, h.size() * sizeof(T)));
+        CU(cudaMemcpy(*d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+        return SSFFT_OK;
+    };
+    int rc;
+    if ((rc = up(&pl->d_flat_ga, ga)) || (rc = up(&pl->d_flat_gb, gb)) || (rc = up(&pl->d_flat_s4, s4)) || (rc = up(&pl->d_flat_twb, twb)))
+        return rc;
+    const int pt = (int)(n2 / e.cta + n1 / e.ctb);
+    int slots = 2 * flat_span(ctas, pt) + 1;
+    if (env_int("SSFFT_FLAT_SLOTS", 0) > slots) slots = env_int("SSFFT_FLAT_SLOTS", 0);
+    CU(cudaMalloc(&pl->d_flat_scratch, (size_t)slots * n * sizeof(cx<T>)));
+    pl->flat_cap = 1 << 16;
+    CU(cudaMalloc(&pl->d_flat_ctrl, (size_t)(32 + 2 * pl->flat_cap) * sizeof(unsigned)));
+    pl->flat_id = id; pl->flat_ctas = ctas; pl->flat_slots = slots;
+    if (!pl->n1) { pl->n1 = n1; pl->n2 = n2; }
+    *ok = true;
+    return SSFFT_OK;
+}
+
+// returns SSFFT_OK, an error, or -1: this input has no tensor map (pointer not 16-byte aligned) -- use the other path
+template <typename T>
+int exec_flat(ssfft_plan *pl, const void *in, void *out, long long batch, int inverse, cudaStream_t s) {
+    const FlatEntry &e = flat_registry()[pl->flat_id];
+    const long long n = (long long)pl->n;
+    if ((reinterpret_cast<uintptr_t>(in) & 15u) != 0) return -1;
+    const int tiles1 = e.n2 / e.cta, tiles2 = e.n1 / e.ctb, pt = tiles1 + tiles2;
+    for (long long b0 = 0; b0 < batch; b0 += pl->flat_cap) {
+        const long long nb = batch - b0 < pl->flat_cap ? batch - b0 : pl->flat_cap;
+        long long ctas = nb * (tiles1 > tiles2 ? tiles1 : tiles2);
+        if (ctas > pl->flat_ctas) ctas = pl->flat_ctas;
+        const int span = flat_span((int)ctas, pt);
+        long long delay = env_int("SSFFT_FLAT_DELAY", -1) >= 0 ? env_int("SSFFT_FLAT_DELAY", -1) : span;
+        if (delay > nb) delay = nb;
+        if (delay > pl->flat_slots - 1) delay = pl->flat_slots - 1;
+        long long slots = env_int("SSFFT_FLAT_SLOTS", 0) > 0 ? env_int("SSFFT_FLAT_SLOTS", 0) : delay + span + 1;
+        if (slots > pl->flat_slots) slots = pl->flat_slots;
+        if (slots < delay + 1) slots = delay + 1;
+        FlatParams<T> q;
+        q.in = (const cx<T> *)in + b0 * n; q.out = (cx<T> *)out + b0 * n; q.scratch = (cx<T> *)pl->d_flat_scratch;
+        q.tw_b = (const cx<T> *)pl->d_flat_twb; q.ga = (const cx<T> *)pl->d_flat_ga; q.gb = (const cx<T> *)pl->d_flat_gb;
+        q.s4 = (const cx<T> *)pl->d_flat_s4; q.ctrl = (unsigned *)pl->d_flat_ctrl;
+        q.batch = nb; q.user_stride = n; q.scratch_per = n; q.cap = nb;
+        q.nslots = (int)slots; q.delay = (int)delay; q.discard = env_int("SSFFT_DISCARD", 1);
+        CU(cudaMemsetAsync(pl->d_flat_ctrl, 0, (size_t)(32 + 2 * nb) * sizeof(unsigned), s));
+        const int rc = e.launch[inverse ? 1 : 0](&q, (int)ctas, s);
+        if (rc == 3) return -1;
+        ++g_launches;
+        if (rc) return cuda_fail(cudaGetLastError(), "fourstep_flat_kernel launch");
+    }
+    return SSFFT_OK;
+}
+
 // Cluster-resident four-step (cluster.cuh): the transform lives in the shared memory of a thread-block cluster.
 // Complex length pl->n; real plans need both the R2C and the C2R kernel.  *ok = false leaves the plan untouched.
 template <typename T>
@@ -314,6 +393,10 @@ template <typename T>
 int exec_complex(ssfft_plan *pl, const void *in, void *out, long long batch, int inverse, cudaStream_t s) {
     const long long n = (long long)pl->n;
     if (batch <= 0 || n == 0) return SSFFT_OK;
+    if (pl->flat_id >= 0 && pl->kind == SSFFT_C2C) {
+        const int rc = exec_flat<T>(pl, in, out, batch, inverse, s);
+        if (rc >= 0) return rc;
+    }
     if (pl->clustered && pl->kind == SSFFT_C2C) return exec_clustered<T>(pl, 0, in, out, batch, inverse, s);
     if (pl->tiled && pl->kind == SSFFT_C2C) return exec_tiled<T>(pl, 0, in, out, batch, inverse, s);
     if (!pl->four_step) {
@@ -364,7 +447,18 @@ int build_plan_typed(ssfft_plan *pl) {
         int rc = setup_tiled<T>(pl, pl->n_real, true, &tiled_ok);
         if (rc) return rc;
     }
-    if (clustered_ok) {
+    bool flat_ok = false;
+    if (pl->kind == SSFFT_C2C && (clustered_ok || tiled_ok)) {
+        int rc = setup_flat<T>(pl, &flat_ok);
+        if (rc) return rc;
+    }
+    if (flat_ok) {
+        const FlatEntry &e = flat_registry()[pl->flat_id];
+        snprintf(buf, sizeof(buf), "complex N=%zu ticket-queue four-step n1=%d x n2=%d (%s): one persistent launch of %d CTAs "
+                 "(%d consumer threads + a TMA producer warp each, ring of %d), %d scratch slots = %.1f MiB in L2", n, e.n1, e.n2,
+                 e.name, pl->flat_ctas, e.threads - 32, e.nstage, pl->flat_slots, pl->flat_slots * (double)n * sizeof(cx<T>) / 1048576.0);
+        pl->desc = buf;
+    } else if (clustered_ok) {
         const int k = pl->kind == SSFFT_C2C ? 0 : 1;
         const ClusterEntry &e = cluster_registry()[pl->cl_id[k]];
         if (pl->kind == SSFFT_C2C)
@@ -675,7 +769,8 @@ int ssfft_plan_destroy(ssfft_plan *pl) {
     free_stage(pl->direct); free_stage(pl->col); free_stage(pl->row);
     void *ptrs[] = {pl->fused.d_twiddles, pl->fused_col.d_twiddles, pl->fused_row.d_twiddles, pl->d_ep_lo, pl->d_ep_hi,
                     pl->d_scratch, pl->d_rtw, pl->d_rot, pl->d_stage_in, pl->d_stage_out, pl->d_tile_tw_a, pl->d_tile_tw_b,
-                    pl->d_tw4, pl->d_fs_ctr, pl->d_ex_in, pl->d_ex_out};
+                    pl->d_tw4, pl->d_fs_ctr, pl->d_ex_in, pl->d_ex_out, pl->d_flat_ga, pl->d_flat_gb, pl->d_flat_s4,
+                    pl->d_flat_twb, pl->d_flat_scratch, pl->d_flat_ctrl};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     for (int k = 0; k < 3; ++k) {

@@ -49,12 +49,14 @@ struct Fiber {
     unsigned cta = 0;  // index among the resident CTAs
     enum { RUNNABLE, AT_BARRIER, DONE } st = RUNNABLE;
     unsigned cl_waits = 0;  // cluster-barrier phases this thread has waited for
+    unsigned bar_id = 0, bar_count = 0;  // AT_BARRIER: 0 = __syncthreads (every live thread), else bar.sync id, count
 };
 
-struct Mbar {  // emulated mbarrier (arrival count 1 + transaction bytes); a CTA's mbarriers are told apart by address
+struct Mbar {  // emulated mbarrier (arrival count + transaction bytes); a CTA's mbarriers are told apart by address
     unsigned phase = 0;
+    unsigned expected = 1, arrived = 0;  // arrivals a phase needs / has seen
     long long pending_tx = 0;  // may go negative: transactions can complete before the expect-tx of their phase
-    bool armed = false;
+    bool armed = false;        // every expected arrival of the current phase is in
     struct Pending { void *dst; const void *src; unsigned bytes; unsigned char value[16]; };  // src == nullptr: `value`
     std::vector<Pending> pending;
 };
@@ -195,13 +197,27 @@ inline bool launch(dim3 grid, dim3 block, const std::function<void()> &body, Lau
         };
         auto release_barriers = [&]() {  // release the block barriers every participant has reached; cluster phases
             for (unsigned c = 0; c < live_ctas; ++c) {
-                size_t at = 0, run = 0;
+                size_t at = 0, run = 0, named[16] = {0}, want[16] = {0};
                 for (unsigned i = 0; i < nthreads; ++i) {
                     const Fiber &f = s.fibers[(size_t)c * nthreads + i];
-                    at += f.st == Fiber::AT_BARRIER;
+                    if (f.st == Fiber::AT_BARRIER) {
+                        if (f.bar_id == 0) ++at;
+                        else { ++named[f.bar_id & 15]; want[f.bar_id & 15] = f.bar_count; }
+                    }
                     run += f.st == Fiber::RUNNABLE;
                 }
-                if (at && !run) {
+                bool any_named = false;
+                for (unsigned id = 1; id < 16; ++id) {
+                    if (!named[id]) continue;
+                    any_named = true;
+                    if (named[id] < want[id]) continue;
+                    for (unsigned i = 0; i < nthreads; ++i) {
+                        Fiber &f = s.fibers[(size_t)c * nthreads + i];
+                        if (f.st == Fiber::AT_BARRIER && f.bar_id == id) f.st = Fiber::RUNNABLE;
+                    }
+                    s.progress = true;
+                }
+                if (at && !run && !any_named) {
                     for (unsigned i = 0; i < nthreads; ++i) {
                         Fiber &f = s.fibers[(size_t)c * nthreads + i];
                         if (f.st == Fiber::AT_BARRIER) f.st = Fiber::RUNNABLE;
@@ -211,6 +227,7 @@ inline bool launch(dim3 grid, dim3 block, const std::function<void()> &body, Lau
             }
             for (unsigned cl = 0; cl < live_ctas / cluster; ++cl) cluster_check(cl);  // threads that returned no longer count
         };
+        int idle_rounds = 0;
         for (;;) {
             s.progress = false;
             if (s.cta_priority == 0) {
@@ -231,7 +248,10 @@ inline bool launch(dim3 grid, dim3 block, const std::function<void()> &body, Lau
                 parked += s.fibers[i].st == Fiber::AT_BARRIER;
             }
             if (!runnable && !parked) break;  // every thread returned
-            if (!s.progress) {
+            // a poll that yields BEFORE it looks (ld_acquire_gpu) sees a change one round late: only several rounds in
+            // a row in which nothing at all happened are a deadlock
+            idle_rounds = s.progress ? 0 : idle_rounds + 1;
+            if (idle_rounds >= 4) {
                 fprintf(stderr, "simt: deadlock (CTAs %u..%u): %zu thread(s) spinning, %zu parked at a barrier nobody else reaches\n",
                         first, first + live_ctas - 1, runnable, parked);
                 return false;
@@ -246,12 +266,17 @@ inline Mbar &mbar_of(unsigned cta, const void *bar) { return state().mbar[cta][b
 inline void mbar_complete_if_ready(Mbar &m) {
     if (m.armed && m.pending_tx == 0) { m.armed = false; ++m.phase; state().progress = true; }
 }
-inline void mbar_init(const void *bar) { mbar_of(self().cta, bar) = Mbar(); }
-inline void mbar_expect_tx(const void *bar, unsigned bytes) {  // arrive (count 1) + expect-tx
+inline void mbar_init(const void *bar, unsigned count = 1) { Mbar m; m.expected = count ? count : 1; mbar_of(self().cta, bar) = m; }
+inline void mbar_arrive_n(Mbar &m) {
+    if (++m.arrived >= m.expected) { m.arrived = 0; m.armed = true; }
+    state().progress = true;
+    mbar_complete_if_ready(m);
+}
+inline void mbar_arrive(const void *bar) { mbar_arrive_n(mbar_of(self().cta, bar)); }  // plain arrival
+inline void mbar_expect_tx(const void *bar, unsigned bytes) {  // one arrival + expect-tx
     Mbar &m = mbar_of(self().cta, bar);
     m.pending_tx += bytes;
-    m.armed = true;
-    mbar_complete_if_ready(m);
+    mbar_arrive_n(m);
 }
 inline void land(Mbar &m, const Mbar::Pending &c) {
     memcpy(c.dst, c.src ? c.src : (const void *)c.value, c.bytes);
@@ -281,6 +306,14 @@ inline void remote_store_tx(unsigned rank, void *peer_dst, const void *value, un
     land(m, c);
     mbar_complete_if_ready(m);
 }
+// mbarrier.test_wait: has the phase with this parity completed?  Never blocks.
+inline bool mbar_test(const void *bar, unsigned parity) {
+    Mbar &m = mbar_of(self().cta, bar);
+    for (auto &c : m.pending) land(m, c);
+    m.pending.clear();
+    mbar_complete_if_ready(m);
+    return (m.phase & 1u) != parity;
+}
 inline void mbar_wait(const void *bar, unsigned parity) {
     State &s = state();
     Mbar &m = mbar_of(self().cta, bar);
@@ -300,6 +333,20 @@ inline void __syncthreads() {
     simt::State &s = simt::state();
     ++s.barriers;
     s.progress = true;
+    simt::self().bar_id = 0;
     simt::self().st = simt::Fiber::AT_BARRIER;
     simt::yield_to_scheduler();
 }
+namespace simt {
+// bar.sync id, count (id >= 1): released when `count` threads of the CTA are parked at barrier `id`; threads that do
+// not take part (a producer warp) keep running
+inline void named_barrier(unsigned id, unsigned count) {
+    State &s = state();
+    ++s.barriers;
+    s.progress = true;
+    self().bar_id = id;
+    self().bar_count = count;
+    self().st = Fiber::AT_BARRIER;
+    yield_to_scheduler();
+}
+}  // namespace simt

@@ -1,0 +1,115 @@
+"""GPU parity tests (-m gpu) of the ticket-queue four-step kernels (fft_b200/csrc/flat.cuh) through the C ABI.
+
+Every registered variant (ring depth x CTAs per SM, SSFFT_FLAT_VARIANT) against the oracle in the same precision, bar
+1e-6 * log2(N) relative L2 per transform: batches from one transform (fewer tiles than CTAs) to several times the number
+of scratch slots (slots are reused, every CTA loops), forward and inverse, in place, repeated calls on one plan (the
+dependency counters are reset per launch), extreme scheduling parameters (no delay / one slot more than the delay), and
+-- at a batch of 4096 -- ifft(fft(x)) = N x plus an oracle-checked subset.
+"""
+import math
+import os
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+import fft_b200  # noqa: E402
+
+SIZES = [32768, 65536]
+VARIANTS = ["1,3", "2,2"]
+
+
+def tol(n):
+    return 1e-6 * math.log2(n)
+
+
+@pytest.fixture
+def flat_env():
+    keys = ("SSFFT_FLAT_VARIANT", "SSFFT_FLAT_DELAY", "SSFFT_FLAT_SLOTS", "SSFFT_DISCARD")
+    saved = {k: os.environ.get(k) for k in keys}
+    yield os.environ
+    for k, v in saved.items():
+        if v is None:
+            os.environ.pop(k, None)
+        else:
+            os.environ[k] = v
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
+@pytest.mark.parametrize("n", SIZES)
+def test_flat_vs_oracle(oracle, cuda_device, flat_env, n, variant):
+    flat_env["SSFFT_FLAT_VARIANT"] = variant
+    f = fft_b200.FFT(n)
+    assert "ticket-queue" in f.describe(), f.describe()
+    for batch in (1, 2, 37, 300):
+        x = oracle.uniform_complex((batch, n), 11 + batch, np.complex64)
+        xd = torch.from_numpy(x).cuda()
+        out = torch.empty_like(xd)
+        for inverse in (False, True):
+            out.zero_()
+            (f.ifft if inverse else f.fft)(xd, out)
+            torch.cuda.synchronize()
+            assert torch.equal(xd.cpu(), torch.from_numpy(x)), "input was changed"
+            ref = oracle.run(oracle.KIND_C2C_INV if inverse else oracle.KIND_C2C_FWD, x, n, threads=8)[0]
+            err = oracle.rel_l2(out.cpu().numpy(), ref)
+            assert err <= tol(n), (n, variant, batch, inverse, err)
+    # same plan again, in place
+    x = oracle.uniform_complex((9, n), 5, np.complex64)
+    xd = torch.from_numpy(x).cuda()
+    f.fft(xd, xd)
+    torch.cuda.synchronize()
+    assert oracle.rel_l2(xd.cpu().numpy(), oracle.run(oracle.KIND_C2C_FWD, x, n, threads=8)[0]) <= tol(n)
+
+
+@pytest.mark.parametrize("n", SIZES)
+def test_flat_scheduling_extremes(oracle, cuda_device, flat_env, n):
+    x = oracle.uniform_complex((150, n), 3, np.complex64)
+    ref = oracle.run(oracle.KIND_C2C_FWD, x, n, threads=8)[0]
+    xd = torch.from_numpy(x).cuda()
+    for delay, slots, discard in (("0", "1", "1"), ("3", "4", "1"), ("1", "64", "0"), ("40", "41", "1")):
+        flat_env["SSFFT_FLAT_DELAY"], flat_env["SSFFT_FLAT_SLOTS"], flat_env["SSFFT_DISCARD"] = delay, slots, discard
+        f = fft_b200.FFT(n)
+        out = torch.zeros_like(xd)
+        f.fft(xd, out)
+        torch.cuda.synchronize()
+        err = oracle.rel_l2(out.cpu().numpy(), ref)
+        assert err <= tol(n), (n, delay, slots, err)
+
+
+def test_flat_falls_back_for_unaligned_input(oracle, cuda_device):
+    n, batch = 65536, 5
+    x = oracle.uniform_complex((batch, n), 9, np.complex64)
+    buf = torch.zeros(batch * n + 1, dtype=torch.complex64, device="cuda")
+    xin = buf[1:].view(batch, n)
+    xin.copy_(torch.from_numpy(x))
+    assert xin.data_ptr() % 16 == 8
+    out = torch.empty((batch, n), dtype=torch.complex64, device="cuda")
+    f = fft_b200.FFT(n)
+    f.fft(xin, out)
+    torch.cuda.synchronize()
+    assert oracle.rel_l2(out.cpu().numpy(), oracle.run(oracle.KIND_C2C_FWD, x, n, threads=4)[0]) <= tol(n)
+
+
+@pytest.mark.parametrize("n", SIZES)
+def test_flat_large_batch_properties(oracle, cuda_device, n):
+    batch = 4096 * 65536 // n // 2
+    xd = torch.empty((batch, n), dtype=torch.complex64, device="cuda")
+    fft_b200.fill_uniform(xd, 77)
+    f = fft_b200.FFT(n)
+    y = torch.empty_like(xd)
+    z = torch.empty_like(xd)
+    f.fft(xd, y)
+    f.ifft(y, z)
+    torch.cuda.synchronize()
+    err = (torch.linalg.vector_norm(z / n - xd) / torch.linalg.vector_norm(xd)).item()
+    assert err <= 2 * tol(n), err
+    # Parseval per transform
+    e_in = torch.linalg.vector_norm(xd, dim=1) ** 2 * n
+    e_out = torch.linalg.vector_norm(y, dim=1) ** 2
+    assert torch.max(torch.abs(e_out / e_in - 1)).item() < 1e-4
+    idx = [0, 1, batch // 2, batch - 2, batch - 1]
+    x_sub = xd[idx].cpu().numpy()
+    ref = oracle.run(oracle.KIND_C2C_FWD, x_sub, n, threads=5)[0]
+    assert oracle.rel_l2(y[idx].cpu().numpy(), ref) <= tol(n)
