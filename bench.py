@@ -30,6 +30,17 @@ sys.path.insert(0, ROOT)
 METRIC = "Batched fp32 C2C FFT GFLOP/s (5N·log2N) & % of HBM roofline, N=4096"
 SEED = 20261017
 
+
+def metric_for(workload):
+    """BASELINE.json's metric is quoted on config 2 (the default workload); other workloads name their own size."""
+    kind, dtype, n, _ = WORKLOADS[workload]
+    if workload == "c2":
+        return METRIC
+    p = "fp32" if dtype == "float32" else "fp64"
+    if kind == "c2c":
+        return f"Batched {p} C2C FFT GFLOP/s (5N·log2N) & % of HBM roofline, N={n}"
+    return f"Batched {p} RealFFT forward+inverse GFLOP/s (2 x 2.5N·log2N) & % of HBM roofline, N={n}"
+
 WORKLOADS = {
     # name: (kind, dtype, N, batch)
     "c2": ("c2c", "float32", 4096, 65536),
@@ -176,7 +187,7 @@ def run_reference(args):
     total = sum(secs)
     value = sample * args.steps * flops_per_transform(kind, n) / total / 1e9
     line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": "GFLOP/s", "n_gpus": args.gpus,
+        "impl": "reference", "metric": metric_for(args.workload), "value": value, "unit": "GFLOP/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32" if dtype == "float32" else "f64",
         "data": "synthetic uniform[-0.5,0.5), counter-based generator, seed %d" % SEED,
@@ -193,6 +204,15 @@ def run_reference(args):
 
 def run_dist(args, n, rank, world, dev, dist):
     """BASELINE config 5: ONE length-n complex transform sharded over all ranks (fft_b200/dist.py)."""
+    line = measure_dist(args, n, rank, world, dev, dist, steps=args.steps, warmup=args.warmup, verify=args.verify)
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def measure_dist(args, n, rank, world, dev, dist, steps, warmup, verify):
     import torch
 
     import fft_b200
@@ -216,7 +236,7 @@ def run_dist(args, n, rank, world, dev, dist):
     elif not args.nccl_exchange:
         plan.enable_peer_exchange(dev)
         exchange = "fused transpose + direct peer stores over NVLink (CUDA IPC), no NCCL on the data path"
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         plan.fft(x, y)
     barrier()
     sampler = ClockSampler(int(os.environ.get("LOCAL_RANK", "0")))
@@ -227,7 +247,7 @@ def run_dist(args, n, rank, world, dev, dist):
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     ev0.record()
-    for _ in range(args.steps):
+    for _ in range(steps):
         plan.fft(x, y)
     ev1.record()
     barrier()
@@ -238,7 +258,7 @@ def run_dist(args, n, rank, world, dev, dist):
         t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_total = float(t.item())
-    ms_step = ms_total / args.steps
+    ms_step = ms_total / steps
     # per-phase breakdown (outside the timed region): two extra calls with CUDA events between the phases
     plan.profile = {}
     for _ in range(2):
@@ -252,7 +272,7 @@ def run_dist(args, n, rank, world, dev, dist):
     # size-independent checks (the oracle cannot run 2^30 casually): single tone -> N delta,
     # Parseval, and ifft(fft(x)) = N x on the random input
     checks = None
-    if args.verify:
+    if verify:
         def allsum(v):
             t = torch.tensor([float(v)], dtype=torch.float64, device=dev)
             if world > 1:
@@ -281,11 +301,12 @@ def run_dist(args, n, rank, world, dev, dist):
         checks = {"tone_rel_err": tone_err, "parseval_rel_err": abs(ey / (n * ex) - 1.0), "roundtrip_rel_l2": rt_err,
                   "tolerance": lim, "ok": bool(tone_err <= lim and rt_err <= 2 * lim and abs(ey / (n * ex) - 1.0) < 1e-4)}
         del back
+    line = None
     if rank == 0:
         line = {
             "metric": "Distributed fp32 C2C FFT GFLOP/s (5N·log2N), single transform N=%d" % n,
-            "value": flops / (ms_step * 1e-3) / 1e9, "unit": "GFLOP/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
+            "value": flops / (ms_step * 1e-3) / 1e9, "unit": "GFLOP/s", "n_gpus": world, "steps": steps,
+            "warmup": warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32",
             "data": f"synthetic uniform[-0.5,0.5), counter-based generator, seed {SEED}",
             "config": {"workload": f"{args.workload}: one c2c float32 transform of N={n} = {plan.n1} x {plan.n2}, "
@@ -300,10 +321,133 @@ def run_dist(args, n, rank, world, dev, dist):
         }
         if checks:
             line["checks"] = checks
-        print(json.dumps(line))
+    barrier()
+    if getattr(plan, "_peers", None) is not None:  # unmap the peers' exchange buffers, free mine
+        plan._peers.close()
+    del plan, x, y
+    torch.cuda.empty_cache()
+    return line
+
+
+def measure_batched(name, dev, rank, world, dist, steps=5, warmup=3, subset=4):
+    """One BASELINE config other than the headline: device-resident timing (CUDA events, max over ranks) plus the
+    relative L2 error of a few transforms against the oracle in the same precision."""
+    import numpy as np
+    import torch
+
+    import fft_b200
+
+    kind, dtype, n, batch = WORKLOADS[name]
+    tdt = torch.float32 if dtype == "float32" else torch.float64
+    cdt = torch.complex64 if dtype == "float32" else torch.complex128
+    if kind == "c2c":
+        plan = fft_b200.FFT(n, dtype=dtype)
+        x = torch.empty((batch, n), dtype=cdt, device=dev)
+        y = torch.empty_like(x)
+        fft_b200.fill_uniform(x, SEED, first_idx=rank * batch * n * 2)
+
+        def step():
+            plan.fft(x, y)
+    else:
+        plan = fft_b200.RealFFT(n, dtype=dtype)
+        x = torch.empty((batch, n), dtype=tdt, device=dev)
+        y = torch.empty((batch, n // 2), dtype=cdt, device=dev)
+        z = torch.empty_like(x)
+        fft_b200.fill_uniform(x, SEED, first_idx=rank * batch * n)
+
+        def step():
+            plan.fft(x, y)
+            plan.ifft(y, z)
+
+    for _ in range(warmup):
+        step()
+    torch.cuda.synchronize()
     if world > 1:
-        dist.destroy_process_group()
-    return 0
+        dist.barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(steps):
+        step()
+    ev1.record()
+    torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1) / steps
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    peak, _ = measured_peak()
+    out = {"workload": f"{kind} {dtype} N={n} x {batch} per GPU" + (" fwd+inv" if kind != "c2c" else ""), "ms": ms,
+           "gflops": world * batch * flops_per_transform(kind, n) / (ms * 1e-3) / 1e9,
+           "roofline_frac": batch * alg_bytes_per_transform(kind, n, dtype) / (ms * 1e-3) / 1e9 / peak,
+           "plan": plan.describe()[:160]}
+    if rank == 0:
+        from oracle import oracle as O  # checker only
+
+        xs = x[:subset].cpu().numpy()
+        if kind == "c2c":
+            ref = O.run(O.KIND_C2C_FWD, xs, n, subset)[0]
+            out["parity_relL2_vs_oracle_on_a_subset"] = float(O.rel_l2(y[:subset].cpu().numpy(), ref))
+        else:
+            ref = O.rfft(xs)
+            out["parity_relL2_vs_oracle_on_a_subset"] = float(O.rel_l2(y[:subset].cpu().numpy(), ref))
+            back = O.run(O.KIND_C2R, ref, n, subset)[0]
+            out["parity_relL2_inverse"] = float(O.rel_l2(z[:subset].cpu().numpy(), back))
+        lim = (1e-6 if dtype == "float32" else 1e-14) * math.log2(n)
+        out["parity_tolerance"] = lim
+        out["parity_ok"] = bool(out["parity_relL2_vs_oracle_on_a_subset"] <= lim and out.get("parity_relL2_inverse", 0.0) <= 2 * lim)
+    return out
+
+
+def measure_c1(dev):
+    """BASELINE config 1: ONE FFT<double> N=1024 transform, fft + ifft round trip -- device-resident and through the
+    host call a reference user makes (numpy in / out -> ssfft_exec_host), beside the reference on one host core."""
+    import numpy as np
+    import torch
+
+    import fft_b200
+    from oracle import oracle as O  # checker / baseline only
+
+    n = 1024
+    plan = fft_b200.FFT(n, dtype="float64")
+    xh = O.uniform_complex((1, n), SEED, np.complex128)
+    x = torch.from_numpy(xh).to(dev)
+    y = torch.empty_like(x)
+    z = torch.empty_like(x)
+    for _ in range(20):
+        plan.fft(x, y)
+        plan.ifft(y, z)
+    torch.cuda.synchronize()
+    iters = 300
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(iters):
+        plan.fft(x, y)
+        plan.ifft(y, z)
+    ev1.record()
+    torch.cuda.synchronize()
+    dev_us = 1e3 * ev0.elapsed_time(ev1) / iters
+    yh, zh = np.empty_like(xh), np.empty_like(xh)
+    for _ in range(20):
+        plan.fft(xh, yh)
+        plan.ifft(yh, zh)
+    t0 = time.perf_counter()
+    for _ in range(iters):
+        plan.fft(xh, yh)
+        plan.ifft(yh, zh)
+    host_us = 1e6 * (time.perf_counter() - t0) / iters
+    impl = "reference" if O.have_reference() else "port"
+    reps = np.repeat(xh, 2000, axis=0)
+    secs = O.run(O.KIND_C2C_FWD, reps, n, 1, impl)[1] + O.run(O.KIND_C2C_INV, reps, n, 1, impl)[1]
+    ref = O.fft(xh)
+    err = float(O.rel_l2(yh, ref))
+    rt = float(O.rel_l2(zh / n, xh))
+    flops = 2 * 5.0 * n * math.log2(n)
+    return {"workload": "c2c float64 N=1024 x 1, fft + ifft round trip", "device_resident_us_per_pair": dev_us,
+            "e2e_host_call_us_per_pair": host_us, "e2e_gflops": flops / host_us / 1e3,
+            "reference_cpu_us_per_pair_1_core": 1e6 * secs / 2000, "reference_kind": impl,
+            "parity_relL2_vs_oracle_on_a_subset": err, "roundtrip_relL2": rt, "parity_tolerance": 1e-14 * math.log2(n),
+            "parity_ok": bool(err <= 1e-14 * math.log2(n)),
+            "note": "launch-latency bound: one 16 KiB transform cannot fill a GPU; the batched configs are the product"}
 
 
 def main():
@@ -316,6 +460,7 @@ def main():
     ap.add_argument("--batch", type=int, default=0, help="override transforms per GPU (tests only)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the short runs of the other BASELINE configs")
     ap.add_argument("--verify", action="store_true", help="c5: tone / Parseval / round-trip checks at full size")
     ap.add_argument("--nccl-exchange", action="store_true", help="c5: use NCCL all_to_all instead of fused peer stores")
     args = ap.parse_args()
@@ -476,10 +621,41 @@ def main():
                          f"threads, one {'FFT' if kind == 'c2c' else 'RealFFT'}<{dtype}> object per thread, plan "
                          "build excluded, best of 2"}
 
+    # ---- the other BASELINE configs, short runs (the headline fields above stay config 2)
+    configs = None
+    if args.workload == "c2" and not args.no_configs and not args.batch:
+        del x, y
+        torch.cuda.empty_cache()
+        configs = {}
+        t_cfg = time.perf_counter()
+        names = ["c3", "c4-1000", "c4-2187", "c4-3125", "c4-6000", "c4-1000-f64", "c4-2187-f64", "c4-3125-f64", "c4-6000-f64"]
+        for name in names:
+            try:
+                configs[name] = measure_batched(name, dev, rank, world, dist)
+            except Exception as exc:  # a config that cannot run must not lose the headline
+                configs[name] = {"error": repr(exc)[:300]}
+            torch.cuda.empty_cache()
+        if rank == 0 and world == 1:
+            try:
+                configs["c1"] = measure_c1(dev)
+            except Exception as exc:
+                configs["c1"] = {"error": repr(exc)[:300]}
+        if world > 1:
+            try:
+                c5 = measure_dist(args, 1 << 30, rank, world, dev, dist, steps=3, warmup=2, verify=True)
+                if rank == 0:
+                    configs["c5"] = {"workload": c5["config"]["workload"], "ms": c5["ms_per_step"], "gflops": c5["value"],
+                                     "phase_ms_rank0": c5["config"]["phase_ms_rank0"],
+                                     "nvlink_GBps_per_gpu_if_exchange_only": c5["roofline"]["nvlink_GBps_per_gpu_if_exchange_only"],
+                                     "checks": c5.get("checks")}
+            except Exception as exc:
+                configs["c5"] = {"error": repr(exc)[:300]}
+        configs["seconds"] = round(time.perf_counter() - t_cfg, 1)
+
     traffic, traffic_src = profiled_traffic(args.workload) if not args.batch else (None, None)
     if rank == 0:
         line = {
-            "metric": METRIC, "value": value, "unit": "GFLOP/s", "n_gpus": world, "steps": args.steps,
+            "metric": metric_for(args.workload), "value": value, "unit": "GFLOP/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32" if dtype == "float32" else "f64",
             "data": f"synthetic uniform[-0.5,0.5), counter-based generator (device twin of the oracle's), seed {SEED}",
@@ -498,6 +674,8 @@ def main():
             line["e2e"] = e2e
         if cpu:
             line["cpu_baseline"] = cpu
+        if configs:
+            line["configs"] = configs
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

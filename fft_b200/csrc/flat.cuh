@@ -38,8 +38,8 @@ struct FlatParams {
     cx<T> *out;
     cx<T> *scratch;         // nslots * scratch_per elements
     const cx<T> *tw_b;      // row-stage pass twiddles ([r-1][m'] as in tiled.cuh)
-    const cx<T> *ga, *gb;   // W_N1^(b*2^k) [N1/R0][LOG0]   and   W_N^(n2*2^k) [N2][LOG0]
-    const cx<T> *s4;        // W_N^(n2*R0*r1) [N2][R1]
+    const cx<T> *ga[2], *gb[2];  // per non-last column pass p: W_(N1/P)^(m'*2^k) [N1/(P R)][LOG R]  and  W_(N/P)^(n2*2^k) [N2][LOG R]
+    const cx<T> *s4;        // W_N^(n2*P_last*r) [N2][R_last]
     unsigned *ctrl;         // [0] ticket counter; cnt1 = ctrl + 32; cnt2 = cnt1 + cap
     long long batch, user_stride, scratch_per, cap;
     int nslots, delay, discard;
@@ -48,19 +48,25 @@ struct FlatParams {
 __host__ __device__ constexpr int flat_ilog2(int v) { return v <= 1 ? 0 : 1 + flat_ilog2(v / 2); }
 __host__ __device__ constexpr int flat_topbit(int v) { return 1 << flat_ilog2(v); }
 
-// shared-memory map of a CTA (bytes)
-template <typename CfgA, typename CfgB, int NSTAGE>
+// shared-memory map of a CTA (bytes).  INPLACE: a ring slot is also the exchange buffer of the tile it holds (the TMA
+// copy lands dense at its start, the passes overwrite it with the padded image, the tile's slice of s4 sits behind it),
+// so a ring of two fits three CTAs per SM; otherwise one separate exchange buffer, dense slots and a small ring of s4
+// slices.  The row-stage pass table lives in shared memory when it is small (two-pass row tiles), else it is read
+// through L1 like the column-stage tables.
+template <typename CfgA, typename CfgB, int NSTAGE, bool INPLACE>
 struct FlatLayout {
     using T = typename CfgA::T;
     static constexpr size_t al(size_t v) { return (v + 127) / 128 * 128; }
     static constexpr size_t kTileA = (size_t)CfgA::L * CfgA::CT * sizeof(cx<T>), kTileB = (size_t)CfgB::L * CfgB::CT * sizeof(cx<T>);
-    static constexpr size_t kSlot = al(kTileA > kTileB ? kTileA : kTileB);
     static constexpr size_t kExchA = CfgA::smem_bytes, kExchB = CfgB::smem_bytes;
     static constexpr size_t kExch = al(kExchA > kExchB ? kExchA : kExchB);
-    static constexpr size_t kSBlk = al((size_t)CfgA::CT * CfgA::radix(1) * sizeof(cx<T>));
-    static constexpr size_t kTwB = al((size_t)(CfgB::tw_total > 0 ? CfgB::tw_total : 1) * sizeof(cx<T>));
-    static constexpr size_t oExch = 0, oSlots = oExch + kExch, oSBlk = oSlots + NSTAGE * kSlot, oTwB = oSBlk + (NSTAGE + 1) * kSBlk,
-                            oDesc = oTwB + kTwB, oBars = oDesc + al((size_t)(2 * NSTAGE + 1) * 16);
+    static constexpr size_t kSBlk = al((size_t)CfgA::CT * CfgA::radix(CfgA::NP - 1) * sizeof(cx<T>));
+    static constexpr size_t kSlot = INPLACE ? kExch + kSBlk : al(kTileA > kTileB ? kTileA : kTileB);
+    static constexpr bool kTwBShared = (size_t)CfgB::tw_total * sizeof(cx<T>) <= 2048;
+    static constexpr size_t kTwB = kTwBShared ? al((size_t)(CfgB::tw_total > 0 ? CfgB::tw_total : 1) * sizeof(cx<T>)) : 0;
+    static constexpr size_t oExch = 0, oSlots = oExch + (INPLACE ? 0 : kExch), oSBlk = oSlots + NSTAGE * kSlot,
+                            oTwB = oSBlk + (INPLACE ? 0 : (NSTAGE + 1) * kSBlk), oDesc = oTwB + kTwB,
+                            oBars = oDesc + al((size_t)(2 * NSTAGE + 1) * 16);
     static constexpr size_t smem_bytes = oBars + al((size_t)(3 * NSTAGE + 1) * 8);
 };
 
@@ -160,140 +166,160 @@ __device__ __forceinline__ void apply_powers(cx<T> (&w)[R], const cx<T> (&pw2)[f
     });
 }
 
-// ---- column tile: CT adjacent columns, length-L FFT each, times W_N^(n2*k1), into the tile-major scratch
-template <typename Cfg, int INV, int N2C, int CTBLOG, typename T, typename Release>
+// ---- column tile: CT adjacent columns, length-L FFT each, times W_N^(n2*k1), into the tile-major scratch.
+// Pass p (radix R, P = product of the earlier radices, butterfly b: m' = b / P, racc = b % P) writes digit r of
+// k1 = sum_p P_p r_p; its inter-pass twiddle W_L^(P m' r) and the factor W_N^(n2 P r) of the four-step twiddle are the
+// powers g^r of g = W_(L/P)^(m') * W_(N/P)^(n2) (tables ga[p], gb[p]); the last pass multiplies by s4[n2][r].
+template <typename Cfg, int INV, int N2C, int CTBLOG, bool INPLACE, typename T, typename Release>
 __device__ __forceinline__ void flat_stage_a(const FlatParams<T> &q, const cx<T> *st, const cx<T> *sb, cx<T> *sm, cx<T> *scr, int lane0,
                                              int tid, Release release) {
-    constexpr int L = Cfg::L, TX = Cfg::TX, CT = Cfg::CT, E = Cfg::E, PITCH = Cfg::PITCH, NC = Cfg::THREADS;
-    constexpr int R0 = Cfg::radix(0), R1 = Cfg::radix(1);
-    static_assert(Cfg::NP == 2, "two-pass tiles");
-    constexpr int U0 = E / R0, NR0 = L / R0, U1 = E / R1, NR1 = L / R1, LOG0 = flat_ilog2(R0);
-    static_assert(NR1 == R0 && (1 << LOG0) == R0 && R1 % 2 == 0, "radix layout");
+    constexpr int L = Cfg::L, TX = Cfg::TX, CT = Cfg::CT, E = Cfg::E, PITCH = Cfg::PITCH, NC = Cfg::THREADS, NP = Cfg::NP;
+    static_assert(NP == 2 || NP == 3, "two or three passes per tile");
     constexpr int CTB = 1 << CTBLOG;
-    static_assert(R0 % CTB == 0 || CTB % R0 == 0, "first radix and scratch block height must nest");
-    const int c = tid % CT, t = tid / CT;
+    constexpr int RL = Cfg::radix(NP - 1), PL = Cfg::prod(NP - 1);
+    static_assert(PL % CTB == 0 || CTB % PL == 0, "last-pass stride and scratch block height must nest");
+    static_assert(RL % 2 == 0, "pairs of last-pass twiddles are loaded together");
+    const int c = tid % CT, t = tid / CT;    // lanes along the columns (global / ring accesses)
+    const int t2 = tid % TX, c2 = tid / TX;  // last pass: lanes along k1 (scratch written in runs of consecutive k1)
     cx<T> v[E];
+    sfor<0, NP>([&](auto pc) {
+        constexpr int ps = decltype(pc)::value;
+        constexpr int R = Cfg::radix(ps), P = Cfg::prod(ps), NR = L / R, U = E / R, LOG = flat_ilog2(R);
+        constexpr bool first = ps == 0, last = ps == NP - 1;
+        static_assert((1 << LOG) == R && (P & (P - 1)) == 0, "power-of-two radices");
+        const int tt = last ? t2 : t, cc = last ? c2 : c;
+        if constexpr (first) {
 #pragma unroll
-    for (int u = 0; u < U0; ++u)
+            for (int u = 0; u < U; ++u)
 #pragma unroll
-        for (int j = 0; j < R0; ++j) {
-            const cx<T> x = st[(t + TX * u + NR0 * j) * CT + c];
-            v[u * R0 + j] = INV ? cswap(x) : x;
-        }
-    release();  // the ring slot may be refilled
-#pragma unroll
-    for (int u = 0; u < U0; ++u) {
-        const int b = t + TX * u;
-        cx<T> g[LOG0];
-        {
-            cx<T> ga[LOG0], gb[LOG0];
-            if constexpr (LOG0 % 2 == 0) {
-#pragma unroll
-                for (int k = 0; k < LOG0; k += 2) {
-                    ld_pair_global(q.ga + b * LOG0 + k, ga[k], ga[k + 1]);
-                    ld_pair_global(q.gb + (lane0 + c) * LOG0 + k, gb[k], gb[k + 1]);
+                for (int j = 0; j < R; ++j) {
+                    const cx<T> x = st[(t + TX * u + NR * j) * CT + c];
+                    v[u * R + j] = INV ? cswap(x) : x;
                 }
-            } else {
+            if constexpr (INPLACE) consumer_barrier(NC);  // the dense image is read: the padded image may overwrite it
+            else release();                               // the ring slot may be refilled
+        } else {
 #pragma unroll
-                for (int k = 0; k < LOG0; ++k) {
-                    ga[k] = ld_table(q.ga + b * LOG0 + k);
-                    gb[k] = ld_table(q.gb + (lane0 + c) * LOG0 + k);
+            for (int u = 0; u < U; ++u)
+#pragma unroll
+                for (int j = 0; j < R; ++j) v[u * R + j] = sm[(tt + TX * u + NR * j) * PITCH + cc];
+            if constexpr (!(INPLACE && last)) consumer_barrier(NC);  // everybody has read the exchange buffer: it may be overwritten
+        }
+        if constexpr (!last) {
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int b = tt + TX * u, mp = b / P, racc = b % P;
+                cx<T> g[LOG];
+                {
+                    cx<T> ga[LOG], gb[LOG];
+                    const cx<T> *pa = q.ga[ps] + mp * LOG, *pb = q.gb[ps] + (lane0 + cc) * LOG;
+                    if constexpr (LOG % 2 == 0) {
+#pragma unroll
+                        for (int k = 0; k < LOG; k += 2) {
+                            ld_pair_global(pa + k, ga[k], ga[k + 1]);
+                            ld_pair_global(pb + k, gb[k], gb[k + 1]);
+                        }
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < LOG; ++k) { ga[k] = ld_table(pa + k); gb[k] = ld_table(pb + k); }
+                    }
+#pragma unroll
+                    for (int k = 0; k < LOG; ++k) g[k] = cmul(ga[k], gb[k]);
+                }
+                cx<T> w[R];
+#pragma unroll
+                for (int j = 0; j < R; ++j) w[j] = v[u * R + j];
+                Dft<R>::run(w);
+                apply_powers<R>(w, g);
+                const int o = racc + P * R * mp;
+#pragma unroll
+                for (int r = 0; r < R; ++r) sm[(o + P * r) * PITCH + cc] = w[r];
+            }
+            consumer_barrier(NC);
+        } else {
+            cx<T> s[R];
+#pragma unroll
+            for (int r = 0; r < R; r += 2) ld_pair_shared(sb + cc * R + r, s[r], s[r + 1]);
+            if constexpr (INPLACE) release();  // tile and twiddle slice are in registers: the slot may be refilled
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                cx<T> w[R];
+#pragma unroll
+                for (int j = 0; j < R; ++j) w[j] = v[u * R + j];
+                Dft<R>::run(w);
+                const int b = tt + TX * u;  // k1 = b + P * r lives at block k1 / CTB, row k1 % CTB of the tile-major scratch
+                if constexpr (P % CTB == 0) {
+                    cx<T> *dst = scr + (long long)(b >> CTBLOG) * ((long long)CTB * N2C) + (long long)(lane0 + cc) * CTB + (b & (CTB - 1));
+#pragma unroll
+                    for (int r = 0; r < R; ++r) st_plain(dst + (long long)r * (P / CTB) * ((long long)CTB * N2C), cmul(w[r], s[r]));
+                } else {
+                    constexpr int Q = CTB / P;
+                    cx<T> *dst = scr + (long long)(lane0 + cc) * CTB + b;
+#pragma unroll
+                    for (int r = 0; r < R; ++r) st_plain(dst + (long long)(r / Q) * ((long long)CTB * N2C) + P * (r % Q), cmul(w[r], s[r]));
                 }
             }
-#pragma unroll
-            for (int k = 0; k < LOG0; ++k) g[k] = cmul(ga[k], gb[k]);
         }
-        cx<T> w[R0];
-#pragma unroll
-        for (int j = 0; j < R0; ++j) w[j] = v[u * R0 + j];
-        Dft<R0>::run(w);
-        apply_powers<R0>(w, g);
-#pragma unroll
-        for (int r = 0; r < R0; ++r) sm[(R0 * b + r) * PITCH + c] = w[r];
-    }
-    consumer_barrier(NC);
-    // last pass with the threads transposed (lanes along k1): the scratch is written in runs of consecutive k1
-    const int t2 = tid % TX, c2 = tid / TX;
-#pragma unroll
-    for (int u = 0; u < U1; ++u)
-#pragma unroll
-        for (int j = 0; j < R1; ++j) v[u * R1 + j] = sm[(t2 + TX * u + NR1 * j) * PITCH + c2];
-    consumer_barrier(NC);
-    cx<T> s[R1];
-#pragma unroll
-    for (int r = 0; r < R1; r += 2) ld_pair_shared(sb + c2 * R1 + r, s[r], s[r + 1]);
-#pragma unroll
-    for (int u = 0; u < U1; ++u) {
-        cx<T> w[R1];
-#pragma unroll
-        for (int j = 0; j < R1; ++j) w[j] = v[u * R1 + j];
-        Dft<R1>::run(w);
-        const int r0 = t2 + TX * u;  // k1 = r0 + R0 * r lives at block k1 / CTB, row k1 % CTB of the tile-major scratch
-        if constexpr (R0 % CTB == 0) {
-            cx<T> *dst = scr + (long long)(r0 >> CTBLOG) * ((long long)CTB * N2C) + (long long)(lane0 + c2) * CTB + (r0 & (CTB - 1));
-#pragma unroll
-            for (int r = 0; r < R1; ++r) st_plain(dst + (long long)r * (R0 / CTB) * ((long long)CTB * N2C), cmul(w[r], s[r]));
-        } else {
-            constexpr int Q = CTB / R0;
-            cx<T> *dst = scr + (long long)(lane0 + c2) * CTB + r0;
-#pragma unroll
-            for (int r = 0; r < R1; ++r) st_plain(dst + (long long)(r / Q) * ((long long)CTB * N2C) + R0 * (r % Q), cmul(w[r], s[r]));
-        }
-    }
+    });
 }
 
 // ---- row tile: CT adjacent rows k1 (one contiguous tile-major scratch block), length-L FFT each, stored transposed
-template <typename Cfg, int INV, int N1C, typename T, typename Release>
+template <typename Cfg, int INV, int N1C, bool INPLACE, bool TWSH, typename T, typename Release>
 __device__ __forceinline__ void flat_stage_b(const cx<T> *twb, const cx<T> *st, cx<T> *sm, cx<T> *uout, int lane0, int tid,
                                              Release release) {
-    constexpr int L = Cfg::L, TX = Cfg::TX, CT = Cfg::CT, E = Cfg::E, PITCH = Cfg::PITCH, NC = Cfg::THREADS;
-    constexpr int R0 = Cfg::radix(0), R1 = Cfg::radix(1);
-    static_assert(Cfg::NP == 2, "two-pass tiles");
-    constexpr int U0 = E / R0, NR0 = L / R0, U1 = E / R1, NR1 = L / R1;
-    static_assert(NR1 == R0, "radix layout");
+    constexpr int L = Cfg::L, TX = Cfg::TX, CT = Cfg::CT, E = Cfg::E, PITCH = Cfg::PITCH, NC = Cfg::THREADS, NP = Cfg::NP;
+    static_assert(NP == 2 || NP == 3, "two or three passes per tile");
     const int c = tid % CT, t = tid / CT;
     cx<T> v[E];
+    sfor<0, NP>([&](auto pc) {
+        constexpr int ps = decltype(pc)::value;
+        constexpr int R = Cfg::radix(ps), P = Cfg::prod(ps), NR = L / R, U = E / R, MN = Cfg::mnext(ps);
+        constexpr bool first = ps == 0, last = ps == NP - 1;
+        if constexpr (first) {
 #pragma unroll
-    for (int u = 0; u < U0; ++u)
+            for (int u = 0; u < U; ++u)
 #pragma unroll
-        for (int j = 0; j < R0; ++j) v[u * R0 + j] = st[(t + TX * u + NR0 * j) * CT + c];
-    release();
+                for (int j = 0; j < R; ++j) v[u * R + j] = st[(t + TX * u + NR * j) * CT + c];
+            if constexpr (INPLACE) consumer_barrier(NC);
+            else release();
+        } else {
 #pragma unroll
-    for (int u = 0; u < U0; ++u) {
-        const int b = t + TX * u;
-        cx<T> w[R0];
+            for (int u = 0; u < U; ++u)
 #pragma unroll
-        for (int j = 0; j < R0; ++j) w[j] = v[u * R0 + j];
-        Dft<R0>::run(w);
+                for (int j = 0; j < R; ++j) v[u * R + j] = sm[(t + TX * u + NR * j) * PITCH + c];
+            if constexpr (INPLACE && last) release();
+            else consumer_barrier(NC);
+        }
 #pragma unroll
-        for (int r = 1; r < R0; ++r) w[r] = cmul(w[r], twb[(r - 1) * NR0 + b]);
+        for (int u = 0; u < U; ++u) {
+            const int b = t + TX * u, mp = b / P, racc = b % P;
+            cx<T> w[R];
 #pragma unroll
-        for (int r = 0; r < R0; ++r) sm[(R0 * b + r) * PITCH + c] = w[r];
-    }
-    consumer_barrier(NC);
+            for (int j = 0; j < R; ++j) w[j] = v[u * R + j];
+            Dft<R>::run(w);
+            if constexpr (!last) {
+                const cx<T> *twp = twb + Cfg::tw_off(ps) + mp;
 #pragma unroll
-    for (int u = 0; u < U1; ++u)
+                for (int r = 1; r < R; ++r) w[r] = cmul(w[r], TWSH ? twp[(r - 1) * MN] : ld_table(twp + (r - 1) * MN));
+                const int o = racc + P * R * mp;
 #pragma unroll
-        for (int j = 0; j < R1; ++j) v[u * R1 + j] = sm[(t + TX * u + NR1 * j) * PITCH + c];
-    consumer_barrier(NC);
+                for (int r = 0; r < R; ++r) sm[(o + P * r) * PITCH + c] = w[r];
+            } else {
+                cx<T> *dst = uout + (lane0 + c) + (long long)N1C * b;  // k2 = b + P * r
 #pragma unroll
-    for (int u = 0; u < U1; ++u) {
-        cx<T> w[R1];
-#pragma unroll
-        for (int j = 0; j < R1; ++j) w[j] = v[u * R1 + j];
-        Dft<R1>::run(w);
-        cx<T> *dst = uout + (lane0 + c) + (long long)N1C * (t + TX * u);
-#pragma unroll
-        for (int r = 0; r < R1; ++r) st_stream(dst + (long long)N1C * R0 * r, INV ? cswap(w[r]) : w[r]);
-    }
+                for (int r = 0; r < R; ++r) st_stream(dst + (long long)N1C * P * r, INV ? cswap(w[r]) : w[r]);
+            }
+        }
+        if constexpr (!last) consumer_barrier(NC);
+    });
 }
 
 // KIND 0: C2C.  (real flavours stay on the cluster kernel of tiled.cuh for now)
-template <typename CfgA, typename CfgB, int INV, int NSTAGE, int MINB>
+template <typename CfgA, typename CfgB, int INV, int NSTAGE, int MINB, bool INPLACE>
 __global__ void __launch_bounds__(CfgA::THREADS + 32, MINB)
 fourstep_flat_kernel(FlatParams<typename CfgA::T> q, const __grid_constant__ CUtensorMap tmap) {
     using T = typename CfgA::T;
-    using Lay = FlatLayout<CfgA, CfgB, NSTAGE>;
+    using Lay = FlatLayout<CfgA, CfgB, NSTAGE, INPLACE>;
     static_assert(CfgA::THREADS == CfgB::THREADS, "both stages must use the same CTA size");
     constexpr int NC = CfgA::THREADS;
     constexpr int N1 = CfgA::L, N2 = CfgB::L;
@@ -304,7 +330,8 @@ fourstep_flat_kernel(FlatParams<typename CfgA::T> q, const __grid_constant__ CUt
     constexpr int NDONE = NSTAGE + 1;
     SSFFT_DYNAMIC_SMEM(ssfft_smem);
     cx<T> *exch = reinterpret_cast<cx<T> *>(ssfft_smem + Lay::oExch);
-    cx<T> *twb = reinterpret_cast<cx<T> *>(ssfft_smem + Lay::oTwB);
+    cx<T> *twb_sm = reinterpret_cast<cx<T> *>(ssfft_smem + Lay::oTwB);
+    const cx<T> *twb = Lay::kTwBShared ? twb_sm : q.tw_b;
     FlatDesc *desc = reinterpret_cast<FlatDesc *>(ssfft_smem + Lay::oDesc);  // [NSTAGE] ring, then [NDONE] producer history
     unsigned long long *full = reinterpret_cast<unsigned long long *>(ssfft_smem + Lay::oBars);
     unsigned long long *empty = full + NSTAGE, *done = empty + NSTAGE;
@@ -313,7 +340,8 @@ fourstep_flat_kernel(FlatParams<typename CfgA::T> q, const __grid_constant__ CUt
         for (int s = 0; s < NSTAGE; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], NC); }
         for (int s = 0; s < NDONE; ++s) mbar_init(&done[s], NC);
     }
-    for (int i = tid; i < CfgB::tw_total; i += NC + 32) twb[i] = ld_table(q.tw_b + i);
+    if constexpr (Lay::kTwBShared)
+        for (int i = tid; i < CfgB::tw_total; i += NC + 32) twb_sm[i] = ld_table(q.tw_b + i);
     __syncthreads();
 
     if (tid >= NC) {
@@ -323,7 +351,7 @@ fourstep_flat_kernel(FlatParams<typename CfgA::T> q, const __grid_constant__ CUt
         unsigned *cnt1 = q.ctrl + 32, *cnt2 = cnt1 + q.cap;
         const long long total = (q.batch + q.delay) * PT;
         long long issued = 0, signaled = 0;
-        bool have = false, exhausted = false;
+        bool have = false, exhausted = false, ready = false;
         FlatDesc cur{2, 0, 0};
         long long t_idle = clock64();  // bounded waits: a scheduling surprise becomes a launch error, never a hung GPU
         for (;;) {
@@ -339,12 +367,20 @@ fourstep_flat_kernel(FlatParams<typename CfgA::T> q, const __grid_constant__ CUt
                     moved = true;
                 }
             }
-            if (!have && !exhausted) {
+            // a ticket is taken as late as the ring allows (ring of one: right away, its copy must start the moment the
+            // slot frees; deeper rings: when a slot is free) -- tickets held idle widen the window of transforms in flight
+            // and with it the scratch the schedule needs
+            bool want = !have && !exhausted;
+            if (want && NSTAGE > 1)
+                want = issued - signaled <= NSTAGE &&
+                       (issued < NSTAGE || mbar_test(&empty[issued % NSTAGE], (unsigned)(((issued / NSTAGE) - 1) & 1)));
+            if (want) {
                 const long long tk = (long long)atomicAdd(q.ctrl, 1u);
+                ready = false;
                 if (tk >= total) {
                     exhausted = true;
                     cur.kind = 2;
-                    have = true;
+                    have = ready = true;
                 } else {
                     const long long ph = tk / PT;
                     const int r = (int)(tk - ph * PT);
@@ -354,7 +390,12 @@ fourstep_flat_kernel(FlatParams<typename CfgA::T> q, const __grid_constant__ CUt
                 }
                 moved = true;
             }
-            if (have && issued - signaled <= NSTAGE) {
+            if (have && !ready) {  // dependencies are polled while the ring slot is still busy: the copy starts the moment it frees
+                if (cur.kind == 0) ready = cur.b < q.nslots || ld_acquire_gpu(&cnt2[cur.b - q.nslots]) >= (unsigned)tiles2;
+                else ready = ld_acquire_gpu(&cnt1[cur.b]) >= (unsigned)tiles1;
+                if (ready) moved = true;
+            }
+            if (have && ready && issued - signaled <= NSTAGE) {
                 const int s = (int)(issued % NSTAGE);
                 const bool slot_free = issued < NSTAGE || mbar_test(&empty[s], (unsigned)(((issued / NSTAGE) - 1) & 1));
                 if (slot_free) {
@@ -363,23 +404,21 @@ fourstep_flat_kernel(FlatParams<typename CfgA::T> q, const __grid_constant__ CUt
                         mbar_arrive(&full[s]);
                         break;
                     }
-                    bool ready;
-                    if (cur.kind == 0) ready = cur.b < q.nslots || ld_acquire_gpu(&cnt2[cur.b - q.nslots]) >= (unsigned)tiles2;
-                    else ready = ld_acquire_gpu(&cnt1[cur.b]) >= (unsigned)tiles1;
-                    if (ready) {
+                    {
                         desc[s] = cur;
                         hist[issued % NDONE] = cur;
                         cx<T> *slot = reinterpret_cast<cx<T> *>(ssfft_smem + Lay::oSlots + (size_t)s * Lay::kSlot);
                         if (cur.kind == 0) {
-                            cx<T> *sblk = reinterpret_cast<cx<T> *>(ssfft_smem + Lay::oSBlk + (size_t)(issued % NDONE) * Lay::kSBlk);
-                            constexpr unsigned sbytes = (unsigned)(CfgA::CT * CfgA::radix(1) * sizeof(cx<T>));
+                            cx<T> *sblk = INPLACE ? reinterpret_cast<cx<T> *>(reinterpret_cast<unsigned char *>(slot) + Lay::kExch)
+                                                  : reinterpret_cast<cx<T> *>(ssfft_smem + Lay::oSBlk + (size_t)(issued % NDONE) * Lay::kSBlk);
+                            constexpr unsigned sbytes = (unsigned)(CfgA::CT * CfgA::radix(CfgA::NP - 1) * sizeof(cx<T>));
                             mbar_expect_tx(&full[s], (unsigned)Lay::kTileA + sbytes);
                             constexpr int kBoxRows = N1 > 256 ? 256 : N1;
 #pragma unroll
                             for (int r0 = 0; r0 < N1; r0 += kBoxRows)
                                 tma_tile_3d<T>(slot + (size_t)r0 * CfgA::CT, &tmap, q.in, N1, N2, kBoxRows, CfgA::CT, cur.tile * CfgA::CT, r0,
                                                cur.b, &full[s]);
-                            bulk_g2s(sblk, q.s4 + (long long)cur.tile * CfgA::CT * CfgA::radix(1), sbytes, &full[s]);
+                            bulk_g2s(sblk, q.s4 + (long long)cur.tile * CfgA::CT * CfgA::radix(CfgA::NP - 1), sbytes, &full[s]);
                         } else {
                             mbar_expect_tx(&full[s], (unsigned)Lay::kTileB);
                             fence_proxy_async();  // other CTAs' generic-proxy scratch stores -> async-proxy read
@@ -424,19 +463,21 @@ fourstep_flat_kernel(FlatParams<typename CfgA::T> q, const __grid_constant__ CUt
         mbar_wait(&full[s], (unsigned)((j / NSTAGE) & 1));
         const FlatDesc d = desc[s];
         if (d.kind == 2) break;
-        const cx<T> *st = reinterpret_cast<const cx<T> *>(ssfft_smem + Lay::oSlots + (size_t)s * Lay::kSlot);
+        cx<T> *st = reinterpret_cast<cx<T> *>(ssfft_smem + Lay::oSlots + (size_t)s * Lay::kSlot);
+        cx<T> *xb = INPLACE ? st : exch;  // exchange buffer of this tile
         auto release = [&]() { mbar_arrive(&empty[s]); };
         cx<T> *scr = q.scratch + (d.b % q.nslots) * q.scratch_per;
         if (d.kind == 0) {
-            const cx<T> *sblk = reinterpret_cast<const cx<T> *>(ssfft_smem + Lay::oSBlk + (size_t)(j % NDONE) * Lay::kSBlk);
-            flat_stage_a<CfgA, INV, N2, kCtbLog>(q, st, sblk, exch, scr, d.tile * CfgA::CT, tid, release);
+            const cx<T> *sblk = INPLACE ? reinterpret_cast<const cx<T> *>(reinterpret_cast<const unsigned char *>(st) + Lay::kExch)
+                                        : reinterpret_cast<const cx<T> *>(ssfft_smem + Lay::oSBlk + (size_t)(j % NDONE) * Lay::kSBlk);
+            flat_stage_a<CfgA, INV, N2, kCtbLog, INPLACE>(q, st, sblk, xb, scr, d.tile * CfgA::CT, tid, release);
         } else {
             if (q.discard) {  // the block is in shared memory now: drop its lines from L2 without a write-back
                 constexpr int kLines = (int)(Lay::kTileB / 128);
                 const char *blk = reinterpret_cast<const char *>(scr + (long long)d.tile * CfgB::CT * N2);
                 for (int i = tid; i < kLines; i += NC) discard_l2_line(blk + (size_t)i * 128);
             }
-            flat_stage_b<CfgB, INV, N1>(twb, st, exch, q.out + d.b * q.user_stride, d.tile * CfgB::CT, tid, release);
+            flat_stage_b<CfgB, INV, N1, INPLACE, Lay::kTwBShared>(twb, st, xb, q.out + d.b * q.user_stride, d.tile * CfgB::CT, tid, release);
         }
         mbar_arrive(&done[j % NDONE]);
     }
@@ -450,8 +491,8 @@ fourstep_flat_kernel(FlatParams<typename CfgA::T> q, const __grid_constant__ CUt
 struct FlatEntry {
     int prec, n1, n2;
     const char *name;
-    int ra0, ra1, cta, ctb;  // column-stage radices / lanes, row-stage lanes
-    int threads, nstage, minb;
+    int ra[3], na_passes, cta, ctb;  // column-stage radices / lanes, row-stage lanes
+    int threads, nstage, minb, inplace;
     size_t smem_bytes;
     int tile_b_tw;  // entries of the row-stage pass table
     int rb[3], nb_passes;
@@ -460,18 +501,18 @@ struct FlatEntry {
 };
 const std::vector<FlatEntry> &flat_registry();
 
-// first registered entry of the size, or the variant named by SSFFT_FLAT_VARIANT="ring,ctas_per_sm"
+// first registered entry of the size, or the variant named by SSFFT_FLAT_VARIANT="ring,ctas_per_sm[,inplace]"
 template <typename T>
 inline int find_flat(size_t n1, size_t n2) {
     const int prec = sizeof(T) == 4 ? 0 : 1;
     const auto &reg = flat_registry();
-    int want_ring = 0, want_minb = 0;
-    if (const char *e = getenv("SSFFT_FLAT_VARIANT")) sscanf(e, "%d,%d", &want_ring, &want_minb);
+    int want_ring = 0, want_minb = 0, want_inplace = 1;
+    if (const char *e = getenv("SSFFT_FLAT_VARIANT")) sscanf(e, "%d,%d,%d", &want_ring, &want_minb, &want_inplace);
     int first = -1;
     for (size_t i = 0; i < reg.size(); ++i)
         if (reg[i].prec == prec && (size_t)reg[i].n1 == n1 && (size_t)reg[i].n2 == n2) {
             if (first < 0) first = (int)i;
-            if (reg[i].nstage == want_ring && reg[i].minb == want_minb) return (int)i;
+            if (reg[i].nstage == want_ring && reg[i].minb == want_minb && reg[i].inplace == want_inplace) return (int)i;
         }
     return first;
 }
@@ -483,20 +524,30 @@ inline void flat_root(T *dst, unsigned long long num, unsigned long long den) {
     dst[0] = (T)cosl(a);
     dst[1] = (T)(-sinl(a));
 }
-// ga[b][k] = W_N1^(b * 2^k), gb[n2][k] = W_N^(n2 * 2^k), s4[n2][r] = W_N^(n2 * R0 * r)   (interleaved re, im)
+// Tables of the column stage (interleaved re, im), radices ra[0 .. passes-1] of the length-n1 transform:
+//   per non-last pass p (P = product of the earlier radices, R = ra[p], LOG = log2 R):
+//     ga[p][m'][k] = W_(n1/P)^(m' * 2^k), m' < n1 / (P R);      gb[p][c][k] = W_(n/P)^(c * 2^k), c < n2
+//   s4[c][r] = W_n^(c * P_last * r), r < R_last
 template <typename T>
-inline void fill_flat_tables(std::vector<T> &ga, std::vector<T> &gb, std::vector<T> &s4, size_t n1, size_t n2, int r0, int r1) {
+inline void fill_flat_tables(std::vector<T> (&ga)[2], std::vector<T> (&gb)[2], std::vector<T> &s4, size_t n1, size_t n2, const int *ra,
+                             int passes) {
     const size_t n = n1 * n2;
-    const int lg = flat_ilog2(r0);
-    ga.assign(2 * (n1 / r0) * lg, (T)0);
-    gb.assign(2 * n2 * lg, (T)0);
-    s4.assign(2 * n2 * r1, (T)0);
-    for (size_t b = 0; b < n1 / r0; ++b)
-        for (int k = 0; k < lg; ++k) flat_root<T>(&ga[2 * (b * lg + k)], (unsigned long long)b << k, n1);
-    for (size_t c = 0; c < n2; ++c) {
-        for (int k = 0; k < lg; ++k) flat_root<T>(&gb[2 * (c * lg + k)], (unsigned long long)c << k, n);
-        for (int r = 0; r < r1; ++r) flat_root<T>(&s4[2 * (c * r1 + r)], (unsigned long long)c * r0 * r, n);
+    size_t P = 1;
+    for (int p = 0; p + 1 < passes; ++p) {
+        const int R = ra[p], lg = flat_ilog2(R);
+        const size_t mcount = n1 / (P * R);
+        ga[p].assign(2 * mcount * lg, (T)0);
+        gb[p].assign(2 * n2 * lg, (T)0);
+        for (size_t m = 0; m < mcount; ++m)
+            for (int k = 0; k < lg; ++k) flat_root<T>(&ga[p][2 * (m * lg + k)], (unsigned long long)m << k, n1 / P);
+        for (size_t c = 0; c < n2; ++c)
+            for (int k = 0; k < lg; ++k) flat_root<T>(&gb[p][2 * (c * lg + k)], (unsigned long long)c << k, n / P);
+        P *= R;
     }
+    const int RL = ra[passes - 1];
+    s4.assign(2 * n2 * RL, (T)0);
+    for (size_t c = 0; c < n2; ++c)
+        for (int r = 0; r < RL; ++r) flat_root<T>(&s4[2 * (c * RL + r)], (unsigned long long)c * P * r, n);
 }
 // row-stage pass table, same layout as build_tile_twiddles ([r-1][m'] per pass)
 template <typename T>

@@ -8,10 +8,10 @@
 
 namespace ssfft {
 
-template <typename CfgA, typename CfgB, int INV, int NSTAGE, int MINB>
+template <typename CfgA, typename CfgB, int INV, int NSTAGE, int MINB, bool INPLACE>
 int flat_max_ctas() {
-    using Lay = FlatLayout<CfgA, CfgB, NSTAGE>;
-    auto kern = fourstep_flat_kernel<CfgA, CfgB, INV, NSTAGE, MINB>;
+    using Lay = FlatLayout<CfgA, CfgB, NSTAGE, INPLACE>;
+    auto kern = fourstep_flat_kernel<CfgA, CfgB, INV, NSTAGE, MINB, INPLACE>;
     static int cached[32] = {0};
     static std::mutex m;
     int dev = 0;
@@ -33,37 +33,38 @@ int flat_max_ctas() {
 }
 
 // returns 0 on success, 2 on a launch error, 3 when the input cannot be described by a tensor map (caller falls back)
-template <typename CfgA, typename CfgB, int INV, int NSTAGE, int MINB>
+template <typename CfgA, typename CfgB, int INV, int NSTAGE, int MINB, bool INPLACE>
 int launch_flat(const void *params, int ctas, cudaStream_t s) {
     using T = typename CfgA::T;
-    using Lay = FlatLayout<CfgA, CfgB, NSTAGE>;
+    using Lay = FlatLayout<CfgA, CfgB, NSTAGE, INPLACE>;
     const FlatParams<T> &q = *reinterpret_cast<const FlatParams<T> *>(params);
     if (q.batch <= 0) return 0;
-    if (flat_max_ctas<CfgA, CfgB, INV, NSTAGE, MINB>() < 1) return 2;  // also sets the shared-memory attribute
+    if (flat_max_ctas<CfgA, CfgB, INV, NSTAGE, MINB, INPLACE>() < 1) return 2;  // also sets the shared-memory attribute
     CUtensorMap tmap;
     memset(&tmap, 0, sizeof(tmap));
     constexpr int kBoxRows = CfgA::L > 256 ? 256 : CfgA::L;
     if (!encode_tensor_map_3d(&tmap, q.in, q.batch, CfgA::L, CfgB::L, kBoxRows, CfgA::CT)) return 3;
-    fourstep_flat_kernel<CfgA, CfgB, INV, NSTAGE, MINB><<<(unsigned)ctas, CfgA::THREADS + 32, Lay::smem_bytes, s>>>(q, tmap);
+    fourstep_flat_kernel<CfgA, CfgB, INV, NSTAGE, MINB, INPLACE><<<(unsigned)ctas, CfgA::THREADS + 32, Lay::smem_bytes, s>>>(q, tmap);
     return cudaGetLastError() == cudaSuccess ? 0 : 2;
 }
 
-template <typename CfgA, typename CfgB, int NSTAGE, int MINB>
+template <typename CfgA, typename CfgB, int NSTAGE, int MINB, bool INPLACE = true>
 FlatEntry make_flat_entry(const char *name) {
-    using Lay = FlatLayout<CfgA, CfgB, NSTAGE>;
+    using Lay = FlatLayout<CfgA, CfgB, NSTAGE, INPLACE>;
     FlatEntry e;
     e.prec = sizeof(typename CfgA::T) == 4 ? 0 : 1;
     e.n1 = CfgA::L; e.n2 = CfgB::L; e.name = name;
-    e.ra0 = CfgA::radix(0); e.ra1 = CfgA::radix(1); e.cta = CfgA::CT; e.ctb = CfgB::CT;
-    e.threads = CfgA::THREADS + 32; e.nstage = NSTAGE; e.minb = MINB;
+    for (int i = 0; i < 3; ++i) e.ra[i] = CfgA::radix(i);
+    e.na_passes = CfgA::NP; e.cta = CfgA::CT; e.ctb = CfgB::CT;
+    e.threads = CfgA::THREADS + 32; e.nstage = NSTAGE; e.minb = MINB; e.inplace = INPLACE ? 1 : 0;
     e.smem_bytes = Lay::smem_bytes;
     e.tile_b_tw = CfgB::tw_total;
     e.nb_passes = CfgB::NP;
     for (int i = 0; i < 3; ++i) e.rb[i] = CfgB::radix(i);
-    e.launch[0] = &launch_flat<CfgA, CfgB, 0, NSTAGE, MINB>;
-    e.launch[1] = &launch_flat<CfgA, CfgB, 1, NSTAGE, MINB>;
-    e.max_ctas[0] = &flat_max_ctas<CfgA, CfgB, 0, NSTAGE, MINB>;
-    e.max_ctas[1] = &flat_max_ctas<CfgA, CfgB, 1, NSTAGE, MINB>;
+    e.launch[0] = &launch_flat<CfgA, CfgB, 0, NSTAGE, MINB, INPLACE>;
+    e.launch[1] = &launch_flat<CfgA, CfgB, 1, NSTAGE, MINB, INPLACE>;
+    e.max_ctas[0] = &flat_max_ctas<CfgA, CfgB, 0, NSTAGE, MINB, INPLACE>;
+    e.max_ctas[1] = &flat_max_ctas<CfgA, CfgB, 1, NSTAGE, MINB, INPLACE>;
     return e;
 }
 

@@ -83,6 +83,8 @@ int fourstep_cluster_size() {
 
 void register_flat_f32_a(std::vector<FlatEntry> &);
 void register_flat_f32_b(std::vector<FlatEntry> &);
+void register_flat_f32_c(std::vector<FlatEntry> &);
+void register_flat_f32_d(std::vector<FlatEntry> &);
 
 const std::vector<FlatEntry> &flat_registry() {
     static const std::vector<FlatEntry> reg = [] {
@@ -92,6 +94,8 @@ const std::vector<FlatEntry> &flat_registry() {
         if ((off && off[0] == '1') || (off2 && off2[0] == '1')) return v;
         register_flat_f32_a(v);
         register_flat_f32_b(v);
+        register_flat_f32_c(v);
+        register_flat_f32_d(v);
         return v;
     }();
     return reg;

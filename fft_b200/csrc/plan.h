@@ -62,7 +62,7 @@ struct ssfft_plan {
     int flat_id = -1;
     int flat_ctas = 0;                     // co-resident CTAs of the persistent launch
     int flat_slots = 0;                    // scratch slots (transforms) allocated
-    void *d_flat_ga = nullptr, *d_flat_gb = nullptr, *d_flat_s4 = nullptr, *d_flat_twb = nullptr;
+    void *d_flat_ga[2] = {nullptr, nullptr}, *d_flat_gb[2] = {nullptr, nullptr}, *d_flat_s4 = nullptr, *d_flat_twb = nullptr;
     void *d_flat_scratch = nullptr, *d_flat_ctrl = nullptr;
     long long flat_cap = 0;                // transforms per launch the dependency counters cover
 

@@ -259,9 +259,20 @@ int exec_tiled(ssfft_plan *pl, int kind, const void *in, void *out, long long ba
 
 // Ticket-queue four-step (flat.cuh), complex transforms: tables, scratch slots and dependency counters.  *ok = false
 // leaves the plan on its other paths (which stay set up as the fallback for inputs a tensor map cannot describe).
-int flat_span(int ctas, int tickets_per_phase) {  // phases that are in flight at once, with head-room
-    const int v = (3 * ctas + 2 * tickets_per_phase - 1) / (2 * tickets_per_phase);
-    return v < 1 ? 1 : v;
+// Schedule of a launch: `span` = phases (transforms) whose tickets are held by the CTAs at any time, `delay` = phases
+// between the column tiles of a transform and its row tiles, `slots` = scratch slots; delay + 1 <= slots is what
+// correctness needs, the head-room is what keeps the dependency waits free.
+struct FlatSchedule { int span, delay, slots; };
+FlatSchedule flat_schedule(int ctas, int ring, int tickets_per_phase) {
+    const long long window = (long long)ctas * (ring == 1 ? 3 : ring);  // executing + loading (+ in hand)
+    FlatSchedule f;
+    f.span = (int)((window + tickets_per_phase - 1) / tickets_per_phase);
+    if (f.span < 1) f.span = 1;
+    f.delay = (3 * f.span + 1) / 2;
+    const int pct = env_int("SSFFT_FLAT_DELAY_PCT", 100);  // A/B measurements of the schedule
+    if (pct > 0 && pct != 100) f.delay = (int)((long long)f.delay * pct / 100);
+    f.slots = f.delay + f.span + 2;
+    return f;
 }
 template <typename T>
 int setup_flat(ssfft_plan *pl, bool *ok) {
@@ -279,8 +290,8 @@ int setup_flat(ssfft_plan *pl, bool *ok) {
     const int ctas_inv = e.max_ctas[1]();
     if (ctas_inv < ctas) ctas = ctas_inv;
     if (ctas < 1) return SSFFT_OK;
-    std::vector<T> ga, gb, s4, twb;
-    fill_flat_tables<T>(ga, gb, s4, n1, n2, e.ra0, e.ra1);
+    std::vector<T> ga[2], gb[2], s4, twb;
+    fill_flat_tables<T>(ga, gb, s4, n1, n2, e.ra, e.na_passes);
     fill_flat_row_twiddles<T>(twb, e.n2, e.rb, e.nb_passes, e.tile_b_tw);
     auto up = [&](void **d, const std::vector<T> &h) -> int {
         CU(cudaMalloc(d, h.size() * sizeof(T)));
@@ -288,10 +299,11 @@ int setup_flat(ssfft_plan *pl, bool *ok) {
         return SSFFT_OK;
     };
     int rc;
-    if ((rc = up(&pl->d_flat_ga, ga)) || (rc = up(&pl->d_flat_gb, gb)) || (rc = up(&pl->d_flat_s4, s4)) || (rc = up(&pl->d_flat_twb, twb)))
-        return rc;
+    for (int p = 0; p + 1 < e.na_passes; ++p)
+        if ((rc = up(&pl->d_flat_ga[p], ga[p])) || (rc = up(&pl->d_flat_gb[p], gb[p]))) return rc;
+    if ((rc = up(&pl->d_flat_s4, s4)) || (rc = up(&pl->d_flat_twb, twb))) return rc;
     const int pt = (int)(n2 / e.cta + n1 / e.ctb);
-    int slots = 2 * flat_span(ctas, pt) + 1;
+    int slots = flat_schedule(ctas, e.nstage, pt).slots;
     if (env_int("SSFFT_FLAT_SLOTS", 0) > slots) slots = env_int("SSFFT_FLAT_SLOTS", 0);
     CU(cudaMalloc(&pl->d_flat_scratch, (size_t)slots * n * sizeof(cx<T>)));
     pl->flat_cap = 1 << 16;
@@ -313,16 +325,17 @@ int exec_flat(ssfft_plan *pl, const void *in, void *out, long long batch, int in
         const long long nb = batch - b0 < pl->flat_cap ? batch - b0 : pl->flat_cap;
         long long ctas = nb * (tiles1 > tiles2 ? tiles1 : tiles2);
         if (ctas > pl->flat_ctas) ctas = pl->flat_ctas;
-        const int span = flat_span((int)ctas, pt);
-        long long delay = env_int("SSFFT_FLAT_DELAY", -1) >= 0 ? env_int("SSFFT_FLAT_DELAY", -1) : span;
+        const FlatSchedule fs = flat_schedule((int)ctas, e.nstage, pt);
+        long long delay = env_int("SSFFT_FLAT_DELAY", -1) >= 0 ? env_int("SSFFT_FLAT_DELAY", -1) : fs.delay;
         if (delay > nb) delay = nb;
         if (delay > pl->flat_slots - 1) delay = pl->flat_slots - 1;
-        long long slots = env_int("SSFFT_FLAT_SLOTS", 0) > 0 ? env_int("SSFFT_FLAT_SLOTS", 0) : delay + span + 1;
+        long long slots = env_int("SSFFT_FLAT_SLOTS", 0) > 0 ? env_int("SSFFT_FLAT_SLOTS", 0) : delay + fs.span + 2;
         if (slots > pl->flat_slots) slots = pl->flat_slots;
         if (slots < delay + 1) slots = delay + 1;
         FlatParams<T> q;
         q.in = (const cx<T> *)in + b0 * n; q.out = (cx<T> *)out + b0 * n; q.scratch = (cx<T> *)pl->d_flat_scratch;
-        q.tw_b = (const cx<T> *)pl->d_flat_twb; q.ga = (const cx<T> *)pl->d_flat_ga; q.gb = (const cx<T> *)pl->d_flat_gb;
+        q.tw_b = (const cx<T> *)pl->d_flat_twb;
+        for (int p = 0; p < 2; ++p) { q.ga[p] = (const cx<T> *)pl->d_flat_ga[p]; q.gb[p] = (const cx<T> *)pl->d_flat_gb[p]; }
         q.s4 = (const cx<T> *)pl->d_flat_s4; q.ctrl = (unsigned *)pl->d_flat_ctrl;
         q.batch = nb; q.user_stride = n; q.scratch_per = n; q.cap = nb;
         q.nslots = (int)slots; q.delay = (int)delay; q.discard = env_int("SSFFT_DISCARD", 1);
@@ -455,8 +468,8 @@ int build_plan_typed(ssfft_plan *pl) {
     if (flat_ok) {
         const FlatEntry &e = flat_registry()[pl->flat_id];
         snprintf(buf, sizeof(buf), "complex N=%zu ticket-queue four-step n1=%d x n2=%d (%s): one persistent launch of %d CTAs "
-                 "(%d consumer threads + a TMA producer warp each, ring of %d), %d scratch slots = %.1f MiB in L2", n, e.n1, e.n2,
-                 e.name, pl->flat_ctas, e.threads - 32, e.nstage, pl->flat_slots, pl->flat_slots * (double)n * sizeof(cx<T>) / 1048576.0);
+                 "(%d consumer threads + a TMA producer warp each, ring of %d%s), %d scratch slots = %.1f MiB in L2", n, e.n1, e.n2,
+                 e.name, pl->flat_ctas, e.threads - 32, e.nstage, e.inplace ? " in place" : "", pl->flat_slots, pl->flat_slots * (double)n * sizeof(cx<T>) / 1048576.0);
         pl->desc = buf;
     } else if (clustered_ok) {
         const int k = pl->kind == SSFFT_C2C ? 0 : 1;
@@ -769,7 +782,7 @@ int ssfft_plan_destroy(ssfft_plan *pl) {
     free_stage(pl->direct); free_stage(pl->col); free_stage(pl->row);
     void *ptrs[] = {pl->fused.d_twiddles, pl->fused_col.d_twiddles, pl->fused_row.d_twiddles, pl->d_ep_lo, pl->d_ep_hi,
                     pl->d_scratch, pl->d_rtw, pl->d_rot, pl->d_stage_in, pl->d_stage_out, pl->d_tile_tw_a, pl->d_tile_tw_b,
-                    pl->d_tw4, pl->d_fs_ctr, pl->d_ex_in, pl->d_ex_out, pl->d_flat_ga, pl->d_flat_gb, pl->d_flat_s4,
+                    pl->d_tw4, pl->d_fs_ctr, pl->d_ex_in, pl->d_ex_out, pl->d_flat_ga[0], pl->d_flat_ga[1], pl->d_flat_gb[0], pl->d_flat_gb[1], pl->d_flat_s4,
                     pl->d_flat_twb, pl->d_flat_scratch, pl->d_flat_ctrl};
     for (void *p : ptrs)
         if (p) cudaFree(p);

@@ -19,7 +19,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CSRC = os.path.join(ROOT, "fft_b200", "csrc")
 HOST = os.path.join(ROOT, "tests", "host")
 
-_PAIR = re.compile(r'make_flat_entry<TileCfg<([^>]*)>,\s*TileCfg<([^>]*)>,\s*(\d+),\s*(\d+)>\("([^"]*)"\)')
+_PAIR = re.compile(r'make_flat_entry<TileCfg<([^>]*)>,\s*TileCfg<([^>]*)>,\s*(\d+),\s*(\d+)(?:,\s*\w+)?>\("([^"]*)"\)')
 
 
 def registered_pairs():
@@ -65,4 +65,4 @@ def test_every_flat_kernel_runs_on_cpu(tmp_path, oracle):
     for res in results:
         assert res.returncode == 0 and "FLAT-EMUL-OK" in res.stdout, res.stdout[-4000:] + res.stderr[-2000:]
         runs += int(res.stdout.split(" runs,")[0].split()[-1])
-    assert runs == 16 * len(pairs)  # 2 ring depths x 4 shapes x forward / inverse
+    assert runs == 40 * len(pairs)  # (ring 1, 2 separate exchange buffer + ring 1, 2, 3 in place) x 4 shapes x forward / inverse

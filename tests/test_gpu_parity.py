@@ -326,13 +326,14 @@ def test_cluster_resident_four_step(oracle, cuda_device):
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     for tma in ("1", "0"):
-        env = dict(os.environ, SSFFT_DSMEM_ALL="1", SSFFT_CLUSTER_TMA=tma)
+        env = dict(os.environ, SSFFT_DSMEM_ALL="1", SSFFT_CLUSTER_TMA=tma, SSFFT_DISABLE_FLAT="1")
         res = subprocess.run([sys.executable, os.path.join(root, "tests", "gpu_cluster_check.py")], cwd=root, env=env,
                              capture_output=True, text=True, timeout=900)
         assert "CLUSTER-GPU-OK" in res.stdout, (tma, res.stdout[-2000:] + res.stderr[-2000:])
-    # default planner choice: complex 32768 runs cluster-resident
+    # default planner choice since round 2: the ticket-queue four-step (flat.cuh); the cluster-resident kernel is the
+    # fallback for inputs a tensor map cannot describe
     f = fft_b200.FFT(32768)
-    assert "cluster-resident" in f.describe(), f.describe()
+    assert "ticket-queue" in f.describe(), f.describe()
 
 
 def test_l2_scratch_four_step_still_matches(oracle, cuda_device):
@@ -342,6 +343,7 @@ def test_l2_scratch_four_step_still_matches(oracle, cuda_device):
     code = r"""
 import os, sys, math
 os.environ["SSFFT_DISABLE_DSMEM"] = "1"
+os.environ["SSFFT_DISABLE_FLAT"] = "1"
 sys.path.insert(0, os.getcwd())
 import numpy as np, torch, fft_b200
 from oracle import oracle as O

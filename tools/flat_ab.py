@@ -52,13 +52,15 @@ def run(n, env):
 def main():
     tag = sys.argv[1] if len(sys.argv) > 1 else "flat"
     sizes = [int(a) for a in sys.argv[2:]] or [32768, 65536]
+    V = "SSFFT_FLAT_VARIANT"
     configs = [("round-1 path", {"SSFFT_DISABLE_FLAT": "1"}),
-               ("flat ring1 3/SM", {"SSFFT_FLAT_VARIANT": "1,3"}),
-               ("flat ring2 2/SM", {"SSFFT_FLAT_VARIANT": "2,2"}),
-               ("flat ring1 3/SM no discard", {"SSFFT_FLAT_VARIANT": "1,3", "SSFFT_DISCARD": "0"}),
-               ("flat ring1 3/SM delay 4", {"SSFFT_FLAT_VARIANT": "1,3", "SSFFT_FLAT_DELAY": "4"}),
-               ("flat ring1 3/SM delay 60 slots 128", {"SSFFT_FLAT_VARIANT": "1,3", "SSFFT_FLAT_DELAY": "60", "SSFFT_FLAT_SLOTS": "128"}),
-               ("flat ring2 2/SM no discard", {"SSFFT_FLAT_VARIANT": "2,2", "SSFFT_DISCARD": "0"})]
+               ("flat ring2 3/SM in place (default)", {}),
+               ("flat ring3 2/SM in place", {V: "3,2,1"}),
+               ("flat ring1 3/SM separate", {V: "1,3,0"}),
+               ("flat ring2 2/SM separate", {V: "2,2,0"}),
+               ("default, no discard", {"SSFFT_DISCARD": "0"}),
+               ("default, half the delay", {"SSFFT_FLAT_DELAY_PCT": "50"}),
+               ("default, twice the delay", {"SSFFT_FLAT_DELAY_PCT": "200"})]
     rows = []
     for n in sizes:
         base = None
