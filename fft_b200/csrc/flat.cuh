@@ -43,7 +43,17 @@ struct FlatParams {
     unsigned *ctrl;         // [0] ticket counter; cnt1 = ctrl + 32; cnt2 = cnt1 + cap
     long long batch, user_stride, scratch_per, cap;
     int nslots, delay, discard;
+    unsigned long long *stats;  // -DSSFFT_FLAT_STATS builds only: kFlatStats counters per CTA (else unused, null)
 };
+constexpr int kFlatStats = 16;
+#ifndef SSFFT_FLAT_STATS
+#define SSFFT_FLAT_STATS 0
+#endif
+// -DSSFFT_FLAT_NOCOMPUTE=1 (measurement build): the consumers skip butterflies and twiddles -- same copies, barriers,
+// dependency traffic and stores, wrong results: what the schedule and the memory system can do without the arithmetic
+#ifndef SSFFT_FLAT_NOCOMPUTE
+#define SSFFT_FLAT_NOCOMPUTE 0
+#endif
 
 __host__ __device__ constexpr int flat_ilog2(int v) { return v <= 1 ? 0 : 1 + flat_ilog2(v / 2); }
 __host__ __device__ constexpr int flat_topbit(int v) { return 1 << flat_ilog2(v); }
@@ -66,7 +76,7 @@ struct FlatLayout {
     static constexpr size_t kTwB = kTwBShared ? al((size_t)(CfgB::tw_total > 0 ? CfgB::tw_total : 1) * sizeof(cx<T>)) : 0;
     static constexpr size_t oExch = 0, oSlots = oExch + (INPLACE ? 0 : kExch), oSBlk = oSlots + NSTAGE * kSlot,
                             oTwB = oSBlk + (INPLACE ? 0 : (NSTAGE + 1) * kSBlk), oDesc = oTwB + kTwB,
-                            oBars = oDesc + al((size_t)(2 * NSTAGE + 1) * 16);
+                            oBars = oDesc + al((size_t)(2 * NSTAGE + 1) * 32);
     static constexpr size_t smem_bytes = oBars + al((size_t)(3 * NSTAGE + 1) * 8);
 };
 
@@ -74,7 +84,9 @@ struct FlatDesc {  // what the producer tells the consumers about a ring slot (a
     int kind;      // 0 column tile, 1 row tile, 2 end of work
     int tile;
     long long b;
+    long long t_issue, pad;  // statistics builds: clock64() when the copy was issued
 };
+static_assert(sizeof(FlatDesc) == 32, "descriptor slots are 32 bytes");
 
 #ifdef __CUDACC__
 
@@ -229,8 +241,12 @@ __device__ __forceinline__ void flat_stage_a(const FlatParams<T> &q, const cx<T>
                 cx<T> w[R];
 #pragma unroll
                 for (int j = 0; j < R; ++j) w[j] = v[u * R + j];
-                Dft<R>::run(w);
-                apply_powers<R>(w, g);
+                if constexpr (!SSFFT_FLAT_NOCOMPUTE) {
+                    Dft<R>::run(w);
+                    apply_powers<R>(w, g);
+                } else {
+                    w[0] = w[0] + g[0];
+                }
                 const int o = racc + P * R * mp;
 #pragma unroll
                 for (int r = 0; r < R; ++r) sm[(o + P * r) * PITCH + cc] = w[r];
@@ -246,17 +262,17 @@ __device__ __forceinline__ void flat_stage_a(const FlatParams<T> &q, const cx<T>
                 cx<T> w[R];
 #pragma unroll
                 for (int j = 0; j < R; ++j) w[j] = v[u * R + j];
-                Dft<R>::run(w);
+                if constexpr (!SSFFT_FLAT_NOCOMPUTE) Dft<R>::run(w);
                 const int b = tt + TX * u;  // k1 = b + P * r lives at block k1 / CTB, row k1 % CTB of the tile-major scratch
                 if constexpr (P % CTB == 0) {
                     cx<T> *dst = scr + (long long)(b >> CTBLOG) * ((long long)CTB * N2C) + (long long)(lane0 + cc) * CTB + (b & (CTB - 1));
 #pragma unroll
-                    for (int r = 0; r < R; ++r) st_plain(dst + (long long)r * (P / CTB) * ((long long)CTB * N2C), cmul(w[r], s[r]));
+                    for (int r = 0; r < R; ++r) st_plain(dst + (long long)r * (P / CTB) * ((long long)CTB * N2C), SSFFT_FLAT_NOCOMPUTE ? w[r] + s[r] : cmul(w[r], s[r]));
                 } else {
                     constexpr int Q = CTB / P;
                     cx<T> *dst = scr + (long long)(lane0 + cc) * CTB + b;
 #pragma unroll
-                    for (int r = 0; r < R; ++r) st_plain(dst + (long long)(r / Q) * ((long long)CTB * N2C) + P * (r % Q), cmul(w[r], s[r]));
+                    for (int r = 0; r < R; ++r) st_plain(dst + (long long)(r / Q) * ((long long)CTB * N2C) + P * (r % Q), SSFFT_FLAT_NOCOMPUTE ? w[r] + s[r] : cmul(w[r], s[r]));
                 }
             }
         }
@@ -296,11 +312,13 @@ __device__ __forceinline__ void flat_stage_b(const cx<T> *twb, const cx<T> *st, 
             cx<T> w[R];
 #pragma unroll
             for (int j = 0; j < R; ++j) w[j] = v[u * R + j];
-            Dft<R>::run(w);
+            if constexpr (!SSFFT_FLAT_NOCOMPUTE) Dft<R>::run(w);
             if constexpr (!last) {
                 const cx<T> *twp = twb + Cfg::tw_off(ps) + mp;
+                if constexpr (!SSFFT_FLAT_NOCOMPUTE) {
 #pragma unroll
-                for (int r = 1; r < R; ++r) w[r] = cmul(w[r], TWSH ? twp[(r - 1) * MN] : ld_table(twp + (r - 1) * MN));
+                    for (int r = 1; r < R; ++r) w[r] = cmul(w[r], TWSH ? twp[(r - 1) * MN] : ld_table(twp + (r - 1) * MN));
+                }
                 const int o = racc + P * R * mp;
 #pragma unroll
                 for (int r = 0; r < R; ++r) sm[(o + P * r) * PITCH + c] = w[r];
@@ -352,7 +370,9 @@ fourstep_flat_kernel(FlatParams<typename CfgA::T> q, const __grid_constant__ CUt
         const long long total = (q.batch + q.delay) * PT;
         long long issued = 0, signaled = 0;
         bool have = false, exhausted = false, ready = false;
-        FlatDesc cur{2, 0, 0};
+        FlatDesc cur{2, 0, 0, 0, 0};
+        [[maybe_unused]] unsigned long long st_[kFlatStats] = {0};
+        [[maybe_unused]] long long t_have = 0, t_ready = 0;
         long long t_idle = clock64();  // bounded waits: a scheduling surprise becomes a launch error, never a hung GPU
         for (;;) {
             bool moved = false;
@@ -361,8 +381,10 @@ fourstep_flat_kernel(FlatParams<typename CfgA::T> q, const __grid_constant__ CUt
                 const int k = (int)(signaled % NDONE);
                 if (mbar_test(&done[k], (unsigned)((signaled / NDONE) & 1))) {
                     const FlatDesc h = hist[k];
+                    [[maybe_unused]] const long long t0 = clock64();
                     __threadfence();
                     atomicAdd(h.kind == 0 ? &cnt1[h.b] : &cnt2[h.b], 1u);
+                    if constexpr (SSFFT_FLAT_STATS) st_[9] += clock64() - t0;
                     ++signaled;
                     moved = true;
                 }
@@ -375,7 +397,9 @@ fourstep_flat_kernel(FlatParams<typename CfgA::T> q, const __grid_constant__ CUt
                 want = issued - signaled <= NSTAGE &&
                        (issued < NSTAGE || mbar_test(&empty[issued % NSTAGE], (unsigned)(((issued / NSTAGE) - 1) & 1)));
             if (want) {
+                [[maybe_unused]] const long long t0 = clock64();
                 const long long tk = (long long)atomicAdd(q.ctrl, 1u);
+                if constexpr (SSFFT_FLAT_STATS) { t_have = clock64(); st_[3] += t_have - t0; ++st_[4]; }
                 ready = false;
                 if (tk >= total) {
                     exhausted = true;
@@ -394,6 +418,10 @@ fourstep_flat_kernel(FlatParams<typename CfgA::T> q, const __grid_constant__ CUt
                 if (cur.kind == 0) ready = cur.b < q.nslots || ld_acquire_gpu(&cnt2[cur.b - q.nslots]) >= (unsigned)tiles2;
                 else ready = ld_acquire_gpu(&cnt1[cur.b]) >= (unsigned)tiles1;
                 if (ready) moved = true;
+                if constexpr (SSFFT_FLAT_STATS) {
+                    if (ready) { t_ready = clock64(); st_[cur.kind == 0 ? 5 : 6] += t_ready - t_have; }
+                    else ++st_[7];  // polls that found the dependency open
+                }
             }
             if (have && ready && issued - signaled <= NSTAGE) {
                 const int s = (int)(issued % NSTAGE);
@@ -405,6 +433,7 @@ fourstep_flat_kernel(FlatParams<typename CfgA::T> q, const __grid_constant__ CUt
                         break;
                     }
                     {
+                        if constexpr (SSFFT_FLAT_STATS) { cur.t_issue = clock64(); st_[8] += cur.t_issue - t_ready; }
                         desc[s] = cur;
                         hist[issued % NDONE] = cur;
                         cx<T> *slot = reinterpret_cast<cx<T> *>(ssfft_smem + Lay::oSlots + (size_t)s * Lay::kSlot);
@@ -454,14 +483,33 @@ fourstep_flat_kernel(FlatParams<typename CfgA::T> q, const __grid_constant__ CUt
                 if (clock64() - t_idle > 8000000000LL) __trap();
             }
         }
+        if constexpr (SSFFT_FLAT_STATS)
+            if (q.stats)
+                for (int i = 3; i < 10; ++i) q.stats[(size_t)blockIdx.x * kFlatStats + i] = st_[i];
         return;
     }
 
     // ================= consumers =================
+    [[maybe_unused]] unsigned long long cs_[kFlatStats] = {0};
+    [[maybe_unused]] const long long t_begin = clock64();
     for (long long j = 0;; ++j) {
         const int s = (int)(j % NSTAGE);
+        [[maybe_unused]] bool waited = false;
+        [[maybe_unused]] long long t0 = 0;
+        if constexpr (SSFFT_FLAT_STATS) {
+            waited = !mbar_test(&full[s], (unsigned)((j / NSTAGE) & 1));
+            t0 = clock64();
+        }
         mbar_wait(&full[s], (unsigned)((j / NSTAGE) & 1));
         const FlatDesc d = desc[s];
+        if constexpr (SSFFT_FLAT_STATS) {
+            const long long t1 = clock64();
+            if (d.kind != 2) {
+                cs_[1] += t1 - t0;
+                ++cs_[2];
+                if (waited) { cs_[d.kind == 0 ? 10 : 12] += t1 - d.t_issue; ++cs_[d.kind == 0 ? 11 : 13]; }
+            }
+        }
         if (d.kind == 2) break;
         cx<T> *st = reinterpret_cast<cx<T> *>(ssfft_smem + Lay::oSlots + (size_t)s * Lay::kSlot);
         cx<T> *xb = INPLACE ? st : exch;  // exchange buffer of this tile
@@ -481,6 +529,12 @@ fourstep_flat_kernel(FlatParams<typename CfgA::T> q, const __grid_constant__ CUt
         }
         mbar_arrive(&done[j % NDONE]);
     }
+    if constexpr (SSFFT_FLAT_STATS)
+        if (q.stats && tid == 0) {
+            unsigned long long *o = q.stats + (size_t)blockIdx.x * kFlatStats;
+            o[0] = clock64() - t_begin; o[1] = cs_[1]; o[2] = cs_[2];
+            for (int i = 10; i < 14; ++i) o[i] = cs_[i];
+        }
 }
 
 #endif  // __CUDACC__

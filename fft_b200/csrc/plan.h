@@ -4,6 +4,7 @@
 
 #include <cstddef>
 #include <cstdint>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -77,10 +78,25 @@ struct ssfft_plan {
     void *d_rtw = nullptr;  // twiddlesMinusI
     void *d_rot = nullptr;  // modifiedRotations
 
-    // host-pointer path staging (grow-only)
-    void *d_stage_in = nullptr, *d_stage_out = nullptr;
-    size_t stage_in_bytes = 0, stage_out_bytes = 0;
-    cudaStream_t host_stream = nullptr;
+    // Execution order.  A plan is NOT re-entrant: scratch, dependency counters, workspaces and the host-path staging
+    // are per plan.  Calls on one plan are serialised on the host by exec_mu, and a call issued on another stream than
+    // the previous one first waits (on the device) for that one's event, so concurrent use from several streams or
+    // threads is slow but correct.  Independent work wants one plan per stream (copies of the C++ objects get one).
+    std::mutex exec_mu;
+    cudaEvent_t exec_done = nullptr;
+    cudaStream_t exec_last = nullptr;
+    bool exec_any = false;
+
+    // host-pointer path (ssfft_exec_host): three streams (H2D, kernels, D2H) linked by events over a ring of
+    // slice-sized device buffers, all owned by the plan; tiny calls go through pinned mapped host buffers instead
+    static constexpr int kRing = 3;
+    cudaStream_t st_h2d = nullptr, st_comp = nullptr, st_d2h = nullptr;
+    cudaEvent_t ev_h2d[kRing] = {nullptr, nullptr, nullptr}, ev_comp[kRing] = {nullptr, nullptr, nullptr},
+                ev_d2h[kRing] = {nullptr, nullptr, nullptr};
+    void *d_ring_in[kRing] = {nullptr, nullptr, nullptr}, *d_ring_out[kRing] = {nullptr, nullptr, nullptr};
+    size_t ring_bytes = 0;
+    void *h_zc_in = nullptr, *h_zc_out = nullptr;  // pinned, mapped (zero-copy) staging for tiny transfers
+    size_t zc_bytes = 0;
 
     // extended execution (ssfft_exec_*_ex) without a fused kernel: gather / scatter workspaces (grow-only)
     void *d_ex_in = nullptr, *d_ex_out = nullptr;

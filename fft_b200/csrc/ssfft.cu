@@ -53,6 +53,32 @@ struct DeviceGuard {
     ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
 };
 
+// Orders a call behind the previous call on the same plan (see plan.h): host-side mutex for the duration of the
+// enqueue, device-side event when the stream changes.  Streams under capture are left alone (an outside event would
+// break the capture); capturing code uses one plan per captured stream.
+struct PlanExec {
+    ssfft_plan *pl;
+    cudaStream_t s;
+    bool capturing = false;
+    PlanExec(ssfft_plan *p, cudaStream_t st) : pl(p), s(st) {
+        pl->exec_mu.lock();
+        cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+        if (cudaStreamIsCapturing(s, &cs) != cudaSuccess) cudaGetLastError();
+        capturing = cs != cudaStreamCaptureStatusNone;
+        if (!capturing && pl->exec_any && pl->exec_last != s && pl->exec_done) cudaStreamWaitEvent(s, pl->exec_done, 0);
+    }
+    ~PlanExec() {
+        if (!capturing) {
+            if (!pl->exec_done && cudaEventCreateWithFlags(&pl->exec_done, cudaEventDisableTiming) != cudaSuccess) pl->exec_done = nullptr;
+            if (pl->exec_done && cudaEventRecord(pl->exec_done, s) == cudaSuccess) { pl->exec_last = s; pl->exec_any = true; }
+        }
+        pl->exec_mu.unlock();
+    }
+};
+bool plan_is_stateful(const ssfft_plan *pl) {  // owns device state that a concurrent call would trample
+    return pl->d_scratch || pl->d_flat_scratch || pl->d_ex_in || pl->d_ex_out;
+}
+
 int max_optin_smem(int device) {
     int v = 0;
     if (cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, device) != cudaSuccess) return 48 * 1024;
@@ -339,11 +365,37 @@ int exec_flat(ssfft_plan *pl, const void *in, void *out, long long batch, int in
         q.s4 = (const cx<T> *)pl->d_flat_s4; q.ctrl = (unsigned *)pl->d_flat_ctrl;
         q.batch = nb; q.user_stride = n; q.scratch_per = n; q.cap = nb;
         q.nslots = (int)slots; q.delay = (int)delay; q.discard = env_int("SSFFT_DISCARD", 1);
+        q.stats = nullptr;
+#if SSFFT_FLAT_STATS
+        static unsigned long long *d_stats = nullptr;  // measurement build: one buffer, calls are serialised below
+        if (!d_stats) CU(cudaMalloc(&d_stats, (size_t)4096 * kFlatStats * sizeof(unsigned long long)));
+        CU(cudaMemsetAsync(d_stats, 0, (size_t)4096 * kFlatStats * sizeof(unsigned long long), s));
+        q.stats = d_stats;
+#endif
         CU(cudaMemsetAsync(pl->d_flat_ctrl, 0, (size_t)(32 + 2 * nb) * sizeof(unsigned), s));
         const int rc = e.launch[inverse ? 1 : 0](&q, (int)ctas, s);
         if (rc == 3) return -1;
         ++g_launches;
         if (rc) return cuda_fail(cudaGetLastError(), "fourstep_flat_kernel launch");
+#if SSFFT_FLAT_STATS
+        if (env_int("SSFFT_FLAT_STATS_PRINT", 0)) {
+            CU(cudaStreamSynchronize(s));
+            std::vector<unsigned long long> h((size_t)ctas * kFlatStats);
+            CU(cudaMemcpy(h.data(), d_stats, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+            double sum[kFlatStats] = {0};
+            for (long long c = 0; c < ctas; ++c)
+                for (int i = 0; i < kFlatStats; ++i) sum[i] += (double)h[(size_t)c * kFlatStats + i];
+            const double items = sum[2] > 0 ? sum[2] : 1, tk = sum[4] > 0 ? sum[4] : 1;
+            fprintf(stderr,
+                    "flat stats (%s, %lld CTAs, delay %lld, slots %lld): cycles/CTA %.0f | consumers wait for data %.1f %% | per item: "
+                    "cycles %.0f, ticket atomic %.0f, signal %.0f, dep wait col %.0f row %.0f (open polls %.2f), slot wait %.0f | "
+                    "copy latency when waited: col %.0f (%.0f %% of items) row %.0f (%.0f %%)\n",
+                    e.name, ctas, delay, slots, sum[0] / ctas, 100.0 * sum[1] / (sum[0] > 0 ? sum[0] : 1), sum[0] / items,
+                    sum[3] / tk, sum[9] / items, sum[5] / items * 2, sum[6] / items * 2, sum[7] / items, sum[8] / items,
+                    sum[11] > 0 ? sum[10] / sum[11] : 0.0, 200.0 * sum[11] / items, sum[13] > 0 ? sum[12] / sum[13] : 0.0,
+                    200.0 * sum[13] / items);
+        }
+#endif
     }
     return SSFFT_OK;
 }
@@ -618,10 +670,7 @@ int exec_c2r_typed(ssfft_plan *pl, const void *in, void *out, long long batch, c
 // =============================================================================================
 int ex_workspace(void **ptr, size_t *have, size_t need) {
     if (*have >= need) return SSFFT_OK;
-    if (*ptr) {
-        CU(cudaDeviceSynchronize());  // an earlier extended call may still be using the old workspace
-        cudaFree(*ptr);
-    }
+    if (*ptr) CU(cudaFree(*ptr));  // cudaFree waits for the device; calls on one plan are ordered (PlanExec), captures must pre-size
     *ptr = nullptr; *have = 0;
     CU(cudaMalloc(ptr, need));
     *have = need;
@@ -721,6 +770,7 @@ int exec_ex(ssfft_plan *pl, int op, const void *d_in, void *d_out, size_t batch,
     int rc = ex_validate(pl->kind, pl->n, pl->n_real, pl->elem, op, io, (long long)batch, d_in, d_out, x);
     if (rc) return rc;
     DeviceGuard guard(pl->device);
+    PlanExec order(pl, (cudaStream_t)stream);
     return pl->prec == SSFFT_F32 ? exec_ex_typed<float>(pl, op, d_in, d_out, (long long)batch, inverse, x, (cudaStream_t)stream)
                                  : exec_ex_typed<double>(pl, op, d_in, d_out, (long long)batch, inverse, x, (cudaStream_t)stream);
 }
@@ -781,7 +831,7 @@ int ssfft_plan_destroy(ssfft_plan *pl) {
     DeviceGuard guard(pl->device);
     free_stage(pl->direct); free_stage(pl->col); free_stage(pl->row);
     void *ptrs[] = {pl->fused.d_twiddles, pl->fused_col.d_twiddles, pl->fused_row.d_twiddles, pl->d_ep_lo, pl->d_ep_hi,
-                    pl->d_scratch, pl->d_rtw, pl->d_rot, pl->d_stage_in, pl->d_stage_out, pl->d_tile_tw_a, pl->d_tile_tw_b,
+                    pl->d_scratch, pl->d_rtw, pl->d_rot, pl->d_tile_tw_a, pl->d_tile_tw_b,
                     pl->d_tw4, pl->d_fs_ctr, pl->d_ex_in, pl->d_ex_out, pl->d_flat_ga[0], pl->d_flat_ga[1], pl->d_flat_gb[0], pl->d_flat_gb[1], pl->d_flat_s4,
                     pl->d_flat_twb, pl->d_flat_scratch, pl->d_flat_ctrl};
     for (void *p : ptrs)
@@ -793,7 +843,19 @@ int ssfft_plan_destroy(ssfft_plan *pl) {
         if (pl->d_cl_twb[k]) cudaFree(pl->d_cl_twb[k]);
         if (pl->d_cl_tw4[k]) cudaFree(pl->d_cl_tw4[k]);
     }
-    if (pl->host_stream) cudaStreamDestroy(pl->host_stream);
+    for (int i = 0; i < ssfft_plan::kRing; ++i) {
+        if (pl->d_ring_in[i]) cudaFree(pl->d_ring_in[i]);
+        if (pl->d_ring_out[i]) cudaFree(pl->d_ring_out[i]);
+        if (pl->ev_h2d[i]) cudaEventDestroy(pl->ev_h2d[i]);
+        if (pl->ev_comp[i]) cudaEventDestroy(pl->ev_comp[i]);
+        if (pl->ev_d2h[i]) cudaEventDestroy(pl->ev_d2h[i]);
+    }
+    if (pl->h_zc_in) cudaFreeHost(pl->h_zc_in);
+    if (pl->h_zc_out) cudaFreeHost(pl->h_zc_out);
+    if (pl->st_h2d) cudaStreamDestroy(pl->st_h2d);
+    if (pl->st_comp) cudaStreamDestroy(pl->st_comp);
+    if (pl->st_d2h) cudaStreamDestroy(pl->st_d2h);
+    if (pl->exec_done) cudaEventDestroy(pl->exec_done);
     delete pl;
     return SSFFT_OK;
 }
@@ -816,6 +878,11 @@ int ssfft_exec_c2c(ssfft_plan *pl, const void *d_in, void *d_out, size_t batch, 
     if (!d_in || !d_out) return SSFFT_ERR_INVALID;
     DeviceGuard guard(pl->device);
     const int inv = direction == SSFFT_INVERSE;
+    if (plan_is_stateful(pl)) {
+        PlanExec order(pl, (cudaStream_t)stream);
+        return pl->prec == SSFFT_F32 ? exec_complex<float>(pl, d_in, d_out, (long long)batch, inv, (cudaStream_t)stream)
+                                     : exec_complex<double>(pl, d_in, d_out, (long long)batch, inv, (cudaStream_t)stream);
+    }
     return pl->prec == SSFFT_F32 ? exec_complex<float>(pl, d_in, d_out, (long long)batch, inv, (cudaStream_t)stream)
                                  : exec_complex<double>(pl, d_in, d_out, (long long)batch, inv, (cudaStream_t)stream);
 }
@@ -825,6 +892,7 @@ int ssfft_exec_r2c(ssfft_plan *pl, const void *d_in, void *d_out, size_t batch, 
     if (batch == 0 || pl->n == 0) return SSFFT_OK;
     if (!d_in || !d_out) return SSFFT_ERR_INVALID;
     DeviceGuard guard(pl->device);
+    PlanExec order(pl, (cudaStream_t)stream);
     return pl->prec == SSFFT_F32 ? exec_r2c_typed<float>(pl, d_in, d_out, (long long)batch, (cudaStream_t)stream)
                                  : exec_r2c_typed<double>(pl, d_in, d_out, (long long)batch, (cudaStream_t)stream);
 }
@@ -834,6 +902,7 @@ int ssfft_exec_c2r(ssfft_plan *pl, const void *d_in, void *d_out, size_t batch, 
     if (batch == 0 || pl->n == 0) return SSFFT_OK;
     if (!d_in || !d_out) return SSFFT_ERR_INVALID;
     DeviceGuard guard(pl->device);
+    PlanExec order(pl, (cudaStream_t)stream);
     return pl->prec == SSFFT_F32 ? exec_c2r_typed<float>(pl, d_in, d_out, (long long)batch, (cudaStream_t)stream)
                                  : exec_c2r_typed<double>(pl, d_in, d_out, (long long)batch, (cudaStream_t)stream);
 }
@@ -864,69 +933,139 @@ int ssfft_exec_c2r_ex(ssfft_plan *pl, const void *d_in, void *d_out, size_t batc
     return exec_ex(pl, EX_C2R, d_in, d_out, batch, 1, io, stream);
 }
 
+// One slice of a host call on the plan's own path (no PlanExec: the caller holds the order)
+static int exec_host_kernels(ssfft_plan *pl, int op, const void *di, void *dout, size_t nb, cudaStream_t cs) {
+    const long long b = (long long)nb;
+    if (pl->prec == SSFFT_F32) {
+        if (op == 0) return exec_complex<float>(pl, di, dout, b, 0, cs);
+        if (op == 1) return exec_complex<float>(pl, di, dout, b, 1, cs);
+        if (op == 2) return exec_r2c_typed<float>(pl, di, dout, b, cs);
+        return exec_c2r_typed<float>(pl, di, dout, b, cs);
+    }
+    if (op == 0) return exec_complex<double>(pl, di, dout, b, 0, cs);
+    if (op == 1) return exec_complex<double>(pl, di, dout, b, 1, cs);
+    if (op == 2) return exec_r2c_typed<double>(pl, di, dout, b, cs);
+    return exec_c2r_typed<double>(pl, di, dout, b, cs);
+}
+
+static int host_path_setup(ssfft_plan *pl) {
+    if (pl->st_comp) return SSFFT_OK;
+    CU(cudaStreamCreateWithFlags(&pl->st_h2d, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&pl->st_comp, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&pl->st_d2h, cudaStreamNonBlocking));
+    for (int i = 0; i < ssfft_plan::kRing; ++i) {
+        CU(cudaEventCreateWithFlags(&pl->ev_h2d[i], cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&pl->ev_comp[i], cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&pl->ev_d2h[i], cudaEventDisableTiming));
+    }
+    return SSFFT_OK;
+}
+
+// Host buffers in, host buffers out (the call a reference user makes: FFT<V>::fft(container, container)).
+//  * tiny calls (both sides <= 256 KiB): the data goes through pinned, mapped staging buffers owned by the plan and the
+//    kernels read / write them over PCIe themselves -- no cudaMemcpy, one launch, one stream synchronisation;
+//  * everything else: slices of <= 64 MiB through a ring of three device buffers per side; H2D copies, kernels and D2H
+//    copies run on three streams of the plan linked by events, so slice i+1 uploads and slice i-1 downloads while
+//    slice i transforms (PCIe is full duplex) and ALL kernels of the call run on ONE stream in slice order -- the plan's
+//    scratch is never used by two slices at once.  Device memory per call is bounded by the ring (6 slices), not by
+//    the batch.  Pageable host memory works but serialises the copies; pinned memory (cudaHostAlloc / ssfft_host_alloc)
+//    gives the overlap.
 int ssfft_exec_host(ssfft_plan *pl, int op, const void *h_in, void *h_out, size_t batch) {
     if (!pl || op < 0 || op > 3) return SSFFT_ERR_INVALID;
     if ((op <= 1) != (pl->kind == SSFFT_C2C)) return SSFFT_ERR_INVALID;
     if (batch == 0 || pl->n == 0) return SSFFT_OK;
     if (!h_in || !h_out) return SSFFT_ERR_INVALID;
     DeviceGuard guard(pl->device);
+    std::lock_guard<std::mutex> lock(pl->exec_mu);
+    int rc = host_path_setup(pl);
+    if (rc) return rc;
     // bytes per transform on each side: C2C n cx both; real: N reals == n cx on both sides as well
-    const size_t bytes = batch * pl->n * pl->elem;
-    if (!pl->host_stream) CU(cudaStreamCreateWithFlags(&pl->host_stream, cudaStreamNonBlocking));
-    if (pl->stage_in_bytes < bytes) {
-        if (pl->d_stage_in) cudaFree(pl->d_stage_in);
-        pl->d_stage_in = nullptr; pl->stage_in_bytes = 0;
-        CU(cudaMalloc(&pl->d_stage_in, bytes));
-        pl->stage_in_bytes = bytes;
+    const size_t per = pl->n * pl->elem, bytes = batch * per;
+    if (pl->exec_any && pl->exec_done) CU(cudaStreamWaitEvent(pl->st_comp, pl->exec_done, 0));  // behind earlier device calls
+
+    const size_t zc_limit = (size_t)env_int("SSFFT_HOST_ZEROCOPY_KB", 256) << 10;
+    if (bytes <= zc_limit) {
+        if (pl->zc_bytes < bytes) {
+            if (pl->h_zc_in) cudaFreeHost(pl->h_zc_in);
+            if (pl->h_zc_out) cudaFreeHost(pl->h_zc_out);
+            pl->h_zc_in = pl->h_zc_out = nullptr; pl->zc_bytes = 0;
+            const size_t cap = bytes < 65536 ? 65536 : bytes;
+            CU(cudaHostAlloc(&pl->h_zc_in, cap, cudaHostAllocMapped));
+            CU(cudaHostAlloc(&pl->h_zc_out, cap, cudaHostAllocMapped));
+            pl->zc_bytes = cap;
+        }
+        memcpy(pl->h_zc_in, h_in, bytes);
+        void *dz_in = nullptr, *dz_out = nullptr;
+        CU(cudaHostGetDevicePointer(&dz_in, pl->h_zc_in, 0));
+        CU(cudaHostGetDevicePointer(&dz_out, pl->h_zc_out, 0));
+        rc = exec_host_kernels(pl, op, dz_in, dz_out, batch, pl->st_comp);
+        if (rc) return rc;
+        CU(cudaStreamSynchronize(pl->st_comp));
+        memcpy(h_out, pl->h_zc_out, bytes);
+        return SSFFT_OK;
     }
-    if (pl->stage_out_bytes < bytes) {
-        if (pl->d_stage_out) cudaFree(pl->d_stage_out);
-        pl->d_stage_out = nullptr; pl->stage_out_bytes = 0;
-        CU(cudaMalloc(&pl->d_stage_out, bytes));
-        pl->stage_out_bytes = bytes;
+
+    // slices: large enough for PCIe to run at full rate, small enough that fill / drain of the pipeline stay short
+    size_t slice_tr = ((size_t)env_int("SSFFT_HOST_SLICE_MB", 64) << 20) / per;
+    if (slice_tr < 1) slice_tr = 1;
+    const size_t min_slices = 8;  // a call of a few hundred MiB still overlaps its copies
+    if (batch / slice_tr < min_slices && batch >= min_slices) slice_tr = (batch + min_slices - 1) / min_slices;
+    if (slice_tr > batch) slice_tr = batch;
+    const size_t slice_bytes = slice_tr * per;
+    if (pl->ring_bytes < slice_bytes) {
+        for (int i = 0; i < ssfft_plan::kRing; ++i) {
+            if (pl->d_ring_in[i]) cudaFree(pl->d_ring_in[i]);
+            if (pl->d_ring_out[i]) cudaFree(pl->d_ring_out[i]);
+            pl->d_ring_in[i] = pl->d_ring_out[i] = nullptr;
+        }
+        pl->ring_bytes = 0;
+        for (int i = 0; i < ssfft_plan::kRing; ++i) {
+            CU(cudaMalloc(&pl->d_ring_in[i], slice_bytes));
+            CU(cudaMalloc(&pl->d_ring_out[i], slice_bytes));
+        }
+        pl->ring_bytes = slice_bytes;
     }
-    // pipeline in slices so H2D, kernels and D2H overlap (PCIe is full duplex)
-    cudaStream_t s = pl->host_stream;
-    size_t slices = 1;
-    const size_t per = pl->n * pl->elem;
-    // more slices = shorter pipeline fill / drain (first H2D and last D2H are not overlapped); each slice still has to
-    // be large enough to run PCIe at full rate (>= 32 MiB)
-    if (bytes > (64u << 20)) {
-        slices = (size_t)env_int("SSFFT_HOST_SLICES", 0);
-        if (slices < 1) { slices = bytes / (64u << 20); if (slices < 8) slices = 8; if (slices > 32) slices = 32; }
-    }
-    if (slices > batch) slices = batch;
-    // slices rotate over a few streams so that the H2D copy of one slice, the kernels of another and the D2H copy of a
-    // third are in flight together (PCIe is full duplex)
-    int nstreams = env_int("SSFFT_HOST_STREAMS", 3);
-    if (nstreams < 1) nstreams = 1;
-    if (nstreams > 8) nstreams = 8;
-    cudaStream_t extra[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-    if (slices > 1)
-        for (int k = 0; k + 1 < nstreams; ++k) CU(cudaStreamCreateWithFlags(&extra[k], cudaStreamNonBlocking));
-    int rc = SSFFT_OK;
-    for (size_t i = 0; i < slices && rc == SSFFT_OK; ++i) {
-        const size_t b0 = batch * i / slices, b1 = batch * (i + 1) / slices;
-        const int which = (int)(i % (size_t)nstreams);
-        cudaStream_t cs = (slices > 1 && which > 0) ? extra[which - 1] : s;
+    const size_t slices = (batch + slice_tr - 1) / slice_tr;
+    cudaError_t e = cudaSuccess;
+    for (size_t i = 0; i < slices && rc == SSFFT_OK && e == cudaSuccess; ++i) {
+        const int k = (int)(i % ssfft_plan::kRing);
+        const size_t b0 = i * slice_tr, nb = batch - b0 < slice_tr ? batch - b0 : slice_tr;
         const char *hi = (const char *)h_in + b0 * per;
         char *ho = (char *)h_out + b0 * per;
-        char *di = (char *)pl->d_stage_in + b0 * per, *dout = (char *)pl->d_stage_out + b0 * per;
-        cudaError_t e = cudaMemcpyAsync(di, hi, (b1 - b0) * per, cudaMemcpyHostToDevice, cs);
-        if (e != cudaSuccess) { rc = cuda_fail(e, "H2D"); break; }
-        if (op == 0) rc = ssfft_exec_c2c(pl, di, dout, b1 - b0, SSFFT_FORWARD, cs);
-        else if (op == 1) rc = ssfft_exec_c2c(pl, di, dout, b1 - b0, SSFFT_INVERSE, cs);
-        else if (op == 2) rc = ssfft_exec_r2c(pl, di, dout, b1 - b0, cs);
-        else rc = ssfft_exec_c2r(pl, di, dout, b1 - b0, cs);
+        // upload: the kernels of slice i - kRing have read this input buffer
+        if (i >= (size_t)ssfft_plan::kRing) e = cudaStreamWaitEvent(pl->st_h2d, pl->ev_comp[k], 0);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(pl->d_ring_in[k], hi, nb * per, cudaMemcpyHostToDevice, pl->st_h2d);
+        if (e == cudaSuccess) e = cudaEventRecord(pl->ev_h2d[k], pl->st_h2d);
+        // transform: input uploaded, output buffer downloaded (slice i - kRing)
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(pl->st_comp, pl->ev_h2d[k], 0);
+        if (e == cudaSuccess && i >= (size_t)ssfft_plan::kRing) e = cudaStreamWaitEvent(pl->st_comp, pl->ev_d2h[k], 0);
+        if (e != cudaSuccess) break;
+        rc = exec_host_kernels(pl, op, pl->d_ring_in[k], pl->d_ring_out[k], nb, pl->st_comp);
         if (rc) break;
-        e = cudaMemcpyAsync(ho, dout, (b1 - b0) * per, cudaMemcpyDeviceToHost, cs);
-        if (e != cudaSuccess) { rc = cuda_fail(e, "D2H"); break; }
+        e = cudaEventRecord(pl->ev_comp[k], pl->st_comp);
+        // download
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(pl->st_d2h, pl->ev_comp[k], 0);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(ho, pl->d_ring_out[k], nb * per, cudaMemcpyDeviceToHost, pl->st_d2h);
+        if (e == cudaSuccess) e = cudaEventRecord(pl->ev_d2h[k], pl->st_d2h);
     }
-    cudaError_t e1 = cudaStreamSynchronize(s);
-    for (auto &e : extra)
-        if (e) { cudaError_t e2 = cudaStreamSynchronize(e); if (e1 == cudaSuccess) e1 = e2; cudaStreamDestroy(e); }
+    const cudaError_t e1 = cudaStreamSynchronize(pl->st_h2d), e2 = cudaStreamSynchronize(pl->st_comp),
+                      e3 = cudaStreamSynchronize(pl->st_d2h);
     if (rc) return rc;
-    if (e1 != cudaSuccess) return cuda_fail(e1, "cudaStreamSynchronize");
+    if (e != cudaSuccess) return cuda_fail(e, "host path enqueue");
+    if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess)
+        return cuda_fail(e1 != cudaSuccess ? e1 : e2 != cudaSuccess ? e2 : e3, "cudaStreamSynchronize");
+    return SSFFT_OK;
+}
+
+// Pinned (page-locked) host memory for the host path: copies from / to it overlap with the kernels.
+int ssfft_host_alloc(void **h_ptr, size_t bytes) {
+    if (!h_ptr) return SSFFT_ERR_INVALID;
+    *h_ptr = nullptr;
+    if (cudaHostAlloc(h_ptr, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return SSFFT_ERR_ALLOC; }
+    return SSFFT_OK;
+}
+int ssfft_host_free(void *h_ptr) {
+    if (h_ptr) CU(cudaFreeHost(h_ptr));
     return SSFFT_OK;
 }
 

@@ -51,13 +51,33 @@ inline void check(int status, const char *what) {
         throw std::runtime_error(msg);
     }
 }
-// Plans are immutable once built (tables live in HBM), so copies of an FFT object share one handle --
-// reference objects are copyable (they own std::vectors), and this keeps that property.
-inline std::shared_ptr<ssfft_plan> makePlan(int kind, int precision, std::size_t n) {
-    ssfft_plan *raw = nullptr;
-    check(ssfft_plan_create(&raw, kind, precision, n, -1), "ssfft_plan_create");
-    return std::shared_ptr<ssfft_plan>(raw, [](ssfft_plan *p) { ssfft_plan_destroy(p); });
-}
+// Owner of one ssfft_plan.  A plan holds mutable per-call state next to its immutable tables (scratch for the large
+// transforms, staging for the host path), so COPIES GET THEIR OWN PLAN, built from (kind, precision, size) -- reference
+// objects are independent after a copy (they own std::vectors) and a pattern such as
+// std::vector<FFT<float>>(nThreads, FFT<float>(n)) must not make the copies share scratch.  Moves transfer the handle.
+class PlanHandle {
+    ssfft_plan *p_ = nullptr;
+    int kind_ = 0, precision_ = 0;
+    std::size_t n_ = 0;
+
+public:
+    PlanHandle() = default;
+    PlanHandle(int kind, int precision, std::size_t n) : kind_(kind), precision_(precision), n_(n) {
+        check(ssfft_plan_create(&p_, kind, precision, n, -1), "ssfft_plan_create");
+    }
+    PlanHandle(const PlanHandle &o) : kind_(o.kind_), precision_(o.precision_), n_(o.n_) {
+        if (o.p_) check(ssfft_plan_create(&p_, kind_, precision_, n_, -1), "ssfft_plan_create");
+    }
+    PlanHandle(PlanHandle &&o) noexcept : p_(o.p_), kind_(o.kind_), precision_(o.precision_), n_(o.n_) { o.p_ = nullptr; }
+    PlanHandle &operator=(PlanHandle o) noexcept {
+        std::swap(p_, o.p_); std::swap(kind_, o.kind_); std::swap(precision_, o.precision_); std::swap(n_, o.n_);
+        return *this;
+    }
+    ~PlanHandle() { if (p_) ssfft_plan_destroy(p_); }
+    ssfft_plan *get() const { return p_; }
+    explicit operator bool() const { return p_ != nullptr; }
+};
+inline PlanHandle makePlan(int kind, int precision, std::size_t n) { return PlanHandle(kind, precision, n); }
 
 // Accept containers (anything std::begin works on) or iterators/pointers, as the reference does (:56-67).
 template <typename T, typename = void>
@@ -78,7 +98,7 @@ template <typename V>
 class FFT {
     using complex = std::complex<V>;
     std::size_t _size;
-    std::shared_ptr<ssfft_plan> plan;
+    b200_detail::PlanHandle plan;
     std::vector<complex> hostIn, hostOut;  // staging for the host-iterator path
 
     template <bool inverse, typename InputIterator, typename OutputIterator>
@@ -103,7 +123,7 @@ public:
             _size = size;
             hostIn.resize(size);
             hostOut.resize(size);
-            plan = size ? b200_detail::makePlan(SSFFT_C2C, b200_detail::Precision<V>::value, size) : nullptr;
+            plan = size ? b200_detail::makePlan(SSFFT_C2C, b200_detail::Precision<V>::value, size) : b200_detail::PlanHandle();
         }
         return _size;
     }
@@ -160,7 +180,7 @@ class RealFFT {
     static constexpr bool modified = (optionFlags & FFTOptions::halfFreqShift);
     using complex = std::complex<V>;
     std::size_t halfSize;
-    std::shared_ptr<ssfft_plan> plan;
+    b200_detail::PlanHandle plan;
     std::vector<V> hostReal;
     std::vector<complex> hostComplex;
 
@@ -181,7 +201,7 @@ public:
         hostComplex.resize(halfSize);
         plan = halfSize ? b200_detail::makePlan(modified ? SSFFT_REAL_MODIFIED : SSFFT_REAL,
                                                 b200_detail::Precision<V>::value, halfSize * 2)
-                        : nullptr;
+                        : b200_detail::PlanHandle();
         return halfSize;  // the reference returns the COMPLEX size here (:434)
     }
     std::size_t setSizeMinimum(std::size_t size) { return setSize(sizeMinimum(size)); }

@@ -122,11 +122,19 @@ SSFFT_API int ssfft_exec_r2c_ex(ssfft_plan *plan, const void *d_real_in, void *d
 SSFFT_API int ssfft_exec_c2r_ex(ssfft_plan *plan, const void *d_cplx_in, void *d_real_out, size_t batch,
                                 const ssfft_io *io, void *stream);
 
-/* ---- execution on HOST pointers: the call a reference user makes (fft(in, out) on host containers).
- * Stages host -> device (pinned staging buffers owned by the plan), runs the device path above, copies
- * back, and returns when `h_out` is complete.  kind-specific meaning of in/out as for the device calls:
- * op = 0 C2C forward, 1 C2C inverse, 2 R2C, 3 C2R. */
+/* ---- execution on HOST pointers: the call a reference user makes (fft(in, out) on host containers, reference
+ * signalsmith-fft.h:374-386, :446-502).  Returns when `h_out` is complete.  op = 0 C2C forward, 1 C2C inverse, 2 R2C,
+ * 3 C2R; in/out mean what they mean for the device calls.
+ *   - calls of at most 256 KiB per side go through pinned, mapped staging buffers of the plan: the kernels read and
+ *     write them over PCIe themselves (no cudaMemcpy, one launch, one synchronisation);
+ *   - larger calls are cut into slices that move through a ring of three device buffers per side on three streams of
+ *     the plan (upload / kernels / download, linked by events), so device memory is bounded by the ring, the copies of
+ *     neighbouring slices overlap the kernels, and all kernels of a call run in order on one stream.
+ * h_in / h_out may be pageable; pinned memory (ssfft_host_alloc, cudaHostAlloc) is what makes the copies overlap.
+ * A plan is not re-entrant (ssfft_plan: scratch, staging and counters are per plan): calls on one plan are serialised. */
 SSFFT_API int ssfft_exec_host(ssfft_plan *plan, int op, const void *h_in, void *h_out, size_t batch);
+SSFFT_API int ssfft_host_alloc(void **h_ptr, size_t bytes); /* pinned host memory */
+SSFFT_API int ssfft_host_free(void *h_ptr);
 
 /* ---- device-memory helpers so the header-only front end needs no CUDA headers ---- */
 SSFFT_API int ssfft_device_count(int *count);

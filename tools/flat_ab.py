@@ -17,6 +17,9 @@ CHILD = r"""
 import json, math, os, sys
 sys.path.insert(0, os.getcwd())
 import torch, fft_b200
+if os.environ.get("SSFFT_LIB"):
+    from fft_b200 import _lib as _L
+    _L.LIB_PATH = fft_b200.LIB_PATH = os.environ["SSFFT_LIB"]
 PEAK = json.load(open("MEASURED_PEAKS.json"))["hbm_gbs"]
 n = int(sys.argv[1])
 batch = max(1, (1 << 30) // (n * 8))
@@ -43,6 +46,10 @@ def run(n, env):
     e = dict(os.environ)
     e.update(env)
     res = subprocess.run([sys.executable, "-c", CHILD, str(n)], capture_output=True, text=True, env=e, timeout=300)
+    for line in res.stderr.splitlines():
+        if line.startswith("flat stats"):
+            print("      " + line, flush=True)
+            break
     try:
         return json.loads(res.stdout.strip().splitlines()[-1])
     except Exception:
