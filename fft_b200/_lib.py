@@ -93,6 +93,15 @@ def load():
         "ssfft_ipc_close": (i32, [vp]),
         "ssfft_exchange_transpose": (i32, [vp, c.POINTER(vp), i32, sz, sz, sz, sz, sz, u64, i32, i32, vp]),
         "ssfft_memcpy_d2d": (i32, [vp, vp, sz, vp]),
+        "ssfft_host_alloc": (i32, [c.POINTER(vp), sz]),
+        "ssfft_host_free": (i32, [vp]),
+        "ssfft_dist_plan_create": (i32, [c.POINTER(vp), i32, sz, i32, c.POINTER(i32), i32]),
+        "ssfft_dist_plan_destroy": (i32, [vp]),
+        "ssfft_dist_plan_describe": (i32, [vp, c.c_char_p, sz]),
+        "ssfft_dist_plan_factor": (sz, [vp, i32]),
+        "ssfft_dist_exec_c2c": (i32, [vp, c.POINTER(vp), c.POINTER(vp), i32]),
+        "ssfft_dist_synchronize": (i32, [vp]),
+        "ssfft_dist_wait": (i32, [vp, i32, vp]),
         "ssfft_error_string": (c.c_char_p, [i32]),
         "ssfft_last_cuda_error": (c.c_char_p, []),
         "ssfft_launch_count": (u64, []),

@@ -46,6 +46,7 @@ struct FlatParams {
     unsigned long long *stats;  // -DSSFFT_FLAT_STATS builds only: kFlatStats counters per CTA (else unused, null)
 };
 constexpr int kFlatStats = 16;
+constexpr int kFlatHelpers = 64;  // two helper warps per CTA: the TMA producer and the completion signaller
 #ifndef SSFFT_FLAT_STATS
 #define SSFFT_FLAT_STATS 0
 #endif
@@ -53,6 +54,11 @@ constexpr int kFlatStats = 16;
 // dependency traffic and stores, wrong results: what the schedule and the memory system can do without the arithmetic
 #ifndef SSFFT_FLAT_NOCOMPUTE
 #define SSFFT_FLAT_NOCOMPUTE 0
+#endif
+// -DSSFFT_FLAT_NODEPS=1 (measurement build, wrong results): dependencies are never waited for -- the ceiling of the copy /
+// store pipeline alone
+#ifndef SSFFT_FLAT_NODEPS
+#define SSFFT_FLAT_NODEPS 0
 #endif
 
 __host__ __device__ constexpr int flat_ilog2(int v) { return v <= 1 ? 0 : 1 + flat_ilog2(v / 2); }
@@ -77,7 +83,8 @@ struct FlatLayout {
     static constexpr size_t oExch = 0, oSlots = oExch + (INPLACE ? 0 : kExch), oSBlk = oSlots + NSTAGE * kSlot,
                             oTwB = oSBlk + (INPLACE ? 0 : (NSTAGE + 1) * kSBlk), oDesc = oTwB + kTwB,
                             oBars = oDesc + al((size_t)(2 * NSTAGE + 1) * 32);
-    static constexpr size_t smem_bytes = oBars + al((size_t)(3 * NSTAGE + 1) * 8);
+    static constexpr size_t oSync = oBars + al((size_t)(3 * NSTAGE + 1) * 8);  // producer <-> signaller counters
+    static constexpr size_t smem_bytes = oSync + 128;
 };
 
 struct FlatDesc {  // what the producer tells the consumers about a ring slot (and itself about an unsignalled item)
@@ -133,6 +140,10 @@ __device__ __forceinline__ void tma_tile_3d(cx<T> *dst, const void *tmap, const 
         : "memory");
 }
 #endif
+
+// progress counters the two helper threads share through shared memory
+__device__ __forceinline__ long long ld_shared_volatile(const long long *p) { return *reinterpret_cast<const volatile long long *>(p); }
+__device__ __forceinline__ void st_shared_volatile(long long *p, long long v) { *reinterpret_cast<volatile long long *>(p) = v; }
 
 // two consecutive table entries with one 128-bit access where the type allows it
 template <typename T>
@@ -334,7 +345,7 @@ __device__ __forceinline__ void flat_stage_b(const cx<T> *twb, const cx<T> *st, 
 
 // KIND 0: C2C.  (real flavours stay on the cluster kernel of tiled.cuh for now)
 template <typename CfgA, typename CfgB, int INV, int NSTAGE, int MINB, bool INPLACE>
-__global__ void __launch_bounds__(CfgA::THREADS + 32, MINB)
+__global__ void __launch_bounds__(CfgA::THREADS + kFlatHelpers, MINB)
 fourstep_flat_kernel(FlatParams<typename CfgA::T> q, const __grid_constant__ CUtensorMap tmap) {
     using T = typename CfgA::T;
     using Lay = FlatLayout<CfgA, CfgB, NSTAGE, INPLACE>;
@@ -357,18 +368,52 @@ fourstep_flat_kernel(FlatParams<typename CfgA::T> q, const __grid_constant__ CUt
     if (tid == 0) {
         for (int s = 0; s < NSTAGE; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], NC); }
         for (int s = 0; s < NDONE; ++s) mbar_init(&done[s], NC);
+        long long *sync0 = reinterpret_cast<long long *>(ssfft_smem + Lay::oSync);
+        sync0[0] = sync0[1] = sync0[2] = 0;
     }
     if constexpr (Lay::kTwBShared)
-        for (int i = tid; i < CfgB::tw_total; i += NC + 32) twb_sm[i] = ld_table(q.tw_b + i);
+        for (int i = tid; i < CfgB::tw_total; i += NC + kFlatHelpers) twb_sm[i] = ld_table(q.tw_b + i);
     __syncthreads();
 
+    // sync[0]: items the producer has issued; sync[1]: items the signaller has published; sync[2]: 1 = no more items
+    long long *sync = reinterpret_cast<long long *>(ssfft_smem + Lay::oSync);
+    FlatDesc *hist = desc + NSTAGE;
+    unsigned *cnt1 = q.ctrl + 32, *cnt2 = cnt1 + q.cap;
+    if (tid == NC + 32) {
+        // ================= signaller (one thread) =================
+        // When the consumers have finished an item (done mbarrier) it makes their scratch / output stores visible
+        // device-wide (the fence waits for them to drain, ~1 us) and bumps the transform's counter.  Its own thread so
+        // that this wait never delays the next copy.
+        long long signaled = 0;
+        long long t_idle = clock64();
+        for (;;) {
+            const long long issued = ld_shared_volatile(&sync[0]);
+            if (signaled < issued) {
+                const int k = (int)(signaled % NDONE);
+                if (mbar_test(&done[k], (unsigned)((signaled / NDONE) & 1))) {
+                    const FlatDesc h = hist[k];
+                    __threadfence();
+                    atomicAdd(h.kind == 0 ? &cnt1[h.b] : &cnt2[h.b], 1u);
+                    ++signaled;
+                    __threadfence_block();
+                    st_shared_volatile(&sync[1], signaled);
+                    producer_moved();
+                    t_idle = clock64();
+                    continue;
+                }
+            } else if (ld_shared_volatile(&sync[2]) != 0 && signaled >= ld_shared_volatile(&sync[0])) {
+                break;
+            }
+            producer_idle();
+            if (clock64() - t_idle > 8000000000LL) __trap();
+        }
+        return;
+    }
     if (tid >= NC) {
         // ================= producer (one thread) =================
         if (tid != NC) return;
-        FlatDesc *hist = desc + NSTAGE;
-        unsigned *cnt1 = q.ctrl + 32, *cnt2 = cnt1 + q.cap;
         const long long total = (q.batch + q.delay) * PT;
-        long long issued = 0, signaled = 0;
+        long long issued = 0;
         bool have = false, exhausted = false, ready = false;
         FlatDesc cur{2, 0, 0, 0, 0};
         [[maybe_unused]] unsigned long long st_[kFlatStats] = {0};
@@ -376,19 +421,7 @@ fourstep_flat_kernel(FlatParams<typename CfgA::T> q, const __grid_constant__ CUt
         long long t_idle = clock64();  // bounded waits: a scheduling surprise becomes a launch error, never a hung GPU
         for (;;) {
             bool moved = false;
-            // completion signals, in order
-            if (signaled < issued) {
-                const int k = (int)(signaled % NDONE);
-                if (mbar_test(&done[k], (unsigned)((signaled / NDONE) & 1))) {
-                    const FlatDesc h = hist[k];
-                    [[maybe_unused]] const long long t0 = clock64();
-                    __threadfence();
-                    atomicAdd(h.kind == 0 ? &cnt1[h.b] : &cnt2[h.b], 1u);
-                    if constexpr (SSFFT_FLAT_STATS) st_[9] += clock64() - t0;
-                    ++signaled;
-                    moved = true;
-                }
-            }
+            const long long signaled = ld_shared_volatile(&sync[1]);  // items whose history / done slots may be reused
             // a ticket is taken as late as the ring allows (ring of one: right away, its copy must start the moment the
             // slot frees; deeper rings: when a slot is free) -- tickets held idle widen the window of transforms in flight
             // and with it the scratch the schedule needs
@@ -415,7 +448,8 @@ fourstep_flat_kernel(FlatParams<typename CfgA::T> q, const __grid_constant__ CUt
                 moved = true;
             }
             if (have && !ready) {  // dependencies are polled while the ring slot is still busy: the copy starts the moment it frees
-                if (cur.kind == 0) ready = cur.b < q.nslots || ld_acquire_gpu(&cnt2[cur.b - q.nslots]) >= (unsigned)tiles2;
+                if (SSFFT_FLAT_NODEPS) ready = true;
+                else if (cur.kind == 0) ready = cur.b < q.nslots || ld_acquire_gpu(&cnt2[cur.b - q.nslots]) >= (unsigned)tiles2;
                 else ready = ld_acquire_gpu(&cnt1[cur.b]) >= (unsigned)tiles1;
                 if (ready) moved = true;
                 if constexpr (SSFFT_FLAT_STATS) {
@@ -455,6 +489,8 @@ fourstep_flat_kernel(FlatParams<typename CfgA::T> q, const __grid_constant__ CUt
                                      (unsigned)Lay::kTileB, &full[s]);
                         }
                         ++issued;
+                        __threadfence_block();  // the history entry is written before the signaller learns of the item
+                        st_shared_volatile(&sync[0], issued);
                         have = false;
                         moved = true;
                     }
@@ -468,21 +504,8 @@ fourstep_flat_kernel(FlatParams<typename CfgA::T> q, const __grid_constant__ CUt
                 if (clock64() - t_idle > 8000000000LL) __trap();
             }
         }
-        // drain: signal the items still in flight
-        while (signaled < issued) {
-            const int k = (int)(signaled % NDONE);
-            if (mbar_test(&done[k], (unsigned)((signaled / NDONE) & 1))) {
-                const FlatDesc h = hist[k];
-                __threadfence();
-                atomicAdd(h.kind == 0 ? &cnt1[h.b] : &cnt2[h.b], 1u);
-                ++signaled;
-                producer_moved();
-                t_idle = clock64();
-            } else {
-                producer_idle();
-                if (clock64() - t_idle > 8000000000LL) __trap();
-            }
-        }
+        __threadfence_block();
+        st_shared_volatile(&sync[2], 1);  // the signaller drains the items still in flight and leaves
         if constexpr (SSFFT_FLAT_STATS)
             if (q.stats)
                 for (int i = 3; i < 10; ++i) q.stats[(size_t)blockIdx.x * kFlatStats + i] = st_[i];

@@ -23,7 +23,7 @@ int flat_max_ctas() {
         return -1;
     }
     int per_sm = 0, sms = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, CfgA::THREADS + 32, Lay::smem_bytes) != cudaSuccess) {
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, CfgA::THREADS + kFlatHelpers, Lay::smem_bytes) != cudaSuccess) {
         cudaGetLastError();
         return -1;
     }
@@ -44,7 +44,7 @@ int launch_flat(const void *params, int ctas, cudaStream_t s) {
     memset(&tmap, 0, sizeof(tmap));
     constexpr int kBoxRows = CfgA::L > 256 ? 256 : CfgA::L;
     if (!encode_tensor_map_3d(&tmap, q.in, q.batch, CfgA::L, CfgB::L, kBoxRows, CfgA::CT)) return 3;
-    fourstep_flat_kernel<CfgA, CfgB, INV, NSTAGE, MINB, INPLACE><<<(unsigned)ctas, CfgA::THREADS + 32, Lay::smem_bytes, s>>>(q, tmap);
+    fourstep_flat_kernel<CfgA, CfgB, INV, NSTAGE, MINB, INPLACE><<<(unsigned)ctas, CfgA::THREADS + kFlatHelpers, Lay::smem_bytes, s>>>(q, tmap);
     return cudaGetLastError() == cudaSuccess ? 0 : 2;
 }
 
@@ -56,7 +56,7 @@ FlatEntry make_flat_entry(const char *name) {
     e.n1 = CfgA::L; e.n2 = CfgB::L; e.name = name;
     for (int i = 0; i < 3; ++i) e.ra[i] = CfgA::radix(i);
     e.na_passes = CfgA::NP; e.cta = CfgA::CT; e.ctb = CfgB::CT;
-    e.threads = CfgA::THREADS + 32; e.nstage = NSTAGE; e.minb = MINB; e.inplace = INPLACE ? 1 : 0;
+    e.threads = CfgA::THREADS + kFlatHelpers; e.nstage = NSTAGE; e.minb = MINB; e.inplace = INPLACE ? 1 : 0;
     e.smem_bytes = Lay::smem_bytes;
     e.tile_b_tw = CfgB::tw_total;
     e.nb_passes = CfgB::NP;

@@ -67,6 +67,12 @@ struct ssfft_plan {
     void *d_flat_scratch = nullptr, *d_flat_ctrl = nullptr;
     long long flat_cap = 0;                // transforms per launch the dependency counters cover
 
+    // Bluestein (bluestein.cuh): lengths whose largest prime factor fits no on-chip path run as a convolution through
+    // an inner power-of-two plan of length bs_m
+    ssfft_plan *bs_inner = nullptr;
+    size_t bs_m = 0, bs_chunk = 0;          // convolution length, transforms per pass through the work buffers
+    void *d_bs_chirp = nullptr, *d_bs_filter = nullptr, *d_bs_work[2] = {nullptr, nullptr};
+
     // cluster-resident four-step (cluster.cuh): registry id per kind (C2C / R2C / C2R), -1 = not used
     bool clustered = false;
     int cl_id[3] = {-1, -1, -1};

@@ -15,6 +15,7 @@
 #include <string>
 #include <vector>
 
+#include "bluestein.cuh"
 #include "cluster.cuh"
 #include "ex_request.h"
 #include "flat.cuh"
@@ -76,7 +77,7 @@ struct PlanExec {
     }
 };
 bool plan_is_stateful(const ssfft_plan *pl) {  // owns device state that a concurrent call would trample
-    return pl->d_scratch || pl->d_flat_scratch || pl->d_ex_in || pl->d_ex_out;
+    return pl->d_scratch || pl->d_flat_scratch || pl->d_ex_in || pl->d_ex_out || pl->bs_inner;
 }
 
 int max_optin_smem(int device) {
@@ -297,7 +298,7 @@ FlatSchedule flat_schedule(int ctas, int ring, int tickets_per_phase) {
     f.delay = (3 * f.span + 1) / 2;
     const int pct = env_int("SSFFT_FLAT_DELAY_PCT", 100);  // A/B measurements of the schedule
     if (pct > 0 && pct != 100) f.delay = (int)((long long)f.delay * pct / 100);
-    f.slots = f.delay + f.span + 2;
+    f.slots = f.delay + 2 * f.span + 2;  // the previous user of a slot finishes about a span after its tickets went out
     return f;
 }
 template <typename T>
@@ -355,7 +356,7 @@ int exec_flat(ssfft_plan *pl, const void *in, void *out, long long batch, int in
         long long delay = env_int("SSFFT_FLAT_DELAY", -1) >= 0 ? env_int("SSFFT_FLAT_DELAY", -1) : fs.delay;
         if (delay > nb) delay = nb;
         if (delay > pl->flat_slots - 1) delay = pl->flat_slots - 1;
-        long long slots = env_int("SSFFT_FLAT_SLOTS", 0) > 0 ? env_int("SSFFT_FLAT_SLOTS", 0) : delay + fs.span + 2;
+        long long slots = env_int("SSFFT_FLAT_SLOTS", 0) > 0 ? env_int("SSFFT_FLAT_SLOTS", 0) : delay + 2 * fs.span + 2;
         if (slots > pl->flat_slots) slots = pl->flat_slots;
         if (slots < delay + 1) slots = delay + 1;
         FlatParams<T> q;
@@ -453,11 +454,62 @@ int exec_clustered(ssfft_plan *pl, int kind, const void *in, void *out, long lon
     return SSFFT_OK;
 }
 
+// Bluestein: inner plan of length M = 2^k >= 2n - 1, chirp table, spectrum of the wrapped conjugate chirp, work buffers.
+template <typename T>
+int setup_bluestein(ssfft_plan *pl) {
+    const size_t n = pl->n, m = bluestein_length(n);
+    int rc = ssfft_plan_create(&pl->bs_inner, SSFFT_C2C, pl->prec, m, pl->device);
+    if (rc) return rc;
+    pl->bs_m = m;
+    std::vector<T> chirp, wrapped;
+    fill_bluestein_tables<T>(chirp, wrapped, n, m);
+    CU(cudaMalloc(&pl->d_bs_chirp, chirp.size() * sizeof(T)));
+    CU(cudaMemcpy(pl->d_bs_chirp, chirp.data(), chirp.size() * sizeof(T), cudaMemcpyHostToDevice));
+    void *d_wrapped = nullptr;
+    CU(cudaMalloc(&d_wrapped, wrapped.size() * sizeof(T)));
+    CU(cudaMemcpy(d_wrapped, wrapped.data(), wrapped.size() * sizeof(T), cudaMemcpyHostToDevice));
+    CU(cudaMalloc(&pl->d_bs_filter, wrapped.size() * sizeof(T)));
+    rc = ssfft_exec_c2c(pl->bs_inner, d_wrapped, pl->d_bs_filter, 1, SSFFT_FORWARD, nullptr);
+    const cudaError_t e = cudaDeviceSynchronize();
+    cudaFree(d_wrapped);
+    if (rc) return rc;
+    if (e != cudaSuccess) return cuda_fail(e, "bluestein filter");
+    // transforms per pass: two work buffers of at most ~128 MiB each
+    pl->bs_chunk = ((size_t)env_int("SSFFT_BLUESTEIN_MB", 128) << 20) / (m * sizeof(cx<T>));
+    if (pl->bs_chunk < 1) pl->bs_chunk = 1;
+    for (int i = 0; i < 2; ++i) CU(cudaMalloc(&pl->d_bs_work[i], pl->bs_chunk * m * sizeof(cx<T>)));
+    return SSFFT_OK;
+}
+
+template <typename T>
+int exec_bluestein(ssfft_plan *pl, const void *in, void *out, long long batch, int inverse, cudaStream_t s) {
+    const long long n = (long long)pl->n, m = (long long)pl->bs_m;
+    cx<T> *w0 = (cx<T> *)pl->d_bs_work[0], *w1 = (cx<T> *)pl->d_bs_work[1];
+    const cx<T> *chirp = (const cx<T> *)pl->d_bs_chirp, *filt = (const cx<T> *)pl->d_bs_filter;
+    for (long long b0 = 0; b0 < batch; b0 += (long long)pl->bs_chunk) {
+        const long long nb = batch - b0 < (long long)pl->bs_chunk ? batch - b0 : (long long)pl->bs_chunk;
+        const dim3 grid((unsigned)((m + 255) / 256 > 1024 ? 1024 : (m + 255) / 256), (unsigned)(nb > 65535 ? 65535 : nb));
+        bluestein_pre_kernel<T><<<grid, 256, 0, s>>>((const cx<T> *)in + b0 * n, w0, chirp, n, m, nb, inverse);
+        ++g_launches;
+        int rc = ssfft_exec_c2c(pl->bs_inner, w0, w1, (size_t)nb, SSFFT_FORWARD, s);
+        if (rc) return rc;
+        bluestein_mul_kernel<T><<<grid, 256, 0, s>>>(w1, filt, m, nb);
+        ++g_launches;
+        rc = ssfft_exec_c2c(pl->bs_inner, w1, w0, (size_t)nb, SSFFT_INVERSE, s);
+        if (rc) return rc;
+        bluestein_post_kernel<T><<<grid, 256, 0, s>>>(w0, (cx<T> *)out + b0 * n, chirp, n, m, nb, (T)(1.0 / (double)m), inverse);
+        ++g_launches;
+        CU(cudaGetLastError());
+    }
+    return SSFFT_OK;
+}
+
 // Complex core: batch contiguous transforms of length pl->n, in -> out (in == out allowed).
 template <typename T>
 int exec_complex(ssfft_plan *pl, const void *in, void *out, long long batch, int inverse, cudaStream_t s) {
     const long long n = (long long)pl->n;
     if (batch <= 0 || n == 0) return SSFFT_OK;
+    if (pl->bs_inner) return exec_bluestein<T>(pl, in, out, batch, inverse, s);
     if (pl->flat_id >= 0 && pl->kind == SSFFT_C2C) {
         const int rc = exec_flat<T>(pl, in, out, batch, inverse, s);
         if (rc >= 0) return rc;
@@ -520,8 +572,8 @@ int build_plan_typed(ssfft_plan *pl) {
     if (flat_ok) {
         const FlatEntry &e = flat_registry()[pl->flat_id];
         snprintf(buf, sizeof(buf), "complex N=%zu ticket-queue four-step n1=%d x n2=%d (%s): one persistent launch of %d CTAs "
-                 "(%d consumer threads + a TMA producer warp each, ring of %d%s), %d scratch slots = %.1f MiB in L2", n, e.n1, e.n2,
-                 e.name, pl->flat_ctas, e.threads - 32, e.nstage, e.inplace ? " in place" : "", pl->flat_slots, pl->flat_slots * (double)n * sizeof(cx<T>) / 1048576.0);
+                 "(%d consumer threads + TMA producer and signaller warps each, ring of %d%s), %d scratch slots = %.1f MiB in L2", n, e.n1, e.n2,
+                 e.name, pl->flat_ctas, e.threads - kFlatHelpers, e.nstage, e.inplace ? " in place" : "", pl->flat_slots, pl->flat_slots * (double)n * sizeof(cx<T>) / 1048576.0);
         pl->desc = buf;
     } else if (clustered_ok) {
         const int k = pl->kind == SSFFT_C2C ? 0 : 1;
@@ -568,7 +620,21 @@ int build_plan_typed(ssfft_plan *pl) {
         pl->desc = buf;
     } else {
         GenericFourStep fs;
-        if (!plan_generic_fourstep(fs, n, limit)) return SSFFT_ERR_UNSUPPORTED;
+        bool split = plan_generic_fourstep(fs, n, limit);
+        if (split) {  // both legs must fit the pass interpreter (a prime factor above the limit fits neither leg)
+            GenericStage probe_col, probe_row;
+            split = plan_generic_stage(probe_col, fs.n1, sizeof(cx<T>), smem_max) && plan_generic_stage(probe_row, fs.n2, sizeof(cx<T>), smem_max);
+        }
+        if (!split || env_int("SSFFT_FORCE_BLUESTEIN", 0)) {
+            int rc = setup_bluestein<T>(pl);
+            if (rc) return rc;
+            char inner[400] = "";
+            ssfft_plan_describe(pl->bs_inner, inner, sizeof(inner));
+            snprintf(buf, sizeof(buf), "n=%zu Bluestein (largest prime factor fits no on-chip path): convolution of length %zu, "
+                     "%zu transform(s) per pass; inner plan: %.300s", n, pl->bs_m, pl->bs_chunk, inner);
+            pl->desc = buf;
+            goto real_wrappers;
+        }
         const size_t n1 = fs.n1, n2 = fs.n2;
         pl->four_step = true;
         pl->n1 = n1; pl->n2 = n2;
@@ -590,6 +656,7 @@ int build_plan_typed(ssfft_plan *pl) {
         snprintf(buf, sizeof(buf), "n=%zu four-step n1=%zu n2=%zu chunk=%zu (generic x generic)", n, n1, n2, pl->chunk);
         pl->desc = buf;
     }
+real_wrappers:
     if (pl->kind != SSFFT_C2C && !pl->tiled) {
         const bool modified = pl->kind == SSFFT_REAL_MODIFIED;
         // twiddlesMinusI, followed (modified plans) by modifiedRotations so the fused kernel finds both behind one
@@ -843,6 +910,9 @@ int ssfft_plan_destroy(ssfft_plan *pl) {
         if (pl->d_cl_twb[k]) cudaFree(pl->d_cl_twb[k]);
         if (pl->d_cl_tw4[k]) cudaFree(pl->d_cl_tw4[k]);
     }
+    if (pl->bs_inner) ssfft_plan_destroy(pl->bs_inner);
+    for (void *p : {pl->d_bs_chirp, pl->d_bs_filter, pl->d_bs_work[0], pl->d_bs_work[1]})
+        if (p) cudaFree(p);
     for (int i = 0; i < ssfft_plan::kRing; ++i) {
         if (pl->d_ring_in[i]) cudaFree(pl->d_ring_in[i]);
         if (pl->d_ring_out[i]) cudaFree(pl->d_ring_out[i]);

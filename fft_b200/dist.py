@@ -352,3 +352,60 @@ class DistFFT1D:
         recvs = swap(sends)
         outs = new()
         return [self._natural(recvs[r], outs[r]) for r in range(P)]
+
+
+class LocalDistFFT1D:
+    """One length-N complex transform sharded over several GPUs of THIS process, through the C ABI
+    (ssfft_dist_plan_create / ssfft_dist_exec_c2c, include/ssfft.h): exchanges by peer stores over NVLink, the exchange of
+    a chunk under the FFT of the next one, the last exchange straight into the output shards.  `devices` may repeat an
+    index (logical ranks on one GPU).  Shards: lists of CUDA tensors of N / len(devices) complex elements, one per device,
+    block r of the natural order on devices[r]."""
+
+    def __init__(self, n: int, devices, dtype=torch.complex64, transposed_output: bool = False):
+        self.lib = L.load()
+        self.n, self.devices = n, list(devices)
+        self.dtype = dtype
+        prec = L.SSFFT_F32 if dtype == torch.complex64 else L.SSFFT_F64
+        arr = (ctypes.c_int * len(self.devices))(*self.devices)
+        self._plan = ctypes.c_void_p()
+        L.check(self.lib.ssfft_dist_plan_create(ctypes.byref(self._plan), prec, n, len(self.devices), arr,
+                                                1 if transposed_output else 0), f"ssfft_dist_plan_create(n={n})")
+        self.n1 = self.lib.ssfft_dist_plan_factor(self._plan, 0)
+        self.n2 = self.lib.ssfft_dist_plan_factor(self._plan, 1)
+
+    def describe(self) -> str:
+        buf = ctypes.create_string_buffer(1024)
+        self.lib.ssfft_dist_plan_describe(self._plan, buf, 1024)
+        return buf.value.decode()
+
+    def _run(self, xs, outs, direction):
+        P = len(self.devices)
+        assert len(xs) == P and len(outs) == P
+        per = self.n // P
+        for r, (x, o) in enumerate(zip(xs, outs)):
+            assert x.is_cuda and o.is_cuda and x.device.index == self.devices[r] and o.device.index == self.devices[r]
+            assert x.dtype == self.dtype and o.dtype == self.dtype and x.numel() == per and o.numel() == per
+            assert x.is_contiguous() and o.is_contiguous()
+        tin = (ctypes.c_void_p * P)(*[x.data_ptr() for x in xs])
+        tout = (ctypes.c_void_p * P)(*[o.data_ptr() for o in outs])
+        L.check(self.lib.ssfft_dist_exec_c2c(self._plan, tin, tout, direction), "ssfft_dist_exec_c2c")
+
+    def fft(self, xs, outs):
+        self._run(xs, outs, L.SSFFT_FORWARD)
+
+    def ifft(self, xs, outs):
+        self._run(xs, outs, L.SSFFT_INVERSE)
+
+    def synchronize(self):
+        L.check(self.lib.ssfft_dist_synchronize(self._plan), "ssfft_dist_synchronize")
+
+    def close(self):
+        if self._plan:
+            self.lib.ssfft_dist_plan_destroy(self._plan)
+            self._plan = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

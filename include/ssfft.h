@@ -170,6 +170,25 @@ SSFFT_API int ssfft_exchange_transpose(const void *d_src, void *const *d_dst_ptr
                                        int precision, void *stream);
 SSFFT_API int ssfft_memcpy_d2d(void *d_dst, const void *d_src, size_t bytes, void *stream);
 
+/* ---- ONE transform sharded over the GPUs of this process (BASELINE config 5: N = 2^30 on 2 / 4 / 8 GPUs) ----
+ * The reference has no multi-device path; this is the four-step decomposition N = N1 * N2 (the GPU analogue of its
+ * cache-blocking branch, signalsmith-fft.h:130-133) with the all-to-all transposes done by peer stores over NVLink.
+ * devices[r] owns block r of the natural order: d_in_shards[r] / d_out_shards[r] point at N / ndev complex elements in
+ * that device's memory.  exec is asynchronous on streams of the plan; synchronize (or wait, from the caller's own
+ * stream) before reading the output or reusing the input.  A device may be listed several times (logical ranks).
+ * flags: SSFFT_DIST_TRANSPOSED_OUTPUT skips the third exchange, output shard r = rows k1 in [r N1/P, (r+1) N1/P) of
+ * X[k1 + N1 k2], laid out [N1/P][N2].  SSFFT_ERR_UNSUPPORTED: N has no split with both factors divisible by ndev, or
+ * the devices cannot reach each other's memory. */
+#define SSFFT_DIST_TRANSPOSED_OUTPUT 1
+typedef struct ssfft_dist_plan ssfft_dist_plan;
+SSFFT_API int ssfft_dist_plan_create(ssfft_dist_plan **out, int precision, size_t n, int ndev, const int *devices, int flags);
+SSFFT_API int ssfft_dist_plan_destroy(ssfft_dist_plan *plan);
+SSFFT_API int ssfft_dist_plan_describe(const ssfft_dist_plan *plan, char *buf, size_t buflen);
+SSFFT_API size_t ssfft_dist_plan_factor(const ssfft_dist_plan *plan, int which); /* 0: N1, 1: N2 */
+SSFFT_API int ssfft_dist_exec_c2c(ssfft_dist_plan *plan, void *const *d_in_shards, void *const *d_out_shards, int direction);
+SSFFT_API int ssfft_dist_synchronize(ssfft_dist_plan *plan);
+SSFFT_API int ssfft_dist_wait(ssfft_dist_plan *plan, int r, void *stream);
+
 /* ---- diagnostics ---- */
 SSFFT_API const char *ssfft_error_string(int status);
 SSFFT_API const char *ssfft_last_cuda_error(void);

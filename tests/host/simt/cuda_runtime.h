@@ -53,6 +53,7 @@ template <typename V> inline void __stcs(V *p, V v) { simt_check_aligned(p, size
 
 void __syncthreads();  // yields to the block scheduler (simt_emul.h)
 inline void __threadfence() {}
+inline void __threadfence_block() {}
 inline void __nanosleep(unsigned) {}
 inline long long clock64() { return 0; }
 [[noreturn]] inline void __trap() { abort(); }

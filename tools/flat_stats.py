@@ -16,7 +16,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 V = "SSFFT_FLAT_VARIANT"
 VARIANTS = [("ring2 3/SM in place", {}), ("ring1 3/SM separate", {V: "1,3,0"}), ("ring3 2/SM in place", {V: "3,2,1"})]
 
-for lib in ("libssfft_stats.so", "libssfft_nocompute.so"):
+for lib in ("libssfft_stats.so", "libssfft_nocompute.so", "libssfft_nodeps.so"):
     path = os.path.join(ROOT, "fft_b200", lib)
     if not os.path.exists(path):
         continue
