@@ -40,6 +40,10 @@ struct FlatParams {
     const cx<T> *tw_b;      // row-stage pass twiddles ([r-1][m'] as in tiled.cuh)
     const cx<T> *ga[2], *gb[2];  // per non-last column pass p: W_(N1/P)^(m'*2^k) [N1/(P R)][LOG R]  and  W_(N/P)^(n2*2^k) [N2][LOG R]
     const cx<T> *s4;        // W_N^(n2*P_last*r) [N2][R_last]
+    // real transforms (RealFFT<V>::fft / ifft, signalsmith-fft.h:446-502, on the complex length M = N1 * N2, N = 2 M):
+    //   R2C post-twiddle  -i W_N^k / 2,  k = k1 + N1 k2:   ra[k1] = W_N^k1 (k1 < N1),  rb[k2] = -i W_(2 N2)^k2 / 2 (k2 < N2)
+    //   C2R pre-twiddle  conj(-i W_N^n), n = n1 N2 + n2:   ra[n1] = i conj(W_(2 N1)^n1) (n1 < N1),  rb[n2] = conj(W_N^n2) (n2 < N2)
+    const cx<T> *ra, *rb;
     unsigned *ctrl;         // [0] ticket counter; cnt1 = ctrl + 32; cnt2 = cnt1 + cap
     long long batch, user_stride, scratch_per, cap;
     int nslots, delay, discard;
@@ -69,15 +73,20 @@ __host__ __device__ constexpr int flat_topbit(int v) { return 1 << flat_ilog2(v)
 // so a ring of two fits three CTAs per SM; otherwise one separate exchange buffer, dense slots and a small ring of s4
 // slices.  The row-stage pass table lives in shared memory when it is small (two-pass row tiles), else it is read
 // through L1 like the column-stage tables.
-template <typename CfgA, typename CfgB, int NSTAGE, bool INPLACE>
+template <typename CfgA, typename CfgB, int NSTAGE, bool INPLACE, int KIND = 0>
 struct FlatLayout {
     using T = typename CfgA::T;
     static constexpr size_t al(size_t v) { return (v + 127) / 128 * 128; }
-    static constexpr size_t kTileA = (size_t)CfgA::L * CfgA::CT * sizeof(cx<T>), kTileB = (size_t)CfgB::L * CfgB::CT * sizeof(cx<T>);
+    // column tile: dense [L][CT]; C2R: two boxes [L][CT/2] (the second 64 bytes further) + the 2-column box of column N2/2
+    static constexpr size_t kTileA = (size_t)CfgA::L * CfgA::CT * sizeof(cx<T>);
+    static constexpr size_t kSlotA = KIND == 2 ? kTileA + 2 * 8 * sizeof(cx<T>) + (size_t)CfgA::L * 2 * sizeof(cx<T>) : kTileA;
+    // row tile: dense [L][CT]; R2C: two blocks [L][CT/2], the second 64 bytes further
+    static constexpr size_t kTileB = (size_t)CfgB::L * CfgB::CT * sizeof(cx<T>);
+    static constexpr size_t kSlotB = KIND == 1 ? kTileB + 2 * 8 * sizeof(cx<T>) : kTileB;
     static constexpr size_t kExchA = CfgA::smem_bytes, kExchB = CfgB::smem_bytes;
     static constexpr size_t kExch = al(kExchA > kExchB ? kExchA : kExchB);
-    static constexpr size_t kSBlk = al((size_t)CfgA::CT * CfgA::radix(CfgA::NP - 1) * sizeof(cx<T>));
-    static constexpr size_t kSlot = INPLACE ? kExch + kSBlk : al(kTileA > kTileB ? kTileA : kTileB);
+    static constexpr size_t kSBlk = KIND == 2 ? 0 : al((size_t)CfgA::CT * CfgA::radix(CfgA::NP - 1) * sizeof(cx<T>));
+    static constexpr size_t kSlot = INPLACE ? kExch + kSBlk : al(kSlotA > kSlotB ? kSlotA : kSlotB);
     static constexpr bool kTwBShared = (size_t)CfgB::tw_total * sizeof(cx<T>) <= 2048;
     static constexpr size_t kTwB = kTwBShared ? al((size_t)(CfgB::tw_total > 0 ? CfgB::tw_total : 1) * sizeof(cx<T>)) : 0;
     static constexpr size_t oExch = 0, oSlots = oExch + (INPLACE ? 0 : kExch), oSBlk = oSlots + NSTAGE * kSlot,
@@ -104,11 +113,15 @@ inline void consumer_barrier(int n) { simt::named_barrier(1, (unsigned)n); }
 inline void producer_idle() { simt::spin_yield(); }
 inline void producer_moved() { simt::state().progress = true; }  // global counters changed: not a deadlock
 inline void fence_proxy_async() {}
+// a TMA box may start at any column and hang over the edge of the tensor (zero fill): element-wise on the CPU
 template <typename T>
 inline void tma_tile_3d(cx<T> *dst, const void *, const cx<T> *in, int n1, int n2, int box_rows, int ct, int col0, int row0, long long b,
                         unsigned long long *bar) {
     for (int r = 0; r < box_rows; ++r)
-        bulk_g2s(dst + (size_t)r * ct, in + b * (long long)n1 * n2 + (long long)(row0 + r) * n2 + col0, (unsigned)(ct * sizeof(cx<T>)), bar);
+        for (int c = 0; c < ct; ++c) {
+            if (col0 + c < n2) simt::tma_copy(dst + (size_t)r * ct + c, in + b * (long long)n1 * n2 + (long long)(row0 + r) * n2 + col0 + c, (unsigned)sizeof(cx<T>), bar);
+            else simt::tma_zero(dst + (size_t)r * ct + c, (unsigned)sizeof(cx<T>), bar);
+        }
 }
 #else
 __device__ __forceinline__ void mbar_arrive(unsigned long long *bar) {
@@ -193,9 +206,14 @@ __device__ __forceinline__ void apply_powers(cx<T> (&w)[R], const cx<T> (&pw2)[f
 // Pass p (radix R, P = product of the earlier radices, butterfly b: m' = b / P, racc = b % P) writes digit r of
 // k1 = sum_p P_p r_p; its inter-pass twiddle W_L^(P m' r) and the factor W_N^(n2 P r) of the four-step twiddle are the
 // powers g^r of g = W_(L/P)^(m') * W_(N/P)^(n2) (tables ga[p], gb[p]); the last pass multiplies by s4[n2][r].
-template <typename Cfg, int INV, int N2C, int CTBLOG, bool INPLACE, typename T, typename Release>
-__device__ __forceinline__ void flat_stage_a(const FlatParams<T> &q, const cx<T> *st, const cx<T> *sb, cx<T> *sm, cx<T> *scr, int lane0,
+// KIND 0: complex.  KIND 1 (R2C): the same column FFT of the sample pairs, but row k1 of the scratch is stored at position
+// rho(k1) (flat_rho) so that the rows the post-twiddle pairs, k1 and N1 - k1, sit in two blocks of CTB rows that one row
+// tile loads.  KIND 2 (C2R): the tile is CT/2 low columns and their CT/2 partner columns N2 - n2 (two TMA boxes); the
+// pre-twiddle of RealFFT::ifft (:478-492) is applied while the first pass gathers; `tile` is the tile index.
+template <typename Cfg, int INV, int N2C, int CTBLOG, bool INPLACE, int KIND, typename T, typename Release>
+__device__ __forceinline__ void flat_stage_a(const FlatParams<T> &q, const cx<T> *st, const cx<T> *sb, cx<T> *sm, cx<T> *scr, int tile,
                                              int tid, Release release) {
+    const int lane0 = tile * Cfg::CT;
     constexpr int L = Cfg::L, TX = Cfg::TX, CT = Cfg::CT, E = Cfg::E, PITCH = Cfg::PITCH, NC = Cfg::THREADS, NP = Cfg::NP;
     static_assert(NP == 2 || NP == 3, "two or three passes per tile");
     constexpr int CTB = 1 << CTBLOG;
@@ -204,6 +222,17 @@ __device__ __forceinline__ void flat_stage_a(const FlatParams<T> &q, const cx<T>
     static_assert(RL % 2 == 0, "pairs of last-pass twiddles are loaded together");
     const int c = tid % CT, t = tid / CT;    // lanes along the columns (global / ring accesses)
     const int t2 = tid % TX, c2 = tid / TX;  // last pass: lanes along k1 (scratch written in runs of consecutive k1)
+    static_assert(KIND == 0 || !INPLACE, "the real flavours use the separate exchange buffer");
+    // column of a lane: contiguous, or (C2R) low half / mirrored high half, lane CT-1 of tile 0 = the self-paired N2/2
+    auto col_of = [&](int lane) -> int {
+        if constexpr (KIND != 2) return lane0 + lane;
+        else {
+            constexpr int H = CT / 2;
+            if (lane < H) return tile * H + lane;
+            if (tile == 0 && lane == CT - 1) return N2C / 2;
+            return N2C - tile * H - (CT - 1 - lane);
+        }
+    };
     cx<T> v[E];
     sfor<0, NP>([&](auto pc) {
         constexpr int ps = decltype(pc)::value;
@@ -211,7 +240,30 @@ __device__ __forceinline__ void flat_stage_a(const FlatParams<T> &q, const cx<T>
         constexpr bool first = ps == 0, last = ps == NP - 1;
         static_assert((1 << LOG) == R && (P & (P - 1)) == 0, "power-of-two radices");
         const int tt = last ? t2 : t, cc = last ? c2 : c;
-        if constexpr (first) {
+        if constexpr (first && KIND == 2) {
+            // ring slot: [2][L][H] (high half 8 elements further: other banks), then the 2-column box of column N2/2
+            constexpr int H = CT / 2, HALF = L * H + 8;
+            const bool lane_self0 = tile == 0 && c == 0, lane_selfm = tile == 0 && c == CT - 1;
+            const cx<T> *own = lane_selfm ? st + 2 * HALF : st + (c / H) * HALF + (c % H);
+            const int own_pitch = lane_selfm ? 2 : H;
+            const int pc_ = CT - 1 - c;
+            const cx<T> *par = (lane_self0 || lane_selfm) ? own : st + (pc_ / H) * HALF + (pc_ % H);
+            const cx<T> cb = ld_table(q.rb + col_of(c));
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+#pragma unroll
+                for (int j = 0; j < R; ++j) {
+                    const int n1 = t + TX * u + NR * j;
+                    const int n1p = lane_self0 ? ((L - n1) & (L - 1)) : L - 1 - n1;
+                    const cx<T> xo = own[n1 * own_pitch], xp = par[n1p * own_pitch];
+                    const cx<T> tc = cmul(ld_table(q.ra + n1), cb);  // conj(-i W_N^n)
+                    const cx<T> sum = mk<T>(xo.x + xp.x, xo.y - xp.y), dif = mk<T>(xo.x - xp.x, xo.y + xp.y);  // X +- conj X'
+                    cx<T> z = sum + cmul(dif, tc);
+                    if (lane_self0 && n1 == 0) z = mk<T>(xo.x + xo.y, xo.x - xo.y);  // bin 0 packs (DC, Nyquist) (:478-481)
+                    v[u * R + j] = cswap(z);  // inverse transform = forward transform of the swapped data
+                }
+            release();
+        } else if constexpr (first) {
 #pragma unroll
             for (int u = 0; u < U; ++u)
 #pragma unroll
@@ -235,7 +287,7 @@ __device__ __forceinline__ void flat_stage_a(const FlatParams<T> &q, const cx<T>
                 cx<T> g[LOG];
                 {
                     cx<T> ga[LOG], gb[LOG];
-                    const cx<T> *pa = q.ga[ps] + mp * LOG, *pb = q.gb[ps] + (lane0 + cc) * LOG;
+                    const cx<T> *pa = q.ga[ps] + mp * LOG, *pb = q.gb[ps] + col_of(cc) * LOG;
                     if constexpr (LOG % 2 == 0) {
 #pragma unroll
                         for (int k = 0; k < LOG; k += 2) {
@@ -265,8 +317,14 @@ __device__ __forceinline__ void flat_stage_a(const FlatParams<T> &q, const cx<T>
             consumer_barrier(NC);
         } else {
             cx<T> s[R];
+            const int n2 = col_of(cc);
+            if constexpr (KIND == 2) {  // scattered columns: the slice of s4 comes through L1 instead of the ring
 #pragma unroll
-            for (int r = 0; r < R; r += 2) ld_pair_shared(sb + cc * R + r, s[r], s[r + 1]);
+                for (int r = 0; r < R; r += 2) ld_pair_global(q.s4 + (long long)n2 * R + r, s[r], s[r + 1]);
+            } else {
+#pragma unroll
+                for (int r = 0; r < R; r += 2) ld_pair_shared(sb + cc * R + r, s[r], s[r + 1]);
+            }
             if constexpr (INPLACE) release();  // tile and twiddle slice are in registers: the slot may be refilled
 #pragma unroll
             for (int u = 0; u < U; ++u) {
@@ -275,16 +333,141 @@ __device__ __forceinline__ void flat_stage_a(const FlatParams<T> &q, const cx<T>
                 for (int j = 0; j < R; ++j) w[j] = v[u * R + j];
                 if constexpr (!SSFFT_FLAT_NOCOMPUTE) Dft<R>::run(w);
                 const int b = tt + TX * u;  // k1 = b + P * r lives at block k1 / CTB, row k1 % CTB of the tile-major scratch
-                if constexpr (P % CTB == 0) {
-                    cx<T> *dst = scr + (long long)(b >> CTBLOG) * ((long long)CTB * N2C) + (long long)(lane0 + cc) * CTB + (b & (CTB - 1));
+                if constexpr (KIND == 1) {
+                    // rho(k1): k1 < L/2 stays, k1 > L/2 moves down one row, L/2 goes to the last row (flat_rho).  k1 < L/2
+                    // exactly for r < R/2, so both halves are base + immediate; (b, r) = (0, R/2) is the one exception.
+                    static_assert(P % CTB == 0 && R % 2 == 0, "scratch blocks must nest in the last-pass stride");
+                    const long long blk = (long long)CTB * N2C;
+                    cx<T> *lo = scr + (long long)(b >> CTBLOG) * blk + (long long)n2 * CTB + (b & (CTB - 1));
+                    const int bm = b - 1;  // arithmetic shift / mask: floor semantics for b = 0
+                    cx<T> *hi = scr + (long long)(bm >> CTBLOG) * blk + (long long)n2 * CTB + (bm & (CTB - 1));
+                    cx<T> *mid = scr + (long long)((L - 1) >> CTBLOG) * blk + (long long)n2 * CTB + ((L - 1) & (CTB - 1));
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {
+                        const cx<T> val = cmul(w[r], s[r]);
+                        cx<T> *dst = (r < R / 2 ? lo : hi) + (long long)r * (P / CTB) * blk;
+                        if (r == R / 2 && b == 0) dst = mid;
+                        st_plain(dst, val);
+                    }
+                } else if constexpr (P % CTB == 0) {
+                    cx<T> *dst = scr + (long long)(b >> CTBLOG) * ((long long)CTB * N2C) + (long long)n2 * CTB + (b & (CTB - 1));
 #pragma unroll
                     for (int r = 0; r < R; ++r) st_plain(dst + (long long)r * (P / CTB) * ((long long)CTB * N2C), SSFFT_FLAT_NOCOMPUTE ? w[r] + s[r] : cmul(w[r], s[r]));
                 } else {
                     constexpr int Q = CTB / P;
-                    cx<T> *dst = scr + (long long)(lane0 + cc) * CTB + b;
+                    cx<T> *dst = scr + (long long)n2 * CTB + b;
 #pragma unroll
                     for (int r = 0; r < R; ++r) st_plain(dst + (long long)(r / Q) * ((long long)CTB * N2C) + P * (r % Q), SSFFT_FLAT_NOCOMPUTE ? w[r] + s[r] : cmul(w[r], s[r]));
                 }
+            }
+        }
+    });
+}
+
+// Position of row k1 of the R2C intermediate in the scratch (n1 rows): the post-twiddle pairs row k1 with row n1 - k1, so
+// the upper half is stored one row down (block [n1 - HB t - HB, n1 - HB t) then holds exactly the partners of block t's
+// rows) and the self-paired row n1/2 takes the slot that frees at the very end.
+__host__ __device__ constexpr int flat_rho(int k1, int n1) { return k1 < n1 / 2 ? k1 : k1 == n1 / 2 ? n1 - 1 : k1 - 1; }
+
+// ---- row tile of a real forward transform: HB = CT/2 rows k1 = HB tile + l and their partners n1 - k1 (two scratch
+// blocks of HB rows), length-L FFT each, then RealFFT::fft's post-twiddle (:459-472) on the pairs
+// (k1, k2) <-> (n1 - k1, L - 1 - k2) through the exchange buffer, stored as bins k = k1 + n1 k2 of the half spectrum.
+template <typename Cfg, int N1C, bool TWSH, typename T, typename Release>
+__device__ __forceinline__ void flat_stage_b_r2c(const FlatParams<T> &q, const cx<T> *twb, const cx<T> *st, cx<T> *sm, cx<T> *uout,
+                                                 int tile, int tid, Release release) {
+    constexpr int L = Cfg::L, TX = Cfg::TX, CT = Cfg::CT, E = Cfg::E, PITCH = Cfg::PITCH, NC = Cfg::THREADS, NP = Cfg::NP;
+    constexpr int H = CT / 2, HALF = L * H + 8;  // ring slot: [2][L][H], the high block 8 elements further (other banks)
+    static_assert(NP == 2 || NP == 3, "two or three passes per tile");
+    const int c = tid % CT, t = tid / CT;
+    cx<T> v[E];
+    sfor<0, NP>([&](auto pc) {
+        constexpr int ps = decltype(pc)::value;
+        constexpr int R = Cfg::radix(ps), P = Cfg::prod(ps), NR = L / R, U = E / R, MN = Cfg::mnext(ps);
+        constexpr bool first = ps == 0, last = ps == NP - 1;
+        if constexpr (first) {
+            const cx<T> *src = st + (c / H) * HALF + (c % H);
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+#pragma unroll
+                for (int j = 0; j < R; ++j) v[u * R + j] = src[(t + TX * u + NR * j) * H];
+            release();
+        } else {
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+#pragma unroll
+                for (int j = 0; j < R; ++j) v[u * R + j] = sm[(t + TX * u + NR * j) * PITCH + c];
+            consumer_barrier(NC);
+        }
+        if constexpr (!last) {
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int b = t + TX * u, mp = b / P, racc = b % P;
+                cx<T> w[R];
+#pragma unroll
+                for (int j = 0; j < R; ++j) w[j] = v[u * R + j];
+                Dft<R>::run(w);
+                const cx<T> *twp = twb + Cfg::tw_off(ps) + mp;
+#pragma unroll
+                for (int r = 1; r < R; ++r) w[r] = cmul(w[r], TWSH ? twp[(r - 1) * MN] : ld_table(twp + (r - 1) * MN));
+                const int o = racc + P * R * mp;
+#pragma unroll
+                for (int r = 0; r < R; ++r) sm[(o + P * r) * PITCH + c] = w[r];
+            }
+            consumer_barrier(NC);
+        } else {
+            static_assert(R % 2 == 0, "the pairs split the last-pass outputs in halves");
+            // Z[k2][lane] into the exchange buffer, k2 = b + P r
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                cx<T> w[R];
+#pragma unroll
+                for (int j = 0; j < R; ++j) w[j] = v[u * R + j];
+                Dft<R>::run(w);
+                const int b = t + TX * u;
+#pragma unroll
+                for (int r = 0; r < R; ++r) { sm[(b + P * r) * PITCH + c] = w[r]; v[u * R + r] = w[r]; }
+            }
+            consumer_barrier(NC);
+            // my rows: lane -> k1; pairs (k1, k2 < L/2) <-> (n1 - k1, L - 1 - k2) are handled by the owner of the first element
+            const bool row0 = tile == 0 && c == 0, rowm = tile == 0 && c == CT - 1;
+            const int k1 = c < H ? tile * H + c : rowm ? N1C / 2 : N1C - tile * H - (CT - 1 - c);
+            const int pl = (row0 || rowm) ? c : CT - 1 - c;  // partner lane (rows 0 and n1/2 pair with themselves)
+            const cx<T> ta = ld_table(q.ra + k1);
+            cx<T> zp[U * (R / 2)];
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+#pragma unroll
+                for (int r = 0; r < R / 2; ++r) {
+                    const int k2 = t + TX * u + P * r;
+                    const int kp = row0 ? ((L - k2) & (L - 1)) : L - 1 - k2;
+                    zp[u * (R / 2) + r] = sm[kp * PITCH + pl];
+                }
+            cx<T> zmid = mk<T>((T)0, (T)0);
+            if (row0 && t == 0) zmid = sm[(L / 2) * PITCH];  // bin M/2 pairs with itself
+            consumer_barrier(NC);  // partners are in registers: the next tile may overwrite the exchange buffer
+            const int kph = (N1C - k1) & (N1C - 1);  // partner row (0 for row 0)
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+#pragma unroll
+                for (int r = 0; r < R / 2; ++r) {
+                    const int k2 = t + TX * u + P * r;
+                    const cx<T> zm = v[u * R + r], zq = zp[u * (R / 2) + r];
+                    if (row0 && k2 == 0) {  // (DC, Nyquist) packed in bin 0 (:459-462)
+                        st_stream(uout, mk<T>(zm.x + zm.y, zm.x - zm.y));
+                        continue;
+                    }
+                    const cx<T> tw = cmul(ta, ld_table(q.rb + k2));  // -i W_N^k / 2
+                    const cx<T> sum = mk<T>(zm.x + zq.x, zm.y - zq.y), dif = mk<T>(zm.x - zq.x, zm.y + zq.y);  // Z +- conj Z'
+                    const cx<T> rot = cmul(dif, tw), hs = mk<T>((T)0.5 * sum.x, (T)0.5 * sum.y);
+                    const int kp = row0 ? L - k2 : L - 1 - k2;
+                    st_stream(uout + k1 + (long long)N1C * k2, hs + rot);
+                    st_stream(uout + kph + (long long)N1C * kp, mk<T>(hs.x - rot.x, rot.y - hs.y));  // conj(hs - rot)
+                }
+            if (row0 && t == 0) {  // bin M/2 (k1 = 0, k2 = L/2): its own partner
+                const cx<T> tw = cmul(ta, ld_table(q.rb + L / 2));
+                const cx<T> sum = mk<T>(zmid.x + zmid.x, (T)0), dif = mk<T>((T)0, zmid.y + zmid.y);
+                const cx<T> rot = cmul(dif, tw), hs = mk<T>((T)0.5 * sum.x, (T)0.5 * sum.y);
+                st_stream(uout + (long long)N1C * (L / 2), mk<T>(hs.x - rot.x, rot.y - hs.y));
             }
         }
     });
@@ -344,18 +527,23 @@ __device__ __forceinline__ void flat_stage_b(const cx<T> *twb, const cx<T> *st, 
 }
 
 // KIND 0: C2C.  (real flavours stay on the cluster kernel of tiled.cuh for now)
-template <typename CfgA, typename CfgB, int INV, int NSTAGE, int MINB, bool INPLACE>
+// KIND 0: complex (INV = direction).  KIND 1: RealFFT forward on the sample pairs (INV = 0).  KIND 2: RealFFT inverse
+// (INV = 1).  tmap: boxes [box rows][CT] (KIND 2: [box rows][CT/2]) of the (batch, N1, N2) input; tmap2 (KIND 2 only):
+// boxes [box rows][2], for the self-paired column N2/2.
+template <typename CfgA, typename CfgB, int INV, int NSTAGE, int MINB, bool INPLACE, int KIND = 0>
 __global__ void __launch_bounds__(CfgA::THREADS + kFlatHelpers, MINB)
-fourstep_flat_kernel(FlatParams<typename CfgA::T> q, const __grid_constant__ CUtensorMap tmap) {
+fourstep_flat_kernel(FlatParams<typename CfgA::T> q, const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap2) {
     using T = typename CfgA::T;
-    using Lay = FlatLayout<CfgA, CfgB, NSTAGE, INPLACE>;
+    using Lay = FlatLayout<CfgA, CfgB, NSTAGE, INPLACE, KIND>;
+    static_assert(KIND == 0 || (!INPLACE && INV == (KIND == 2)), "real flavours: separate exchange buffer, fixed direction");
     static_assert(CfgA::THREADS == CfgB::THREADS, "both stages must use the same CTA size");
     constexpr int NC = CfgA::THREADS;
     constexpr int N1 = CfgA::L, N2 = CfgB::L;
     constexpr int tiles1 = N2 / CfgA::CT, tiles2 = N1 / CfgB::CT, PT = tiles1 + tiles2;
     static_assert(N2 % CfgA::CT == 0 && N1 % CfgB::CT == 0, "whole tiles");
-    constexpr int kCtbLog = flat_ilog2(CfgB::CT);
-    static_assert((1 << kCtbLog) == CfgB::CT, "row-stage tile width must be a power of two");
+    constexpr int kCtb = KIND == 1 ? CfgB::CT / 2 : CfgB::CT;  // rows per scratch block (R2C: half a tile, see flat_rho)
+    constexpr int kCtbLog = flat_ilog2(kCtb);
+    static_assert((1 << kCtbLog) == kCtb, "row-stage tile width must be a power of two");
     constexpr int NDONE = NSTAGE + 1;
     SSFFT_DYNAMIC_SMEM(ssfft_smem);
     cx<T> *exch = reinterpret_cast<cx<T> *>(ssfft_smem + Lay::oExch);
@@ -471,17 +659,40 @@ fourstep_flat_kernel(FlatParams<typename CfgA::T> q, const __grid_constant__ CUt
                         desc[s] = cur;
                         hist[issued % NDONE] = cur;
                         cx<T> *slot = reinterpret_cast<cx<T> *>(ssfft_smem + Lay::oSlots + (size_t)s * Lay::kSlot);
-                        if (cur.kind == 0) {
+                        constexpr int kBoxRows = N1 > 256 ? 256 : N1;
+                        if (cur.kind == 0 && KIND == 2) {
+                            // low columns [H t, H t + H), their partners [N2 - H t - H + 1, N2 - H t] (for t = 0 the last one
+                            // is outside the tensor: zero fill, unused) and, for t = 0, the self-paired column N2/2
+                            constexpr int H = CfgA::CT / 2, HALF = N1 * H + 8;
+                            constexpr unsigned side = (unsigned)(N1 * 2 * sizeof(cx<T>));
+                            mbar_expect_tx(&full[s], (unsigned)Lay::kTileA + (cur.tile == 0 ? side : 0u));
+#pragma unroll
+                            for (int r0 = 0; r0 < N1; r0 += kBoxRows) {
+                                tma_tile_3d<T>(slot + (size_t)r0 * H, &tmap, q.in, N1, N2, kBoxRows, H, cur.tile * H, r0, cur.b, &full[s]);
+                                tma_tile_3d<T>(slot + HALF + (size_t)r0 * H, &tmap, q.in, N1, N2, kBoxRows, H, N2 - cur.tile * H - H + 1, r0,
+                                               cur.b, &full[s]);
+                                if (cur.tile == 0)
+                                    tma_tile_3d<T>(slot + 2 * HALF + (size_t)r0 * 2, &tmap2, q.in, N1, N2, kBoxRows, 2, N2 / 2, r0, cur.b, &full[s]);
+                            }
+                        } else if (cur.kind == 0) {
                             cx<T> *sblk = INPLACE ? reinterpret_cast<cx<T> *>(reinterpret_cast<unsigned char *>(slot) + Lay::kExch)
                                                   : reinterpret_cast<cx<T> *>(ssfft_smem + Lay::oSBlk + (size_t)(issued % NDONE) * Lay::kSBlk);
                             constexpr unsigned sbytes = (unsigned)(CfgA::CT * CfgA::radix(CfgA::NP - 1) * sizeof(cx<T>));
                             mbar_expect_tx(&full[s], (unsigned)Lay::kTileA + sbytes);
-                            constexpr int kBoxRows = N1 > 256 ? 256 : N1;
 #pragma unroll
                             for (int r0 = 0; r0 < N1; r0 += kBoxRows)
                                 tma_tile_3d<T>(slot + (size_t)r0 * CfgA::CT, &tmap, q.in, N1, N2, kBoxRows, CfgA::CT, cur.tile * CfgA::CT, r0,
                                                cur.b, &full[s]);
                             bulk_g2s(sblk, q.s4 + (long long)cur.tile * CfgA::CT * CfgA::radix(CfgA::NP - 1), sbytes, &full[s]);
+                        } else if (KIND == 1) {
+                            // scratch blocks of H rows: block t (rows H t ...) and block N1/H - 1 - t (their partners, flat_rho)
+                            constexpr int H = CfgB::CT / 2, HALF = N2 * H + 8;
+                            constexpr unsigned half_bytes = (unsigned)(N2 * H * sizeof(cx<T>));
+                            mbar_expect_tx(&full[s], 2 * half_bytes);
+                            fence_proxy_async();
+                            const cx<T> *scr = q.scratch + (cur.b % q.nslots) * q.scratch_per;
+                            bulk_g2s(slot, scr + (long long)cur.tile * H * N2, half_bytes, &full[s]);
+                            bulk_g2s(slot + HALF, scr + (long long)(N1 / H - 1 - cur.tile) * H * N2, half_bytes, &full[s]);
                         } else {
                             mbar_expect_tx(&full[s], (unsigned)Lay::kTileB);
                             fence_proxy_async();  // other CTAs' generic-proxy scratch stores -> async-proxy read
@@ -541,7 +752,15 @@ fourstep_flat_kernel(FlatParams<typename CfgA::T> q, const __grid_constant__ CUt
         if (d.kind == 0) {
             const cx<T> *sblk = INPLACE ? reinterpret_cast<const cx<T> *>(reinterpret_cast<const unsigned char *>(st) + Lay::kExch)
                                         : reinterpret_cast<const cx<T> *>(ssfft_smem + Lay::oSBlk + (size_t)(j % NDONE) * Lay::kSBlk);
-            flat_stage_a<CfgA, INV, N2, kCtbLog, INPLACE>(q, st, sblk, xb, scr, d.tile * CfgA::CT, tid, release);
+            flat_stage_a<CfgA, INV, N2, kCtbLog, INPLACE, KIND>(q, st, sblk, xb, scr, d.tile, tid, release);
+        } else if constexpr (KIND == 1) {
+            if (q.discard) {
+                constexpr int H = CfgB::CT / 2, kLines = (int)(N2 * H * sizeof(cx<T>) / 128);
+                const char *lo = reinterpret_cast<const char *>(scr + (long long)d.tile * H * N2);
+                const char *hi = reinterpret_cast<const char *>(scr + (long long)(N1 / H - 1 - d.tile) * H * N2);
+                for (int i = tid; i < 2 * kLines; i += NC) discard_l2_line((i < kLines ? lo : hi - (size_t)kLines * 128) + (size_t)i * 128);
+            }
+            flat_stage_b_r2c<CfgB, N1, Lay::kTwBShared>(q, twb, st, xb, q.out + d.b * q.user_stride, d.tile, tid, release);
         } else {
             if (q.discard) {  // the block is in shared memory now: drop its lines from L2 without a write-back
                 constexpr int kLines = (int)(Lay::kTileB / 128);
@@ -575,19 +794,22 @@ struct FlatEntry {
     int rb[3], nb_passes;
     int (*launch[2])(const void *params, int ctas, cudaStream_t s);  // [inverse]; params: FlatParams<T>; 3 = no tensor map
     int (*max_ctas[2])();                                            // co-resident CTAs on the current device
+    // RealFFT of length 2 n1 n2 on the same tiles (entries with a separate exchange buffer only): [0] forward, [1] inverse
+    int (*launch_real[2])(const void *params, int ctas, cudaStream_t s);
+    int (*max_ctas_real[2])();
 };
 const std::vector<FlatEntry> &flat_registry();
 
 // first registered entry of the size, or the variant named by SSFFT_FLAT_VARIANT="ring,ctas_per_sm[,inplace]"
 template <typename T>
-inline int find_flat(size_t n1, size_t n2) {
+inline int find_flat(size_t n1, size_t n2, bool need_real = false) {
     const int prec = sizeof(T) == 4 ? 0 : 1;
     const auto &reg = flat_registry();
     int want_ring = 0, want_minb = 0, want_inplace = 1;
     if (const char *e = getenv("SSFFT_FLAT_VARIANT")) sscanf(e, "%d,%d,%d", &want_ring, &want_minb, &want_inplace);
     int first = -1;
     for (size_t i = 0; i < reg.size(); ++i)
-        if (reg[i].prec == prec && (size_t)reg[i].n1 == n1 && (size_t)reg[i].n2 == n2) {
+        if (reg[i].prec == prec && (size_t)reg[i].n1 == n1 && (size_t)reg[i].n2 == n2 && (!need_real || reg[i].launch_real[0])) {
             if (first < 0) first = (int)i;
             if (reg[i].nstage == want_ring && reg[i].minb == want_minb && reg[i].inplace == want_inplace) return (int)i;
         }
@@ -626,6 +848,34 @@ inline void fill_flat_tables(std::vector<T> (&ga)[2], std::vector<T> (&gb)[2], s
     for (size_t c = 0; c < n2; ++c)
         for (int r = 0; r < RL; ++r) flat_root<T>(&s4[2 * (c * RL + r)], (unsigned long long)c * P * r, n);
 }
+// Real-transform twiddles (complex length M = n1 * n2, real length N = 2 M), see FlatParams::ra / rb
+template <typename T>
+inline void fill_flat_real_tables(std::vector<T> &ra, std::vector<T> &rb, size_t n1, size_t n2, bool inverse) {
+    const size_t big = 2 * n1 * n2;
+    ra.assign(2 * n1, (T)0);
+    rb.assign(2 * n2, (T)0);
+    const long double pi2 = 2.0L * 3.14159265358979323846264338327950288L;
+    if (!inverse) {
+        for (size_t k1 = 0; k1 < n1; ++k1) flat_root<T>(&ra[2 * k1], k1, big);              // W_N^k1
+        for (size_t k2 = 0; k2 < n2; ++k2) {                                                  // -i W_(2 n2)^k2 / 2
+            const long double a = pi2 * (long double)k2 / (long double)(2 * n2);
+            rb[2 * k2] = (T)(-0.5L * sinl(a));
+            rb[2 * k2 + 1] = (T)(-0.5L * cosl(a));
+        }
+    } else {
+        for (size_t j = 0; j < n1; ++j) {                                                     // i conj(W_(2 n1)^j) = i e^{+ia} = (-sin a, cos a)
+            const long double a = pi2 * (long double)j / (long double)(2 * n1);
+            ra[2 * j] = (T)(-sinl(a));
+            ra[2 * j + 1] = (T)cosl(a);
+        }
+        for (size_t c = 0; c < n2; ++c) {                                                     // conj(W_N^c)
+            const long double a = pi2 * (long double)c / (long double)big;
+            rb[2 * c] = (T)cosl(a);
+            rb[2 * c + 1] = (T)sinl(a);
+        }
+    }
+}
+
 // row-stage pass table, same layout as build_tile_twiddles ([r-1][m'] per pass)
 template <typename T>
 inline void fill_flat_row_twiddles(std::vector<T> &h, int n2, const int *radix, int passes, int tw_total) {

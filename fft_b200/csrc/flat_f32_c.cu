@@ -1,15 +1,12 @@
-// ticket-queue four-step kernels (flat.cuh), fp32, 2^17 and 2^18 (512-point leg: three radix-8 passes, 8 lanes per tile).  The first entry of a size is its default; the others are
-// selected with SSFFT_FLAT_VARIANT="ring,ctas_per_sm,inplace" (A/B measurements).
+// ticket-queue four-step kernels (flat.cuh), fp32, 2^17 and 2^18 (512-point leg: three radix-8 passes, 8 lanes per tile).  The first entry of a size is its default (measured, profiles/
+// flat_ab_r02e.txt / _r02f.txt); the other is selected with SSFFT_FLAT_VARIANT="ring,ctas_per_sm,inplace".  Entries with a
+// separate exchange buffer also carry the RealFFT kernels of length 2 N1 N2.
 #include "flat_launch.cuh"
 namespace ssfft {
 void register_flat_f32_c(std::vector<FlatEntry> &v) {
-    v.push_back(make_flat_entry<TileCfg<float, 256, 16, 16, 1, 16, 16, 3>, TileCfg<float, 512, 8, 8, 8, 32, 8, 3>, 2, 3, true>("float_flat_256x512_r2c3i"));
-    v.push_back(make_flat_entry<TileCfg<float, 256, 16, 16, 1, 16, 16, 3>, TileCfg<float, 512, 8, 8, 8, 32, 8, 3>, 3, 2, true>("float_flat_256x512_r3c2i"));
     v.push_back(make_flat_entry<TileCfg<float, 256, 16, 16, 1, 16, 16, 3>, TileCfg<float, 512, 8, 8, 8, 32, 8, 3>, 1, 3, false>("float_flat_256x512_r1c3x"));
-    v.push_back(make_flat_entry<TileCfg<float, 256, 16, 16, 1, 16, 16, 3>, TileCfg<float, 512, 8, 8, 8, 32, 8, 3>, 2, 2, false>("float_flat_256x512_r2c2x"));
-    v.push_back(make_flat_entry<TileCfg<float, 512, 8, 8, 8, 32, 8, 3>, TileCfg<float, 512, 8, 8, 8, 32, 8, 3>, 2, 3, true>("float_flat_512x512_r2c3i"));
-    v.push_back(make_flat_entry<TileCfg<float, 512, 8, 8, 8, 32, 8, 3>, TileCfg<float, 512, 8, 8, 8, 32, 8, 3>, 3, 2, true>("float_flat_512x512_r3c2i"));
+    v.push_back(make_flat_entry<TileCfg<float, 256, 16, 16, 1, 16, 16, 3>, TileCfg<float, 512, 8, 8, 8, 32, 8, 3>, 2, 3, true>("float_flat_256x512_r2c3i"));
     v.push_back(make_flat_entry<TileCfg<float, 512, 8, 8, 8, 32, 8, 3>, TileCfg<float, 512, 8, 8, 8, 32, 8, 3>, 1, 3, false>("float_flat_512x512_r1c3x"));
-    v.push_back(make_flat_entry<TileCfg<float, 512, 8, 8, 8, 32, 8, 3>, TileCfg<float, 512, 8, 8, 8, 32, 8, 3>, 2, 2, false>("float_flat_512x512_r2c2x"));
+    v.push_back(make_flat_entry<TileCfg<float, 512, 8, 8, 8, 32, 8, 3>, TileCfg<float, 512, 8, 8, 8, 32, 8, 3>, 2, 3, true>("float_flat_512x512_r2c3i"));
 }
 }  // namespace ssfft

@@ -8,10 +8,10 @@
 
 namespace ssfft {
 
-template <typename CfgA, typename CfgB, int INV, int NSTAGE, int MINB, bool INPLACE>
+template <typename CfgA, typename CfgB, int INV, int NSTAGE, int MINB, bool INPLACE, int KIND = 0>
 int flat_max_ctas() {
-    using Lay = FlatLayout<CfgA, CfgB, NSTAGE, INPLACE>;
-    auto kern = fourstep_flat_kernel<CfgA, CfgB, INV, NSTAGE, MINB, INPLACE>;
+    using Lay = FlatLayout<CfgA, CfgB, NSTAGE, INPLACE, KIND>;
+    auto kern = fourstep_flat_kernel<CfgA, CfgB, INV, NSTAGE, MINB, INPLACE, KIND>;
     static int cached[32] = {0};
     static std::mutex m;
     int dev = 0;
@@ -33,18 +33,21 @@ int flat_max_ctas() {
 }
 
 // returns 0 on success, 2 on a launch error, 3 when the input cannot be described by a tensor map (caller falls back)
-template <typename CfgA, typename CfgB, int INV, int NSTAGE, int MINB, bool INPLACE>
+template <typename CfgA, typename CfgB, int INV, int NSTAGE, int MINB, bool INPLACE, int KIND = 0>
 int launch_flat(const void *params, int ctas, cudaStream_t s) {
     using T = typename CfgA::T;
-    using Lay = FlatLayout<CfgA, CfgB, NSTAGE, INPLACE>;
+    using Lay = FlatLayout<CfgA, CfgB, NSTAGE, INPLACE, KIND>;
     const FlatParams<T> &q = *reinterpret_cast<const FlatParams<T> *>(params);
     if (q.batch <= 0) return 0;
-    if (flat_max_ctas<CfgA, CfgB, INV, NSTAGE, MINB, INPLACE>() < 1) return 2;  // also sets the shared-memory attribute
-    CUtensorMap tmap;
+    if (flat_max_ctas<CfgA, CfgB, INV, NSTAGE, MINB, INPLACE, KIND>() < 1) return 2;  // also sets the shared-memory attribute
+    CUtensorMap tmap, tmap2;
     memset(&tmap, 0, sizeof(tmap));
+    memset(&tmap2, 0, sizeof(tmap2));
     constexpr int kBoxRows = CfgA::L > 256 ? 256 : CfgA::L;
-    if (!encode_tensor_map_3d(&tmap, q.in, q.batch, CfgA::L, CfgB::L, kBoxRows, CfgA::CT)) return 3;
-    fourstep_flat_kernel<CfgA, CfgB, INV, NSTAGE, MINB, INPLACE><<<(unsigned)ctas, CfgA::THREADS + kFlatHelpers, Lay::smem_bytes, s>>>(q, tmap);
+    constexpr int kBoxCols = KIND == 2 ? CfgA::CT / 2 : CfgA::CT;
+    if (!encode_tensor_map_3d(&tmap, q.in, q.batch, CfgA::L, CfgB::L, kBoxRows, kBoxCols)) return 3;
+    if (KIND == 2 && !encode_tensor_map_3d(&tmap2, q.in, q.batch, CfgA::L, CfgB::L, kBoxRows, 2)) return 3;
+    fourstep_flat_kernel<CfgA, CfgB, INV, NSTAGE, MINB, INPLACE, KIND><<<(unsigned)ctas, CfgA::THREADS + kFlatHelpers, Lay::smem_bytes, s>>>(q, tmap, tmap2);
     return cudaGetLastError() == cudaSuccess ? 0 : 2;
 }
 
@@ -65,6 +68,14 @@ FlatEntry make_flat_entry(const char *name) {
     e.launch[1] = &launch_flat<CfgA, CfgB, 1, NSTAGE, MINB, INPLACE>;
     e.max_ctas[0] = &flat_max_ctas<CfgA, CfgB, 0, NSTAGE, MINB, INPLACE>;
     e.max_ctas[1] = &flat_max_ctas<CfgA, CfgB, 1, NSTAGE, MINB, INPLACE>;
+    e.launch_real[0] = e.launch_real[1] = nullptr;
+    e.max_ctas_real[0] = e.max_ctas_real[1] = nullptr;
+    if constexpr (!INPLACE && CfgA::CT % 2 == 0 && CfgB::CT % 2 == 0 && CfgA::prod(CfgA::NP - 1) % (CfgB::CT / 2) == 0) {
+        e.launch_real[0] = &launch_flat<CfgA, CfgB, 0, NSTAGE, MINB, false, 1>;
+        e.launch_real[1] = &launch_flat<CfgA, CfgB, 1, NSTAGE, MINB, false, 2>;
+        e.max_ctas_real[0] = &flat_max_ctas<CfgA, CfgB, 0, NSTAGE, MINB, false, 1>;
+        e.max_ctas_real[1] = &flat_max_ctas<CfgA, CfgB, 1, NSTAGE, MINB, false, 2>;
+    }
     return e;
 }
 

@@ -66,6 +66,8 @@ struct ssfft_plan {
     void *d_flat_ga[2] = {nullptr, nullptr}, *d_flat_gb[2] = {nullptr, nullptr}, *d_flat_s4 = nullptr, *d_flat_twb = nullptr;
     void *d_flat_scratch = nullptr, *d_flat_ctrl = nullptr;
     long long flat_cap = 0;                // transforms per launch the dependency counters cover
+    bool flat_real = false;                // real plan: the entry's RealFFT kernels (forward / inverse) are used
+    void *d_flat_ra[2] = {nullptr, nullptr}, *d_flat_rb[2] = {nullptr, nullptr};  // post- / pre-twiddle factors [fwd, inv]
 
     // Bluestein (bluestein.cuh): lengths whose largest prime factor fits no on-chip path run as a convolution through
     // an inner power-of-two plan of length bs_m

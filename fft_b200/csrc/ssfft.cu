@@ -304,17 +304,19 @@ FlatSchedule flat_schedule(int ctas, int ring, int tickets_per_phase) {
 template <typename T>
 int setup_flat(ssfft_plan *pl, bool *ok) {
     *ok = false;
-    const size_t n = pl->n;
-    if (pl->kind != SSFFT_C2C || n == 0 || (n & (n - 1))) return SSFFT_OK;
+    const size_t n = pl->n;  // complex length (real plans: N / 2)
+    const bool real = pl->kind == SSFFT_REAL;
+    if ((pl->kind != SSFFT_C2C && !real) || n == 0 || (n & (n - 1))) return SSFFT_OK;
+    if (real && env_int("SSFFT_DISABLE_FLAT_REAL", 0)) return SSFFT_OK;
     int lg = 0;
     while (((size_t)1 << lg) < n) ++lg;
     if (lg < env_int("SSFFT_FLAT_MIN_LOG2", 15)) return SSFFT_OK;
     const size_t n1 = (size_t)1 << (lg / 2), n2 = n / n1;
-    const int id = find_flat<T>(n1, n2);
+    const int id = find_flat<T>(n1, n2, real);
     if (id < 0) return SSFFT_OK;
     const FlatEntry &e = flat_registry()[id];
-    int ctas = e.max_ctas[0]();
-    const int ctas_inv = e.max_ctas[1]();
+    int ctas = real ? e.max_ctas_real[0]() : e.max_ctas[0]();
+    const int ctas_inv = real ? e.max_ctas_real[1]() : e.max_ctas[1]();
     if (ctas_inv < ctas) ctas = ctas_inv;
     if (ctas < 1) return SSFFT_OK;
     std::vector<T> ga[2], gb[2], s4, twb;
@@ -329,6 +331,13 @@ int setup_flat(ssfft_plan *pl, bool *ok) {
     for (int p = 0; p + 1 < e.na_passes; ++p)
         if ((rc = up(&pl->d_flat_ga[p], ga[p])) || (rc = up(&pl->d_flat_gb[p], gb[p]))) return rc;
     if ((rc = up(&pl->d_flat_s4, s4)) || (rc = up(&pl->d_flat_twb, twb))) return rc;
+    if (real)
+        for (int inv = 0; inv < 2; ++inv) {
+            std::vector<T> ra, rb;
+            fill_flat_real_tables<T>(ra, rb, n1, n2, inv != 0);
+            if ((rc = up(&pl->d_flat_ra[inv], ra)) || (rc = up(&pl->d_flat_rb[inv], rb))) return rc;
+        }
+    pl->flat_real = real;
     const int pt = (int)(n2 / e.cta + n1 / e.ctb);
     int slots = flat_schedule(ctas, e.nstage, pt).slots;
     if (env_int("SSFFT_FLAT_SLOTS", 0) > slots) slots = env_int("SSFFT_FLAT_SLOTS", 0);
@@ -336,14 +345,15 @@ int setup_flat(ssfft_plan *pl, bool *ok) {
     pl->flat_cap = 1 << 16;
     CU(cudaMalloc(&pl->d_flat_ctrl, (size_t)(32 + 2 * pl->flat_cap) * sizeof(unsigned)));
     pl->flat_id = id; pl->flat_ctas = ctas; pl->flat_slots = slots;
-    if (!pl->n1) { pl->n1 = n1; pl->n2 = n2; }
+    if (!pl->n1 && !real) { pl->n1 = n1; pl->n2 = n2; }
     *ok = true;
     return SSFFT_OK;
 }
 
 // returns SSFFT_OK, an error, or -1: this input has no tensor map (pointer not 16-byte aligned) -- use the other path
+// kind: 0 complex (direction = inverse), 1 RealFFT forward, 2 RealFFT inverse; n = complex length in every case
 template <typename T>
-int exec_flat(ssfft_plan *pl, const void *in, void *out, long long batch, int inverse, cudaStream_t s) {
+int exec_flat(ssfft_plan *pl, const void *in, void *out, long long batch, int inverse, cudaStream_t s, int kind = 0) {
     const FlatEntry &e = flat_registry()[pl->flat_id];
     const long long n = (long long)pl->n;
     if ((reinterpret_cast<uintptr_t>(in) & 15u) != 0) return -1;
@@ -364,6 +374,7 @@ int exec_flat(ssfft_plan *pl, const void *in, void *out, long long batch, int in
         q.tw_b = (const cx<T> *)pl->d_flat_twb;
         for (int p = 0; p < 2; ++p) { q.ga[p] = (const cx<T> *)pl->d_flat_ga[p]; q.gb[p] = (const cx<T> *)pl->d_flat_gb[p]; }
         q.s4 = (const cx<T> *)pl->d_flat_s4; q.ctrl = (unsigned *)pl->d_flat_ctrl;
+        q.ra = (const cx<T> *)pl->d_flat_ra[kind == 2 ? 1 : 0]; q.rb = (const cx<T> *)pl->d_flat_rb[kind == 2 ? 1 : 0];
         q.batch = nb; q.user_stride = n; q.scratch_per = n; q.cap = nb;
         q.nslots = (int)slots; q.delay = (int)delay; q.discard = env_int("SSFFT_DISCARD", 1);
         q.stats = nullptr;
@@ -374,7 +385,7 @@ int exec_flat(ssfft_plan *pl, const void *in, void *out, long long batch, int in
         q.stats = d_stats;
 #endif
         CU(cudaMemsetAsync(pl->d_flat_ctrl, 0, (size_t)(32 + 2 * nb) * sizeof(unsigned), s));
-        const int rc = e.launch[inverse ? 1 : 0](&q, (int)ctas, s);
+        const int rc = kind ? e.launch_real[kind - 1](&q, (int)ctas, s) : e.launch[inverse ? 1 : 0](&q, (int)ctas, s);
         if (rc == 3) return -1;
         ++g_launches;
         if (rc) return cuda_fail(cudaGetLastError(), "fourstep_flat_kernel launch");
@@ -565,11 +576,17 @@ int build_plan_typed(ssfft_plan *pl) {
         if (rc) return rc;
     }
     bool flat_ok = false;
-    if (pl->kind == SSFFT_C2C && (clustered_ok || tiled_ok)) {
+    if ((pl->kind == SSFFT_C2C || pl->kind == SSFFT_REAL) && (clustered_ok || tiled_ok)) {
         int rc = setup_flat<T>(pl, &flat_ok);
         if (rc) return rc;
     }
-    if (flat_ok) {
+    if (flat_ok && pl->flat_real) {
+        const FlatEntry &e = flat_registry()[pl->flat_id];
+        snprintf(buf, sizeof(buf), "real N=%zu as complex N/2 = %d x %d ticket-queue four-step (%s): pairs of samples, post- / pre-twiddle "
+                 "fused into the row / column tiles, one persistent launch of %d CTAs, %d scratch slots = %.1f MiB in L2", pl->n_real,
+                 e.n1, e.n2, e.name, pl->flat_ctas, pl->flat_slots, pl->flat_slots * (double)n * sizeof(cx<T>) / 1048576.0);
+        pl->desc = buf;
+    } else if (flat_ok) {
         const FlatEntry &e = flat_registry()[pl->flat_id];
         snprintf(buf, sizeof(buf), "complex N=%zu ticket-queue four-step n1=%d x n2=%d (%s): one persistent launch of %d CTAs "
                  "(%d consumer threads + TMA producer and signaller warps each, ring of %d%s), %d scratch slots = %.1f MiB in L2", n, e.n1, e.n2,
@@ -685,6 +702,10 @@ int exec_r2c_typed(ssfft_plan *pl, const void *in, void *out, long long batch, c
     const long long h = (long long)pl->n;
     if (h == 0 || batch <= 0) return SSFFT_OK;
     const bool modified = pl->kind == SSFFT_REAL_MODIFIED;
+    if (pl->flat_id >= 0 && pl->flat_real) {
+        const int rc = exec_flat<T>(pl, in, out, batch, 0, s, 1);
+        if (rc >= 0) return rc;
+    }
     if (pl->clustered) return exec_clustered<T>(pl, 1, in, out, batch, 0, s);
     if (pl->tiled) return exec_tiled<T>(pl, 1, in, out, batch, 0, s);
     if (!pl->four_step && pl->fused.id >= 0)
@@ -712,6 +733,10 @@ int exec_c2r_typed(ssfft_plan *pl, const void *in, void *out, long long batch, c
     const long long h = (long long)pl->n;
     if (h == 0 || batch <= 0) return SSFFT_OK;
     const bool modified = pl->kind == SSFFT_REAL_MODIFIED;
+    if (pl->flat_id >= 0 && pl->flat_real) {
+        const int rc = exec_flat<T>(pl, in, out, batch, 1, s, 2);
+        if (rc >= 0) return rc;
+    }
     if (pl->clustered) return exec_clustered<T>(pl, 2, in, out, batch, 1, s);
     if (pl->tiled) return exec_tiled<T>(pl, 2, in, out, batch, 1, s);
     if (!pl->four_step && pl->fused.id >= 0)
@@ -900,7 +925,8 @@ int ssfft_plan_destroy(ssfft_plan *pl) {
     void *ptrs[] = {pl->fused.d_twiddles, pl->fused_col.d_twiddles, pl->fused_row.d_twiddles, pl->d_ep_lo, pl->d_ep_hi,
                     pl->d_scratch, pl->d_rtw, pl->d_rot, pl->d_tile_tw_a, pl->d_tile_tw_b,
                     pl->d_tw4, pl->d_fs_ctr, pl->d_ex_in, pl->d_ex_out, pl->d_flat_ga[0], pl->d_flat_ga[1], pl->d_flat_gb[0], pl->d_flat_gb[1], pl->d_flat_s4,
-                    pl->d_flat_twb, pl->d_flat_scratch, pl->d_flat_ctrl};
+                    pl->d_flat_twb, pl->d_flat_scratch, pl->d_flat_ctrl, pl->d_flat_ra[0], pl->d_flat_ra[1], pl->d_flat_rb[0],
+                    pl->d_flat_rb[1]};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     for (int k = 0; k < 3; ++k) {

@@ -295,6 +295,24 @@ inline void bulk_g2s(void *dst, const void *src, unsigned bytes, const void *bar
     land(m, c);
     mbar_complete_if_ready(m);
 }
+// one piece of a TMA tensor copy (any alignment), or its zero fill outside the tensor
+inline void tma_copy(void *dst, const void *src, unsigned bytes, const void *bar) {
+    State &s = state();
+    Mbar &m = mbar_of(self().cta, bar);
+    s.bulk_bytes += bytes;
+    Mbar::Pending c{dst, src, bytes, {0}};
+    if (s.late_copy) { m.pending.push_back(c); return; }
+    land(m, c);
+    mbar_complete_if_ready(m);
+}
+inline void tma_zero(void *dst, unsigned bytes, const void *bar) {
+    State &s = state();
+    Mbar &m = mbar_of(self().cta, bar);
+    Mbar::Pending c{dst, nullptr, bytes, {0}};
+    if (s.late_copy) { m.pending.push_back(c); return; }
+    land(m, c);
+    mbar_complete_if_ready(m);
+}
 // st.async to CTA `rank` of my cluster: the value lands in the peer's shared memory and completes `bytes` of the PEER's
 // mbarrier at the same shared-memory offset as `bar` (now, or -- late_copy -- when the peer waits for it)
 inline void remote_store_tx(unsigned rank, void *peer_dst, const void *value, unsigned bytes, const void *bar) {
