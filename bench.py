@@ -71,6 +71,35 @@ def alg_bytes_per_transform(kind, n, dtype):
     return 2 * n * 2 * sz if kind == "c2c" else 4 * n * sz
 
 
+def bind_to_gpu_numa_node(index):
+    """Run this process on the CPUs next to GPU `index` (its PCIe root complex) before pinned host memory is allocated:
+    pages are placed on the node of the thread that first touches them, and a host buffer on the far socket halves the
+    copy rate of every rank that shares the inter-socket link.  Returns a short description for the JSON line."""
+    try:
+        import torch
+
+        prop = torch.cuda.get_device_properties(index)
+        bus = f"{getattr(prop, 'pci_domain_id', 0):04x}:{prop.pci_bus_id:02x}:{getattr(prop, 'pci_device_id', 0):02x}.0"
+        base = f"/sys/bus/pci/devices/{bus}"
+        with open(base + "/local_cpulist") as f:
+            cpulist = f.read().strip()
+        node = open(base + "/numa_node").read().strip()
+        cpus = set()
+        for part in cpulist.split(","):
+            if "-" in part:
+                a, b = part.split("-")
+                cpus.update(range(int(a), int(b) + 1))
+            elif part:
+                cpus.add(int(part))
+        allowed = os.sched_getaffinity(0)
+        cpus &= allowed
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return {"pci": bus, "numa_node": node, "cpus": len(cpus) or len(allowed)}
+    except Exception as exc:  # containers without sysfs access: leave the affinity alone
+        return {"error": repr(exc)[:120]}
+
+
 def measured_peak():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -329,6 +358,57 @@ def measure_dist(args, n, rank, world, dev, dist, steps, warmup, verify):
     return line
 
 
+def measure_dist_local(n, world, iters=3):
+    """BASELINE config 5 through ssfft_dist_plan_create / ssfft_dist_exec_c2c: ONE process, `world` GPUs, natural order."""
+    import torch
+
+    import fft_b200
+    from fft_b200.dist import LocalDistFFT1D
+
+    per = n // world
+    out = {}
+    for transposed in (False, True):
+        plan = LocalDistFFT1D(n, list(range(world)), transposed_output=transposed)
+        xs, ys = [], []
+        for r in range(world):
+            with torch.cuda.device(r):
+                x = torch.empty(per, dtype=torch.complex64, device=f"cuda:{r}")
+                fft_b200.fill_uniform(x, SEED, first_idx=r * per * 2)
+                xs.append(x)
+                ys.append(torch.empty_like(x))
+        for r in range(world):
+            torch.cuda.synchronize(r)
+        for _ in range(2):
+            plan.fft(xs, ys)
+        plan.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(iters):
+            plan.fft(xs, ys)
+        plan.synchronize()
+        ms = 1e3 * (time.perf_counter() - t0) / iters
+        key = "transposed_output" if transposed else "natural_order"
+        out[key] = {"ms": ms, "gflops": 5.0 * n * math.log2(n) / ms / 1e6}
+        if not transposed:
+            ex = sum((x.real.double() ** 2 + x.imag.double() ** 2).sum().item() for x in xs)
+            ey = sum((y.real.double() ** 2 + y.imag.double() ** 2).sum().item() for y in ys)
+            backs = [torch.empty_like(x) for x in xs]
+            plan.ifft(ys, backs)
+            plan.synchronize()
+            num = sum(((b.real.double() - n * x.real.double()) ** 2 + (b.imag.double() - n * x.imag.double()) ** 2).sum().item()
+                      for b, x in zip(backs, xs))
+            lim = 1e-6 * math.log2(n)
+            rt = math.sqrt(num / (n * n * ex))
+            out["checks"] = {"parseval_rel_err": abs(ey / (n * ex) - 1.0), "roundtrip_rel_l2": rt, "tolerance": lim,
+                             "ok": bool(rt <= 2 * lim and abs(ey / (n * ex) - 1.0) < 1e-4)}
+            out["plan"] = plan.describe()
+            del backs
+        plan.close()
+        del xs, ys
+        torch.cuda.empty_cache()
+    out["workload"] = f"one c2c float32 transform of N={n} over {world} GPUs of one process (C ABI ssfft_dist_*), wall clock"
+    return out
+
+
 def measure_batched(name, dev, rank, world, dist, steps=5, warmup=3, subset=4):
     """One BASELINE config other than the headline: device-resident timing (CUDA events, max over ranks) plus the
     relative L2 error of a few transforms against the oracle in the same precision."""
@@ -558,6 +638,7 @@ def main():
     # ---- end to end through the host-pointer API (pinned host memory, H2D + D2H inside the timed region)
     e2e = None
     if not args.no_e2e:
+        numa = bind_to_gpu_numa_node(local_rank)
         e2e_steps = max(1, min(args.steps, 8))
         host_in = torch.empty(x.shape, dtype=x.dtype, pin_memory=True)
         host_in.copy_(x)
@@ -589,7 +670,32 @@ def main():
         e2e = {"value": flops_step * e2e_steps / el / 1e9, "unit": "GFLOP/s",
                "h2d_bytes_per_step": io if kind == "c2c" else 2 * io, "d2h_bytes_per_step": io if kind == "c2c" else 2 * io,
                "ms_per_step": 1e3 * el / e2e_steps, "steps": e2e_steps,
-               "api": "fft_b200.FFT.fft(host_in, host_out) -> ssfft_exec_host (pinned buffers, sliced H2D/compute/D2H overlap)"}
+               "api": "fft_b200.FFT.fft(host_in, host_out) -> ssfft_exec_host (pinned buffers, sliced H2D/compute/D2H overlap)",
+               "host_numa": numa}
+        # what the link itself can do: the same bytes as plain pinned copies, both directions at once, no kernels
+        try:
+            cs_in, cs_out = torch.cuda.Stream(), torch.cuda.Stream()
+            dbuf_in = torch.empty(x.shape, dtype=x.dtype, device=dev)
+            dbuf_out = torch.empty(host_out.shape, dtype=host_out.dtype, device=dev)
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(2):
+                with torch.cuda.stream(cs_in):
+                    dbuf_in.copy_(host_in, non_blocking=True)
+                with torch.cuda.stream(cs_out):
+                    host_out.copy_(dbuf_out, non_blocking=True)
+            torch.cuda.synchronize()
+            el_c = (time.perf_counter() - t0) / 2
+            if world > 1:
+                t = torch.tensor([el_c], dtype=torch.float64, device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                el_c = float(t.item())
+            e2e["copy_only_ms_per_step"] = 1e3 * el_c
+            e2e["ceiling_GBps_per_direction_per_gpu"] = e2e["h2d_bytes_per_step"] / el_c / 1e9
+            e2e["frac_of_copy_ceiling"] = el_c / (el / e2e_steps)
+            del dbuf_in, dbuf_out
+        except Exception as exc:
+            e2e["ceiling_error"] = repr(exc)[:200]
         # sanity: the e2e result equals the device-resident result
         if kind == "c2c":
             assert torch.equal(host_out[:4], y[:4].cpu()), "e2e output differs from device output"
@@ -650,6 +756,16 @@ def main():
                                      "checks": c5.get("checks")}
             except Exception as exc:
                 configs["c5"] = {"error": repr(exc)[:300]}
+            # the same transform through the C ABI of the single-process plan (ssfft_dist_*): rank 0 drives all the
+            # GPUs of the node over peer access while the other ranks wait
+            try:
+                torch.cuda.empty_cache()
+                dist.barrier()
+                if rank == 0:
+                    configs["c5_c_abi"] = measure_dist_local(1 << 30, world)
+                dist.barrier()
+            except Exception as exc:
+                configs["c5_c_abi"] = {"error": repr(exc)[:300]}
         configs["seconds"] = round(time.perf_counter() - t_cfg, 1)
 
     traffic, traffic_src = profiled_traffic(args.workload) if not args.batch else (None, None)

@@ -77,9 +77,14 @@ template <typename CfgA, typename CfgB, int NSTAGE, bool INPLACE, int KIND = 0>
 struct FlatLayout {
     using T = typename CfgA::T;
     static constexpr size_t al(size_t v) { return (v + 127) / 128 * 128; }
-    // column tile: dense [L][CT]; C2R: two boxes [L][CT/2] (the second 64 bytes further) + the 2-column box of column N2/2
+    // column tile: dense [L][CT].  C2R (H = CT/2): the low columns [L][H], their partners N2 - n2 in a box [L][H + 2] (a
+    // tensor copy must start on a 16-byte boundary = an even column of 8-byte elements, the partners of an even-aligned
+    // run start on an odd one: the box starts one column early and is two columns wider), and for tile 0 the self-paired
+    // column N2/2 as the first column of a third box [L][H]
     static constexpr size_t kTileA = (size_t)CfgA::L * CfgA::CT * sizeof(cx<T>);
-    static constexpr size_t kSlotA = KIND == 2 ? kTileA + 2 * 8 * sizeof(cx<T>) + (size_t)CfgA::L * 2 * sizeof(cx<T>) : kTileA;
+    static constexpr size_t kC2rLow = (size_t)CfgA::L * (CfgA::CT / 2) * sizeof(cx<T>);
+    static constexpr size_t kC2rHigh = (size_t)CfgA::L * (CfgA::CT / 2 + 2) * sizeof(cx<T>);
+    static constexpr size_t kSlotA = KIND == 2 ? 2 * kC2rLow + kC2rHigh : kTileA;
     // row tile: dense [L][CT]; R2C: two blocks [L][CT/2], the second 64 bytes further
     static constexpr size_t kTileB = (size_t)CfgB::L * CfgB::CT * sizeof(cx<T>);
     static constexpr size_t kSlotB = KIND == 1 ? kTileB + 2 * 8 * sizeof(cx<T>) : kTileB;
@@ -117,6 +122,12 @@ inline void fence_proxy_async() {}
 template <typename T>
 inline void tma_tile_3d(cx<T> *dst, const void *, const cx<T> *in, int n1, int n2, int box_rows, int ct, int col0, int row0, long long b,
                         unsigned long long *bar) {
+    // what the hardware requires and a CPU does not notice: box start on a 16-byte boundary in global memory, box
+    // destination on a 128-byte boundary in shared memory, inner box extent a multiple of 16 bytes
+    if ((col0 * sizeof(cx<T>)) % 16 || (ct * sizeof(cx<T>)) % 16 || reinterpret_cast<uintptr_t>(dst) % 128) {
+        fprintf(stderr, "tensor copy violates the TMA alignment rules: col0 %d, box cols %d, dst %p\n", col0, ct, (void *)dst);
+        abort();
+    }
     for (int r = 0; r < box_rows; ++r)
         for (int c = 0; c < ct; ++c) {
             if (col0 + c < n2) simt::tma_copy(dst + (size_t)r * ct + c, in + b * (long long)n1 * n2 + (long long)(row0 + r) * n2 + col0 + c, (unsigned)sizeof(cx<T>), bar);
@@ -241,13 +252,20 @@ __device__ __forceinline__ void flat_stage_a(const FlatParams<T> &q, const cx<T>
         static_assert((1 << LOG) == R && (P & (P - 1)) == 0, "power-of-two radices");
         const int tt = last ? t2 : t, cc = last ? c2 : c;
         if constexpr (first && KIND == 2) {
-            // ring slot: [2][L][H] (high half 8 elements further: other banks), then the 2-column box of column N2/2
-            constexpr int H = CT / 2, HALF = L * H + 8;
+            // ring slot: low columns [L][H], partner box [L][H + 2] (column N2 - n2 of low column n2 = H tile + i sits at
+            // box column H - i), then for tile 0 the box whose first column is N2/2
+            constexpr int H = CT / 2, HP = H + 2, LOW = L * H, HIGH = L * HP;
             const bool lane_self0 = tile == 0 && c == 0, lane_selfm = tile == 0 && c == CT - 1;
-            const cx<T> *own = lane_selfm ? st + 2 * HALF : st + (c / H) * HALF + (c % H);
-            const int own_pitch = lane_selfm ? 2 : H;
-            const int pc_ = CT - 1 - c;
-            const cx<T> *par = (lane_self0 || lane_selfm) ? own : st + (pc_ / H) * HALF + (pc_ % H);
+            auto where = [&](int lane, int &pitch) -> const cx<T> * {
+                if (lane < H) { pitch = H; return st + lane; }
+                if (tile == 0 && lane == CT - 1) { pitch = H; return st + LOW + HIGH; }
+                pitch = HP;
+                return st + LOW + (lane - H + 1);
+            };
+            int own_pitch, par_pitch;
+            const cx<T> *own = where(c, own_pitch);
+            const cx<T> *par = where(CT - 1 - c, par_pitch);
+            if (lane_self0 || lane_selfm) { par = own; par_pitch = own_pitch; }
             const cx<T> cb = ld_table(q.rb + col_of(c));
 #pragma unroll
             for (int u = 0; u < U; ++u)
@@ -255,7 +273,7 @@ __device__ __forceinline__ void flat_stage_a(const FlatParams<T> &q, const cx<T>
                 for (int j = 0; j < R; ++j) {
                     const int n1 = t + TX * u + NR * j;
                     const int n1p = lane_self0 ? ((L - n1) & (L - 1)) : L - 1 - n1;
-                    const cx<T> xo = own[n1 * own_pitch], xp = par[n1p * own_pitch];
+                    const cx<T> xo = own[n1 * own_pitch], xp = par[n1p * par_pitch];
                     const cx<T> tc = cmul(ld_table(q.ra + n1), cb);  // conj(-i W_N^n)
                     const cx<T> sum = mk<T>(xo.x + xp.x, xo.y - xp.y), dif = mk<T>(xo.x - xp.x, xo.y + xp.y);  // X +- conj X'
                     cx<T> z = sum + cmul(dif, tc);
@@ -661,18 +679,18 @@ fourstep_flat_kernel(FlatParams<typename CfgA::T> q, const __grid_constant__ CUt
                         cx<T> *slot = reinterpret_cast<cx<T> *>(ssfft_smem + Lay::oSlots + (size_t)s * Lay::kSlot);
                         constexpr int kBoxRows = N1 > 256 ? 256 : N1;
                         if (cur.kind == 0 && KIND == 2) {
-                            // low columns [H t, H t + H), their partners [N2 - H t - H + 1, N2 - H t] (for t = 0 the last one
-                            // is outside the tensor: zero fill, unused) and, for t = 0, the self-paired column N2/2
-                            constexpr int H = CfgA::CT / 2, HALF = N1 * H + 8;
-                            constexpr unsigned side = (unsigned)(N1 * 2 * sizeof(cx<T>));
-                            mbar_expect_tx(&full[s], (unsigned)Lay::kTileA + (cur.tile == 0 ? side : 0u));
+                            // low columns [H t, H t + H); their partners [N2 - H t - H + 1, N2 - H t] inside the box of H + 2
+                            // columns that starts at the even column N2 - H t - H (for t = 0 its last two columns are outside
+                            // the tensor: zero fill, unused); for t = 0 also the box that starts at the self-paired column N2/2
+                            constexpr int H = CfgA::CT / 2, HP = H + 2, LOW = N1 * H, HIGH = N1 * HP;
+                            mbar_expect_tx(&full[s], (unsigned)(Lay::kC2rLow + Lay::kC2rHigh + (cur.tile == 0 ? Lay::kC2rLow : 0)));
 #pragma unroll
                             for (int r0 = 0; r0 < N1; r0 += kBoxRows) {
                                 tma_tile_3d<T>(slot + (size_t)r0 * H, &tmap, q.in, N1, N2, kBoxRows, H, cur.tile * H, r0, cur.b, &full[s]);
-                                tma_tile_3d<T>(slot + HALF + (size_t)r0 * H, &tmap, q.in, N1, N2, kBoxRows, H, N2 - cur.tile * H - H + 1, r0,
-                                               cur.b, &full[s]);
+                                tma_tile_3d<T>(slot + LOW + (size_t)r0 * HP, &tmap2, q.in, N1, N2, kBoxRows, HP, N2 - cur.tile * H - H, r0, cur.b,
+                                               &full[s]);
                                 if (cur.tile == 0)
-                                    tma_tile_3d<T>(slot + 2 * HALF + (size_t)r0 * 2, &tmap2, q.in, N1, N2, kBoxRows, 2, N2 / 2, r0, cur.b, &full[s]);
+                                    tma_tile_3d<T>(slot + LOW + HIGH + (size_t)r0 * H, &tmap, q.in, N1, N2, kBoxRows, H, N2 / 2, r0, cur.b, &full[s]);
                             }
                         } else if (cur.kind == 0) {
                             cx<T> *sblk = INPLACE ? reinterpret_cast<cx<T> *>(reinterpret_cast<unsigned char *>(slot) + Lay::kExch)

@@ -46,7 +46,7 @@ int launch_flat(const void *params, int ctas, cudaStream_t s) {
     constexpr int kBoxRows = CfgA::L > 256 ? 256 : CfgA::L;
     constexpr int kBoxCols = KIND == 2 ? CfgA::CT / 2 : CfgA::CT;
     if (!encode_tensor_map_3d(&tmap, q.in, q.batch, CfgA::L, CfgB::L, kBoxRows, kBoxCols)) return 3;
-    if (KIND == 2 && !encode_tensor_map_3d(&tmap2, q.in, q.batch, CfgA::L, CfgB::L, kBoxRows, 2)) return 3;
+    if (KIND == 2 && !encode_tensor_map_3d(&tmap2, q.in, q.batch, CfgA::L, CfgB::L, kBoxRows, CfgA::CT / 2 + 2)) return 3;
     fourstep_flat_kernel<CfgA, CfgB, INV, NSTAGE, MINB, INPLACE, KIND><<<(unsigned)ctas, CfgA::THREADS + kFlatHelpers, Lay::smem_bytes, s>>>(q, tmap, tmap2);
     return cudaGetLastError() == cudaSuccess ? 0 : 2;
 }

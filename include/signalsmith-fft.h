@@ -252,6 +252,48 @@ struct ModifiedRealFFT : public RealFFT<V, FFTOptions::halfFreqShift> {
     using RealFFT<V, FFTOptions::halfFreqShift>::RealFFT;
 };
 
+// NEW (no counterpart in the reference): ONE complex transform sharded over several GPUs of this process.
+// devices[r] owns block r of the natural order: shard pointers address size() / devices.size() elements in that GPU's
+// memory.  The transform is the same unnormalised FFT<V> (fft then ifft scales by size()).  Calls are asynchronous on
+// streams of the plan: synchronize() before reading the output.  transposedOutput skips the last exchange (output shard
+// r = rows k1 in [r N1/P, (r+1) N1/P) of X[k1 + N1 k2]).  Move-only.
+template <typename V>
+class DistributedFFT {
+    using complex = std::complex<V>;
+    ssfft_dist_plan *plan = nullptr;
+    std::size_t _size = 0;
+    std::size_t _devices = 0;
+
+    void run(complex *const *d_in, complex *const *d_out, int direction) {
+        std::vector<void *> in(_devices), out(_devices);
+        for (std::size_t r = 0; r < _devices; ++r) { in[r] = d_in[r]; out[r] = d_out[r]; }
+        b200_detail::check(ssfft_dist_exec_c2c(plan, in.data(), out.data(), direction), "ssfft_dist_exec_c2c");
+    }
+
+public:
+    DistributedFFT(std::size_t size, const std::vector<int> &devices, bool transposedOutput = false)
+        : _size(size), _devices(devices.size()) {
+        b200_detail::check(ssfft_dist_plan_create(&plan, b200_detail::Precision<V>::value, size, (int)devices.size(), devices.data(),
+                                                  transposedOutput ? SSFFT_DIST_TRANSPOSED_OUTPUT : 0),
+                           "ssfft_dist_plan_create");
+    }
+    DistributedFFT(const DistributedFFT &) = delete;
+    DistributedFFT &operator=(const DistributedFFT &) = delete;
+    DistributedFFT(DistributedFFT &&o) noexcept : plan(o.plan), _size(o._size), _devices(o._devices) { o.plan = nullptr; }
+    ~DistributedFFT() { if (plan) ssfft_dist_plan_destroy(plan); }
+
+    std::size_t size() const { return _size; }
+    std::size_t devices() const { return _devices; }
+    void fft(complex *const *d_in_shards, complex *const *d_out_shards) { run(d_in_shards, d_out_shards, SSFFT_FORWARD); }
+    void ifft(complex *const *d_in_shards, complex *const *d_out_shards) { run(d_in_shards, d_out_shards, SSFFT_INVERSE); }
+    void synchronize() { b200_detail::check(ssfft_dist_synchronize(plan), "ssfft_dist_synchronize"); }
+    std::string describe() const {
+        char buf[1024] = "empty";
+        if (plan) ssfft_dist_plan_describe(plan, buf, sizeof(buf));
+        return buf;
+    }
+};
+
 }  // namespace SIGNALSMITH_FFT_NAMESPACE
 
 #undef SIGNALSMITH_FFT_NAMESPACE

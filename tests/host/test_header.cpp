@@ -61,9 +61,40 @@ void testType(const char *name) {
         for (size_t i = 0; i < n; ++i) { e += std::norm(std::complex<double>(back[i]) - (double)n * std::complex<double>(in[i])); d += std::norm((double)n * std::complex<double>(in[i])); }
         CHECK(std::sqrt(e / d) <= 2 * Oracle<V>::tol(n), "%s n=%zu roundtrip err %g", name, n, std::sqrt(e / d));
     }
-    // copies share the immutable plan; setSize re-plans only on change
+    // copies own their plan (reference objects are independent after a copy); setSize re-plans only on change
     signalsmith::FFT<V> a(96), b = a;
     CHECK(b.size() == 96 && a.setSize(96) == 96 && a.setSize(64) == 64 && b.size() == 96, "copy/setSize");
+    {
+        std::vector<signalsmith::FFT<V>> pool(3, signalsmith::FFT<V>(256));  // the pattern of a thread pool
+        std::vector<cplx> in(256), o0(256), o2(256);
+        Oracle<V>::fill((V *)in.data(), 512, 77);
+        pool[0].fft(in, o0);
+        pool[2].fft(in, o2);
+        CHECK(o0 == o2 && pool[1].size() == 256, "copies of an FFT object are independent plans");
+        signalsmith::FFT<V> moved = std::move(pool[1]);
+        moved.fft(in, o2);
+        CHECK(o0 == o2, "moved-from plan handle");
+    }
+    {
+        // one transform sharded over logical ranks on device 0 (DistributedFFT, C ABI ssfft_dist_*)
+        const size_t dn = 1 << 14, P = 2, per = dn / P;
+        std::vector<cplx> x(dn), y(dn), ref(dn);
+        Oracle<V>::fill((V *)x.data(), 2 * dn, 78);
+        signalsmith::DistributedFFT<V> dfft(dn, std::vector<int>(P, 0));
+        void *din[P], *dout[P];
+        for (size_t r = 0; r < P; ++r) {
+            CHECK(ssfft_malloc(&din[r], per * sizeof(cplx)) == 0 && ssfft_malloc(&dout[r], per * sizeof(cplx)) == 0, "malloc");
+            ssfft_memcpy_h2d(din[r], x.data() + r * per, per * sizeof(cplx), nullptr);
+        }
+        ssfft_stream_synchronize(nullptr);
+        dfft.fft((cplx *const *)din, (cplx *const *)dout);
+        dfft.synchronize();
+        for (size_t r = 0; r < P; ++r) ssfft_memcpy_d2h(y.data() + r * per, dout[r], per * sizeof(cplx), nullptr);
+        ssfft_stream_synchronize(nullptr);
+        Oracle<V>::fft(dn, x.data(), ref.data(), 0);
+        CHECK(relL2(y.data(), ref.data(), dn) <= Oracle<V>::tol(dn), "DistributedFFT err %g", relL2(y.data(), ref.data(), dn));
+        for (size_t r = 0; r < P; ++r) { ssfft_free(din[r]); ssfft_free(dout[r]); }
+    }
     CHECK(signalsmith::FFT<V>(1000, 1).size() == 1024 && signalsmith::FFT<V>(1000, -1).size() == 768, "fastDirection");
     CHECK(a.setSizeMinimum(1025) == 1152 && a.setSizeMaximum(1025) == 1024, "setSizeMinimum/Maximum");
 
