@@ -672,6 +672,9 @@ def main():
                "ms_per_step": 1e3 * el / e2e_steps, "steps": e2e_steps,
                "api": "fft_b200.FFT.fft(host_in, host_out) -> ssfft_exec_host (pinned buffers, sliced H2D/compute/D2H overlap)",
                "host_numa": numa}
+        # sanity: the e2e result equals the device-resident result
+        if kind == "c2c":
+            assert torch.equal(host_out[:4], y[:4].cpu()), "e2e output differs from device output"
         # what the link itself can do: the same bytes as plain pinned copies, both directions at once, no kernels
         try:
             cs_in, cs_out = torch.cuda.Stream(), torch.cuda.Stream()
@@ -696,9 +699,6 @@ def main():
             del dbuf_in, dbuf_out
         except Exception as exc:
             e2e["ceiling_error"] = repr(exc)[:200]
-        # sanity: the e2e result equals the device-resident result
-        if kind == "c2c":
-            assert torch.equal(host_out[:4], y[:4].cpu()), "e2e output differs from device output"
         del host_in, host_out
 
     # ---- CPU baseline: the reference's own implementation on this box's host cores (rank 0, N=1 only)

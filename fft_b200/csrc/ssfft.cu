@@ -575,23 +575,30 @@ int build_plan_typed(ssfft_plan *pl) {
         int rc = setup_tiled<T>(pl, pl->n_real, true, &tiled_ok);
         if (rc) return rc;
     }
+    // the ticket-queue kernels need a tensor map of the input (16-byte aligned pointer); every plan that uses them also
+    // carries another path for the inputs that have none: the round-1 kernels where they exist, else the generic one
     bool flat_ok = false;
-    if ((pl->kind == SSFFT_C2C || pl->kind == SSFFT_REAL) && (clustered_ok || tiled_ok)) {
+    const bool have_fallback = clustered_ok || tiled_ok;
+    if (pl->kind == SSFFT_C2C || pl->kind == SSFFT_REAL) {
         int rc = setup_flat<T>(pl, &flat_ok);
         if (rc) return rc;
     }
+    std::string flat_desc;
     if (flat_ok && pl->flat_real) {
         const FlatEntry &e = flat_registry()[pl->flat_id];
         snprintf(buf, sizeof(buf), "real N=%zu as complex N/2 = %d x %d ticket-queue four-step (%s): pairs of samples, post- / pre-twiddle "
                  "fused into the row / column tiles, one persistent launch of %d CTAs, %d scratch slots = %.1f MiB in L2", pl->n_real,
                  e.n1, e.n2, e.name, pl->flat_ctas, pl->flat_slots, pl->flat_slots * (double)n * sizeof(cx<T>) / 1048576.0);
-        pl->desc = buf;
+        flat_desc = buf;
     } else if (flat_ok) {
         const FlatEntry &e = flat_registry()[pl->flat_id];
         snprintf(buf, sizeof(buf), "complex N=%zu ticket-queue four-step n1=%d x n2=%d (%s): one persistent launch of %d CTAs "
                  "(%d consumer threads + TMA producer and signaller warps each, ring of %d%s), %d scratch slots = %.1f MiB in L2", n, e.n1, e.n2,
                  e.name, pl->flat_ctas, e.threads - kFlatHelpers, e.nstage, e.inplace ? " in place" : "", pl->flat_slots, pl->flat_slots * (double)n * sizeof(cx<T>) / 1048576.0);
-        pl->desc = buf;
+        flat_desc = buf;
+    }
+    if (flat_ok && have_fallback) {
+        pl->desc = flat_desc;
     } else if (clustered_ok) {
         const int k = pl->kind == SSFFT_C2C ? 0 : 1;
         const ClusterEntry &e = cluster_registry()[pl->cl_id[k]];
@@ -692,6 +699,7 @@ real_wrappers:
         }
         pl->desc = std::string(modified ? "modified-real " : "real ") + "N=" + std::to_string(pl->n_real) + " core: " + pl->desc;
     }
+    if (flat_ok && !have_fallback) pl->desc = flat_desc + "; inputs without a tensor map: " + pl->desc;
     return SSFFT_OK;
 }
 

@@ -92,6 +92,67 @@ static double run(const float4 *in, float4 *out, float4 *scratch, long long n4, 
     return 2.0 * (double)tiles * TILE * 16 / (best * 1e-3) / 1e9;  // algorithmic GB/s
 }
 
+// The four-step access pattern: a tile is ROWS runs of RUNV float4 (RUNV * 16 bytes) at a pitch of PITCH4 float4 -- the
+// column tile of a transform of ROWS x (2 PITCH4) complex points on the way in (SIN), the transposed store of a row tile
+// on the way out (SOUT); the scratch round trip in between is contiguous as in the kernels.  Neighbouring CTAs take
+// neighbouring tiles of the same transform, as the ticket queue hands them out.
+template <int THREADS, int ROWS, int RUNV, bool SIN, bool SOUT, int PASSES>
+__global__ void __launch_bounds__(THREADS) fourstep_like_kernel(const float4 *in, float4 *out, float4 *scratch, long long tiles, int pitch4) {
+    constexpr int TILE = ROWS * RUNV, U = TILE / THREADS;
+    static_assert(TILE % THREADS == 0, "whole tile per pass of the CTA");
+    float4 *mine = scratch + (long long)blockIdx.x * TILE;
+    const int tpt = pitch4 / RUNV;  // tiles per transform
+    for (long long t = blockIdx.x; t < tiles; t += gridDim.x) {
+        const long long b = t / tpt;
+        const int j = (int)(t - b * tpt);
+        const long long base = b * (long long)ROWS * pitch4 + (long long)j * RUNV;
+        float4 v[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int e = u * THREADS + threadIdx.x, r = e / RUNV, i = e % RUNV;
+            v[u] = ld_stream(in + (SIN ? base + (long long)r * pitch4 + i : t * TILE + e));
+        }
+        if (PASSES > 1) {
+#pragma unroll
+            for (int u = 0; u < U; ++u) st_keep(mine + u * THREADS + threadIdx.x, v[u]);
+            __syncthreads();
+#pragma unroll
+            for (int u = 0; u < U; ++u) v[u] = ld_cg(mine + ((u * THREADS + threadIdx.x + TILE / 4) % TILE));
+            __syncthreads();
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int e = u * THREADS + threadIdx.x, r = e / RUNV, i = e % RUNV;
+            st_stream(out + (SOUT ? base + (long long)r * pitch4 + i : t * TILE + e), v[u]);
+        }
+    }
+}
+
+template <int THREADS, int ROWS, int RUNV, bool SIN, bool SOUT, int PASSES>
+static double run_like(const float4 *in, float4 *out, float4 *scratch, long long n4, int ctas_per_sm, int sms, int pitch4) {
+    constexpr int TILE = ROWS * RUNV;
+    const long long tiles = n4 / TILE;
+    const int grid = ctas_per_sm * sms;
+    cudaEvent_t a, b;
+    CK(cudaEventCreate(&a));
+    CK(cudaEventCreate(&b));
+    auto k = fourstep_like_kernel<THREADS, ROWS, RUNV, SIN, SOUT, PASSES>;
+    for (int i = 0; i < 2; ++i) k<<<grid, THREADS>>>(in, out, scratch, tiles, pitch4);
+    CK(cudaDeviceSynchronize());
+    float best = 1e30f;
+    for (int rep = 0; rep < 6; ++rep) {
+        CK(cudaEventRecord(a));
+        k<<<grid, THREADS>>>(in, out, scratch, tiles, pitch4);
+        CK(cudaEventRecord(b));
+        CK(cudaEventSynchronize(b));
+        float ms;
+        CK(cudaEventElapsedTime(&ms, a, b));
+        if (ms < best) best = ms;
+    }
+    CK(cudaGetLastError());
+    return 2.0 * (double)tiles * TILE * 16 / (best * 1e-3) / 1e9;
+}
+
 int main(int argc, char **argv) {
     const double peak = argc > 1 ? atof(argv[1]) : 6439.5;
     int sms = 0;
@@ -115,5 +176,26 @@ int main(int argc, char **argv) {
     for (int cps : {2, 4}) report(2, 512, 8, cps, run<512, 8, 2>(in, out, scratch, n4, cps, sms));
     for (int cps : {2, 4}) report(2, 1024, 4, cps, run<1024, 4, 2>(in, out, scratch, n4, cps, sms));
     for (int cps : {4, 8}) report(3, 256, 8, cps, run<256, 8, 3>(in, out, scratch, n4, cps, sms));
+    printf("#\n# four-step access pattern (tile = ROWS runs of RUN bytes at the row pitch of the transform), two passes, 4 CTAs/SM unless noted\n");
+    printf("# transform        run    strided side        algorithmic GB/s   fraction of the HBM roofline\n");
+    auto rep2 = [&](const char *shape, int run, const char *side, double gbs) {
+        printf("  %-14s  %4d B  %-18s  %8.1f           %5.1f %%\n", shape, run, side, gbs, 100.0 * gbs / peak);
+    };
+    // 2^16 = 256 x 256: pitch 2 KiB = 128 float4
+    rep2("256 x 256", 128, "in", run_like<256, 256, 8, true, false, 2>(in, out, scratch, n4, 4, sms, 128));
+    rep2("256 x 256", 128, "out", run_like<256, 256, 8, false, true, 2>(in, out, scratch, n4, 4, sms, 128));
+    rep2("256 x 256", 128, "in + out", run_like<256, 256, 8, true, true, 2>(in, out, scratch, n4, 4, sms, 128));
+    rep2("256 x 256", 128, "in + out, 1 pass", run_like<256, 256, 8, true, true, 1>(in, out, scratch, n4, 4, sms, 128));
+    rep2("256 x 256", 256, "in + out", run_like<512, 256, 16, true, true, 2>(in, out, scratch, n4, 2, sms, 128));
+    rep2("256 x 256", 512, "in + out", run_like<1024, 256, 32, true, true, 2>(in, out, scratch, n4, 2, sms, 128));
+    rep2("256 x 256", 64, "in + out", run_like<256, 256, 4, true, true, 2>(in, out, scratch, n4, 8, sms, 128));
+    // 2^18 = 512 x 512: pitch 4 KiB
+    rep2("512 x 512", 64, "in + out", run_like<256, 512, 4, true, true, 2>(in, out, scratch, n4, 4, sms, 256));
+    rep2("512 x 512", 128, "in + out", run_like<512, 512, 8, true, true, 2>(in, out, scratch, n4, 2, sms, 256));
+    rep2("512 x 512", 256, "in + out", run_like<1024, 512, 16, true, true, 2>(in, out, scratch, n4, 2, sms, 256));
+    // 2^20 = 1024 x 1024: pitch 8 KiB
+    rep2("1024 x 1024", 32, "in + out", run_like<256, 1024, 2, true, true, 2>(in, out, scratch, n4, 4, sms, 512));
+    rep2("1024 x 1024", 64, "in + out", run_like<512, 1024, 4, true, true, 2>(in, out, scratch, n4, 2, sms, 512));
+    rep2("1024 x 1024", 128, "in + out", run_like<1024, 1024, 8, true, true, 2>(in, out, scratch, n4, 2, sms, 512));
     return 0;
 }
