@@ -27,6 +27,7 @@
 #pragma once
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 
 #include "tiled.cuh"
 
@@ -91,7 +92,9 @@ struct FlatLayout {
     static constexpr size_t kExchA = CfgA::smem_bytes, kExchB = CfgB::smem_bytes;
     static constexpr size_t kExch = al(kExchA > kExchB ? kExchA : kExchB);
     static constexpr size_t kSBlk = KIND == 2 ? 0 : al((size_t)CfgA::CT * CfgA::radix(CfgA::NP - 1) * sizeof(cx<T>));
-    static constexpr size_t kSlot = INPLACE ? kExch + kSBlk : al(kSlotA > kSlotB ? kSlotA : kSlotB);
+    static constexpr size_t kLanded = al(kSlotA > kSlotB ? kSlotA : kSlotB);  // what the copies of one tile bring
+    static constexpr size_t kImage = kExch > kLanded ? kExch : kLanded;       // in place: landed tile and exchange buffer share it
+    static constexpr size_t kSlot = INPLACE ? kImage + kSBlk : kLanded;
     static constexpr bool kTwBShared = (size_t)CfgB::tw_total * sizeof(cx<T>) <= 2048;
     static constexpr size_t kTwB = kTwBShared ? al((size_t)(CfgB::tw_total > 0 ? CfgB::tw_total : 1) * sizeof(cx<T>)) : 0;
     static constexpr size_t oExch = 0, oSlots = oExch + (INPLACE ? 0 : kExch), oSBlk = oSlots + NSTAGE * kSlot,
@@ -233,7 +236,6 @@ __device__ __forceinline__ void flat_stage_a(const FlatParams<T> &q, const cx<T>
     static_assert(RL % 2 == 0, "pairs of last-pass twiddles are loaded together");
     const int c = tid % CT, t = tid / CT;    // lanes along the columns (global / ring accesses)
     const int t2 = tid % TX, c2 = tid / TX;  // last pass: lanes along k1 (scratch written in runs of consecutive k1)
-    static_assert(KIND == 0 || !INPLACE, "the real flavours use the separate exchange buffer");
     // column of a lane: contiguous, or (C2R) low half / mirrored high half, lane CT-1 of tile 0 = the self-paired N2/2
     auto col_of = [&](int lane) -> int {
         if constexpr (KIND != 2) return lane0 + lane;
@@ -280,7 +282,8 @@ __device__ __forceinline__ void flat_stage_a(const FlatParams<T> &q, const cx<T>
                     if (lane_self0 && n1 == 0) z = mk<T>(xo.x + xo.y, xo.x - xo.y);  // bin 0 packs (DC, Nyquist) (:478-481)
                     v[u * R + j] = cswap(z);  // inverse transform = forward transform of the swapped data
                 }
-            release();
+            if constexpr (INPLACE) consumer_barrier(NC);  // the landed boxes are read: the padded image may overwrite them
+            else release();
         } else if constexpr (first) {
 #pragma unroll
             for (int u = 0; u < U; ++u)
@@ -390,7 +393,7 @@ __host__ __device__ constexpr int flat_rho(int k1, int n1) { return k1 < n1 / 2 
 // ---- row tile of a real forward transform: HB = CT/2 rows k1 = HB tile + l and their partners n1 - k1 (two scratch
 // blocks of HB rows), length-L FFT each, then RealFFT::fft's post-twiddle (:459-472) on the pairs
 // (k1, k2) <-> (n1 - k1, L - 1 - k2) through the exchange buffer, stored as bins k = k1 + n1 k2 of the half spectrum.
-template <typename Cfg, int N1C, bool TWSH, typename T, typename Release>
+template <typename Cfg, int N1C, bool INPLACE, bool TWSH, typename T, typename Release>
 __device__ __forceinline__ void flat_stage_b_r2c(const FlatParams<T> &q, const cx<T> *twb, const cx<T> *st, cx<T> *sm, cx<T> *uout,
                                                  int tile, int tid, Release release) {
     constexpr int L = Cfg::L, TX = Cfg::TX, CT = Cfg::CT, E = Cfg::E, PITCH = Cfg::PITCH, NC = Cfg::THREADS, NP = Cfg::NP;
@@ -408,7 +411,8 @@ __device__ __forceinline__ void flat_stage_b_r2c(const FlatParams<T> &q, const c
             for (int u = 0; u < U; ++u)
 #pragma unroll
                 for (int j = 0; j < R; ++j) v[u * R + j] = src[(t + TX * u + NR * j) * H];
-            release();
+            if constexpr (INPLACE) consumer_barrier(NC);  // both landed blocks are read: the padded image may overwrite them
+            else release();
         } else {
 #pragma unroll
             for (int u = 0; u < U; ++u)
@@ -462,7 +466,10 @@ __device__ __forceinline__ void flat_stage_b_r2c(const FlatParams<T> &q, const c
                 }
             cx<T> zmid = mk<T>((T)0, (T)0);
             if (row0 && t == 0) zmid = sm[(L / 2) * PITCH];  // bin M/2 pairs with itself
-            consumer_barrier(NC);  // partners are in registers: the next tile may overwrite the exchange buffer
+            // partners are in registers: the next tile may overwrite the exchange buffer (in place: the slot may be refilled,
+            // and no consumer touches it again before that copy has landed)
+            if constexpr (INPLACE) release();
+            else consumer_barrier(NC);
             const int kph = (N1C - k1) & (N1C - 1);  // partner row (0 for row 0)
 #pragma unroll
             for (int u = 0; u < U; ++u)
@@ -553,7 +560,7 @@ __global__ void __launch_bounds__(CfgA::THREADS + kFlatHelpers, MINB)
 fourstep_flat_kernel(FlatParams<typename CfgA::T> q, const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap2) {
     using T = typename CfgA::T;
     using Lay = FlatLayout<CfgA, CfgB, NSTAGE, INPLACE, KIND>;
-    static_assert(KIND == 0 || (!INPLACE && INV == (KIND == 2)), "real flavours: separate exchange buffer, fixed direction");
+    static_assert(KIND == 0 || INV == (KIND == 2), "real flavours: fixed direction");
     static_assert(CfgA::THREADS == CfgB::THREADS, "both stages must use the same CTA size");
     constexpr int NC = CfgA::THREADS;
     constexpr int N1 = CfgA::L, N2 = CfgB::L;
@@ -693,7 +700,7 @@ fourstep_flat_kernel(FlatParams<typename CfgA::T> q, const __grid_constant__ CUt
                                     tma_tile_3d<T>(slot + LOW + HIGH + (size_t)r0 * H, &tmap, q.in, N1, N2, kBoxRows, H, N2 / 2, r0, cur.b, &full[s]);
                             }
                         } else if (cur.kind == 0) {
-                            cx<T> *sblk = INPLACE ? reinterpret_cast<cx<T> *>(reinterpret_cast<unsigned char *>(slot) + Lay::kExch)
+                            cx<T> *sblk = INPLACE ? reinterpret_cast<cx<T> *>(reinterpret_cast<unsigned char *>(slot) + Lay::kImage)
                                                   : reinterpret_cast<cx<T> *>(ssfft_smem + Lay::oSBlk + (size_t)(issued % NDONE) * Lay::kSBlk);
                             constexpr unsigned sbytes = (unsigned)(CfgA::CT * CfgA::radix(CfgA::NP - 1) * sizeof(cx<T>));
                             mbar_expect_tx(&full[s], (unsigned)Lay::kTileA + sbytes);
@@ -768,7 +775,7 @@ fourstep_flat_kernel(FlatParams<typename CfgA::T> q, const __grid_constant__ CUt
         auto release = [&]() { mbar_arrive(&empty[s]); };
         cx<T> *scr = q.scratch + (d.b % q.nslots) * q.scratch_per;
         if (d.kind == 0) {
-            const cx<T> *sblk = INPLACE ? reinterpret_cast<const cx<T> *>(reinterpret_cast<const unsigned char *>(st) + Lay::kExch)
+            const cx<T> *sblk = INPLACE ? reinterpret_cast<const cx<T> *>(reinterpret_cast<const unsigned char *>(st) + Lay::kImage)
                                         : reinterpret_cast<const cx<T> *>(ssfft_smem + Lay::oSBlk + (size_t)(j % NDONE) * Lay::kSBlk);
             flat_stage_a<CfgA, INV, N2, kCtbLog, INPLACE, KIND>(q, st, sblk, xb, scr, d.tile, tid, release);
         } else if constexpr (KIND == 1) {
@@ -778,7 +785,7 @@ fourstep_flat_kernel(FlatParams<typename CfgA::T> q, const __grid_constant__ CUt
                 const char *hi = reinterpret_cast<const char *>(scr + (long long)(N1 / H - 1 - d.tile) * H * N2);
                 for (int i = tid; i < 2 * kLines; i += NC) discard_l2_line((i < kLines ? lo : hi - (size_t)kLines * 128) + (size_t)i * 128);
             }
-            flat_stage_b_r2c<CfgB, N1, Lay::kTwBShared>(q, twb, st, xb, q.out + d.b * q.user_stride, d.tile, tid, release);
+            flat_stage_b_r2c<CfgB, N1, INPLACE, Lay::kTwBShared>(q, twb, st, xb, q.out + d.b * q.user_stride, d.tile, tid, release);
         } else {
             if (q.discard) {  // the block is in shared memory now: drop its lines from L2 without a write-back
                 constexpr int kLines = (int)(Lay::kTileB / 128);
@@ -818,16 +825,21 @@ struct FlatEntry {
 };
 const std::vector<FlatEntry> &flat_registry();
 
-// first registered entry of the size, or the variant named by SSFFT_FLAT_VARIANT="ring,ctas_per_sm[,inplace]"
+// first registered entry of the size (real_dir: -1 complex, 0 RealFFT forward, 1 RealFFT inverse -- the first entry that
+// carries that kernel), or the variant named by SSFFT_FLAT_VARIANT="ring,ctas_per_sm[,inplace]" / SSFFT_FLAT_NAME=<part of
+// the entry name> (SSFFT_FLAT_NAME_INV for the inverse real transform alone)
 template <typename T>
-inline int find_flat(size_t n1, size_t n2, bool need_real = false) {
+inline int find_flat(size_t n1, size_t n2, int real_dir = -1) {
     const int prec = sizeof(T) == 4 ? 0 : 1;
     const auto &reg = flat_registry();
     int want_ring = 0, want_minb = 0, want_inplace = 1;
     if (const char *e = getenv("SSFFT_FLAT_VARIANT")) sscanf(e, "%d,%d,%d", &want_ring, &want_minb, &want_inplace);
+    const char *want_name = getenv("SSFFT_FLAT_NAME");
+    if (real_dir == 1 && getenv("SSFFT_FLAT_NAME_INV")) want_name = getenv("SSFFT_FLAT_NAME_INV");
     int first = -1;
     for (size_t i = 0; i < reg.size(); ++i)
-        if (reg[i].prec == prec && (size_t)reg[i].n1 == n1 && (size_t)reg[i].n2 == n2 && (!need_real || reg[i].launch_real[0])) {
+        if (reg[i].prec == prec && (size_t)reg[i].n1 == n1 && (size_t)reg[i].n2 == n2 && (real_dir < 0 || reg[i].launch_real[real_dir])) {
+            if (want_name && *want_name && strstr(reg[i].name, want_name)) return (int)i;
             if (first < 0) first = (int)i;
             if (reg[i].nstage == want_ring && reg[i].minb == want_minb && reg[i].inplace == want_inplace) return (int)i;
         }

@@ -4,7 +4,8 @@
 #include "flat_launch.cuh"
 namespace ssfft {
 void register_flat_f32_a(std::vector<FlatEntry> &v) {
-    v.push_back(make_flat_entry<TileCfg<float, 256, 16, 16, 1, 16, 16, 3>, TileCfg<float, 256, 16, 16, 1, 16, 16, 3>, 2, 3, true>("float_flat_256x256_r2c3i"));
+    v.push_back(make_flat_entry<TileCfg<float, 256, 16, 16, 1, 16, 16, 3>, TileCfg<float, 256, 16, 16, 1, 16, 16, 3>, 2, 3, true, 3>("float_flat_256x256_r2c3i"));
     v.push_back(make_flat_entry<TileCfg<float, 256, 16, 16, 1, 16, 16, 3>, TileCfg<float, 256, 16, 16, 1, 16, 16, 3>, 1, 3, false>("float_flat_256x256_r1c3x"));
+    v.push_back(make_flat_entry<TileCfg<float, 256, 16, 16, 1, 16, 16, 3>, TileCfg<float, 256, 16, 16, 1, 16, 16, 3>, 1, 3, true, 3>("float_flat_256x256_r1c3i"));
 }
 }  // namespace ssfft

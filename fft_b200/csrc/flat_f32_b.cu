@@ -5,6 +5,7 @@
 namespace ssfft {
 void register_flat_f32_b(std::vector<FlatEntry> &v) {
     v.push_back(make_flat_entry<TileCfg<float, 128, 16, 8, 1, 8, 32, 3>, TileCfg<float, 256, 16, 16, 1, 16, 16, 3>, 1, 3, false>("float_flat_128x256_r1c3x"));
-    v.push_back(make_flat_entry<TileCfg<float, 128, 16, 8, 1, 8, 32, 3>, TileCfg<float, 256, 16, 16, 1, 16, 16, 3>, 2, 3, true>("float_flat_128x256_r2c3i"));
+    v.push_back(make_flat_entry<TileCfg<float, 128, 16, 8, 1, 8, 32, 3>, TileCfg<float, 256, 16, 16, 1, 16, 16, 3>, 2, 3, true, 3>("float_flat_128x256_r2c3i"));
+    v.push_back(make_flat_entry<TileCfg<float, 128, 16, 8, 1, 8, 32, 3>, TileCfg<float, 256, 16, 16, 1, 16, 16, 3>, 1, 3, true, 3>("float_flat_128x256_r1c3i"));
 }
 }  // namespace ssfft

@@ -51,7 +51,9 @@ int launch_flat(const void *params, int ctas, cudaStream_t s) {
     return cudaGetLastError() == cudaSuccess ? 0 : 2;
 }
 
-template <typename CfgA, typename CfgB, int NSTAGE, int MINB, bool INPLACE = true>
+// REAL: which RealFFT kernels of length 2 N1 N2 the entry carries -- bit 0 forward, bit 1 inverse (default: both for the
+// entries with a separate exchange buffer).  The first entry of a size that carries a direction is that direction's default.
+template <typename CfgA, typename CfgB, int NSTAGE, int MINB, bool INPLACE = true, int REAL = INPLACE ? 0 : 3>
 FlatEntry make_flat_entry(const char *name) {
     using Lay = FlatLayout<CfgA, CfgB, NSTAGE, INPLACE>;
     FlatEntry e;
@@ -70,11 +72,15 @@ FlatEntry make_flat_entry(const char *name) {
     e.max_ctas[1] = &flat_max_ctas<CfgA, CfgB, 1, NSTAGE, MINB, INPLACE>;
     e.launch_real[0] = e.launch_real[1] = nullptr;
     e.max_ctas_real[0] = e.max_ctas_real[1] = nullptr;
-    if constexpr (!INPLACE && CfgA::CT % 2 == 0 && CfgB::CT % 2 == 0 && CfgA::prod(CfgA::NP - 1) % (CfgB::CT / 2) == 0) {
-        e.launch_real[0] = &launch_flat<CfgA, CfgB, 0, NSTAGE, MINB, false, 1>;
-        e.launch_real[1] = &launch_flat<CfgA, CfgB, 1, NSTAGE, MINB, false, 2>;
-        e.max_ctas_real[0] = &flat_max_ctas<CfgA, CfgB, 0, NSTAGE, MINB, false, 1>;
-        e.max_ctas_real[1] = &flat_max_ctas<CfgA, CfgB, 1, NSTAGE, MINB, false, 2>;
+    constexpr bool real_ok = CfgA::CT % 2 == 0 && CfgB::CT % 2 == 0 && CfgA::prod(CfgA::NP - 1) % (CfgB::CT / 2) == 0;
+    static_assert(REAL == 0 || real_ok, "these tiles cannot carry the real flavours");
+    if constexpr ((REAL & 1) != 0) {
+        e.launch_real[0] = &launch_flat<CfgA, CfgB, 0, NSTAGE, MINB, INPLACE, 1>;
+        e.max_ctas_real[0] = &flat_max_ctas<CfgA, CfgB, 0, NSTAGE, MINB, INPLACE, 1>;
+    }
+    if constexpr ((REAL & 2) != 0) {
+        e.launch_real[1] = &launch_flat<CfgA, CfgB, 1, NSTAGE, MINB, INPLACE, 2>;
+        e.max_ctas_real[1] = &flat_max_ctas<CfgA, CfgB, 1, NSTAGE, MINB, INPLACE, 2>;
     }
     return e;
 }

