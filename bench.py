@@ -760,10 +760,14 @@ def main():
             # GPUs of the node over peer access while the other ranks wait
             try:
                 torch.cuda.empty_cache()
-                dist.barrier()
+                torch.cuda.synchronize()
+                # the other ranks wait on the CPU (gloo): an NCCL barrier would keep a spinning kernel on their GPUs
+                # while rank 0 is timing a transform that uses those GPUs
+                cpu_group = dist.new_group(backend="gloo")
+                dist.barrier(group=cpu_group)
                 if rank == 0:
                     configs["c5_c_abi"] = measure_dist_local(1 << 30, world)
-                dist.barrier()
+                dist.barrier(group=cpu_group)
             except Exception as exc:
                 configs["c5_c_abi"] = {"error": repr(exc)[:300]}
         configs["seconds"] = round(time.perf_counter() - t_cfg, 1)

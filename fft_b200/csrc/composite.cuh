@@ -1,0 +1,101 @@
+// composite.cuh -- N = R * M with a small radix R (2 ... 16) around one of the fast plans of length M.
+//
+// The reference factorises EVERY length into radix-2/3/4/generic steps (signalsmith-fft.h:99-150) and its benchmark walks
+// 2^k * {1, 3, 9} up to 2^24 (benchmark/benchmark.h:27-52).  The specialised kernels of this library cover 2^k up to 2^20
+// and 2^k * {3, 9} up to 9216; the lengths above used to fall to the pass interpreter (generic x generic, 7-15 % of the
+// HBM roofline).  This plan is one decimation-in-time step of radix R around the best plan of length M = N / R:
+//
+//   pre   y[k1][c]  = W_N^(c k1) * sum_r x[r M + c] W_R^(r k1)        (radix_pass_kernel: R strided rows in, R rows out,
+//                                                                      every access coalesced along c; the twiddle is the
+//                                                                      k1-th power of ONE table value W_N^c)
+//   inner Z[k1][.]  = FFT_M(y[k1][.])                                  (any plan of the library, R * batch transforms, in place)
+//   post  X[k1 + R k2] = Z[k1][k2]                                     (interleave_kernel: R rows in, one contiguous run out,
+//                                                                      staged through shared memory)
+//
+// in chunks of transforms small enough that y / Z stay in L2 between the three launches, so HBM is read once and written
+// once per transform whenever N * 8 bytes fits (N up to ~2^21); above that the passes stream through HBM.
+// Inverse transforms swap re / im on the way in and out, the same identity the other kernels use.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <vector>
+
+#include "codelets.cuh"
+#include "cplx.cuh"
+
+namespace ssfft {
+
+#ifdef __CUDACC__
+
+// w[k] = g^k for k < R (w[0] unused), products at most ~log2(R) deep
+template <int R, typename T>
+__device__ __forceinline__ void small_powers(cx<T> (&w)[R], cx<T> g) {
+    if constexpr (R > 1) w[1] = g;
+#pragma unroll
+    for (int k = 2; k < R; ++k) w[k] = cmul(w[k / 2], w[k - k / 2]);
+}
+
+template <typename T, int R>
+__global__ void __launch_bounds__(256) radix_pass_kernel(const cx<T> *__restrict__ in, cx<T> *__restrict__ out, const cx<T> *__restrict__ tw,
+                                                          long long m, long long batch, int inverse) {
+    const long long total = m * batch;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long b = i / m, c = i - b * m;
+        const cx<T> *src = in + b * m * R + c;
+        cx<T> v[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const cx<T> x = src[(long long)r * m];
+            v[r] = inverse ? cswap(x) : x;
+        }
+        Dft<R>::run(v);
+        cx<T> w[R];
+        small_powers<R>(w, tw[c]);
+        cx<T> *dst = out + b * m * R + c;
+        dst[0] = v[0];
+#pragma unroll
+        for (int k = 1; k < R; ++k) dst[(long long)k * m] = cmul(v[k], w[k]);
+    }
+}
+
+// out[b][k1 + R k2] = in[b][k1 M + k2]; a CTA moves tiles of 256 k2 x R through shared memory so that both sides are
+// whole, aligned runs
+template <typename T, int R>
+__global__ void __launch_bounds__(256) interleave_kernel(const cx<T> *__restrict__ in, cx<T> *__restrict__ out, long long m,
+                                                          long long batch, int inverse) {
+    constexpr int K2T = sizeof(T) == 8 ? 128 : 256, PITCH = K2T + 1;  // at most 33 KB of static shared memory (R = 16)
+    __shared__ cx<T> sm[R * PITCH];
+    const long long tiles_per = (m + K2T - 1) / K2T, tiles = tiles_per * batch;
+    for (long long t = blockIdx.x; t < tiles; t += gridDim.x) {
+        const long long b = t / tiles_per, k20 = (t - b * tiles_per) * K2T;
+        const int span = (int)(m - k20 < K2T ? m - k20 : K2T);
+        const cx<T> *src = in + b * m * R + k20;
+#pragma unroll
+        for (int k1 = 0; k1 < R; ++k1)
+            for (int x = threadIdx.x; x < span; x += 256) sm[k1 * PITCH + x] = src[(long long)k1 * m + x];
+        __syncthreads();
+        cx<T> *dst = out + b * m * R + k20 * R;
+        for (int j = threadIdx.x; j < span * R; j += 256) {
+            const cx<T> v = sm[(j % R) * PITCH + j / R];
+            dst[j] = inverse ? cswap(v) : v;
+        }
+        __syncthreads();
+    }
+}
+
+#endif  // __CUDACC__
+
+// tw[c] = W_N^c, c < m (interleaved re, im), N = r * m
+template <typename T>
+inline void fill_composite_twiddles(std::vector<T> &h, size_t r, size_t m) {
+    h.assign(2 * m, (T)0);
+    const long double pi2 = 2.0L * 3.14159265358979323846264338327950288L;
+    const long double n = (long double)r * (long double)m;
+    for (size_t c = 0; c < m; ++c) {
+        const long double a = pi2 * (long double)c / n;
+        h[2 * c] = (T)cosl(a);
+        h[2 * c + 1] = (T)(-sinl(a));
+    }
+}
+
+}  // namespace ssfft

@@ -8,5 +8,9 @@ void register_flat_f32_d(std::vector<FlatEntry> &v) {
     v.push_back(make_flat_entry<TileCfg<float, 512, 8, 8, 8, 32, 8, 3>, TileCfg<float, 1024, 16, 8, 8, 64, 4, 3>, 2, 3, true>("float_flat_512x1024_r2c3i"));
     v.push_back(make_flat_entry<TileCfg<float, 1024, 16, 8, 8, 64, 4, 3>, TileCfg<float, 1024, 16, 8, 8, 64, 4, 3>, 1, 3, false>("float_flat_1024x1024_r1c3x"));
     v.push_back(make_flat_entry<TileCfg<float, 1024, 16, 8, 8, 64, 4, 3>, TileCfg<float, 1024, 16, 8, 8, 64, 4, 3>, 2, 3, true>("float_flat_1024x1024_r2c3i"));
+    // first pass of radix 4: with 4 lanes per tile the first-pass stores of radix 16 hit rows 16 apart = the same banks
+    // (ncu r02c: 25 M conflicts on 47 M shared-memory wavefronts); rows 4 apart spread over all of them
+    v.push_back(make_flat_entry<TileCfg<float, 1024, 4, 16, 16, 64, 4, 3>, TileCfg<float, 1024, 4, 16, 16, 64, 4, 3>, 2, 3, true>("float_flat_1024x1024_p4_r2c3i"));
+    v.push_back(make_flat_entry<TileCfg<float, 512, 8, 8, 8, 32, 8, 3>, TileCfg<float, 1024, 4, 16, 16, 64, 4, 3>, 2, 3, true>("float_flat_512x1024_p4_r2c3i"));
 }
 }  // namespace ssfft

@@ -86,8 +86,6 @@ void register_flat_f32_b(std::vector<FlatEntry> &);
 void register_flat_f32_c(std::vector<FlatEntry> &);
 void register_flat_f32_d(std::vector<FlatEntry> &);
 void register_flat_f32_e(std::vector<FlatEntry> &);
-void register_flat_f32_f(std::vector<FlatEntry> &);
-void register_flat_f32_g(std::vector<FlatEntry> &);
 
 const std::vector<FlatEntry> &flat_registry() {
     static const std::vector<FlatEntry> reg = [] {
@@ -100,8 +98,6 @@ const std::vector<FlatEntry> &flat_registry() {
         register_flat_f32_c(v);
         register_flat_f32_d(v);
         register_flat_f32_e(v);
-        register_flat_f32_f(v);
-        register_flat_f32_g(v);
         return v;
     }();
     return reg;

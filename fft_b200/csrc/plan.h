@@ -72,6 +72,11 @@ struct ssfft_plan {
     void *d_flat_ra[2] = {nullptr, nullptr}, *d_flat_rb[2] = {nullptr, nullptr};  // post- / pre-twiddle factors [fwd, inv]
 
     // Bluestein (bluestein.cuh): lengths whose largest prime factor fits no on-chip path run as a convolution through
+    // composite plan (composite.cuh): N = comp_r * M, one radix pass + the plan of length M + an interleave pass
+    ssfft_plan *comp_inner = nullptr;
+    int comp_r = 0;
+    size_t comp_chunk = 0;                  // transforms per trip through the work buffer
+    void *d_comp_tw = nullptr, *d_comp_work = nullptr;
     // an inner power-of-two plan of length bs_m
     ssfft_plan *bs_inner = nullptr;
     size_t bs_m = 0, bs_chunk = 0;          // convolution length, transforms per pass through the work buffers

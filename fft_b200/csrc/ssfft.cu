@@ -16,6 +16,7 @@
 #include <vector>
 
 #include "bluestein.cuh"
+#include "composite.cuh"
 #include "cluster.cuh"
 #include "ex_request.h"
 #include "flat.cuh"
@@ -77,7 +78,7 @@ struct PlanExec {
     }
 };
 bool plan_is_stateful(const ssfft_plan *pl) {  // owns device state that a concurrent call would trample
-    return pl->d_scratch || pl->d_flat_scratch || pl->d_ex_in || pl->d_ex_out || pl->bs_inner;
+    return pl->d_scratch || pl->d_flat_scratch || pl->d_ex_in || pl->d_ex_out || pl->bs_inner || pl->comp_inner;
 }
 
 int max_optin_smem(int device) {
@@ -479,6 +480,98 @@ int exec_clustered(ssfft_plan *pl, int kind, const void *in, void *out, long lon
     return SSFFT_OK;
 }
 
+// Composite plan (composite.cuh): is there a small radix R such that M = N / R has one of the fast plans?
+// fast = a registered single-pass kernel, or a power of two the four-step kernels cover.  Larger R first: the inner
+// transform is the slower part, and shorter inner transforms are faster.
+template <typename T>
+bool composite_inner_is_fast(size_t m) {
+    if (find_fused<T>(m, 0) >= 0) return true;
+    return m >= ((size_t)1 << 14) && m <= ((size_t)1 << 20) && (m & (m - 1)) == 0;
+}
+template <typename T>
+int choose_composite_radix(size_t n) {
+    if (env_int("SSFFT_DISABLE_COMPOSITE", 0)) return 0;
+    const int forced = env_int("SSFFT_COMPOSITE_RADIX", 0);
+    static const int radices[] = {16, 9, 8, 4, 3, 2};
+    if (forced > 0) {
+        for (int r : radices)
+            if (r == forced && n % (size_t)r == 0) return r;
+        return 0;
+    }
+    for (int r : radices)
+        if (n % (size_t)r == 0 && composite_inner_is_fast<T>(n / (size_t)r)) return r;
+    // two levels (3 * 2^21 = 3 x (16 x 2^17), ...): the inner plan is itself a composite
+    for (int r : radices)
+        if (n % (size_t)r == 0)
+            for (int r2 : radices)
+                if ((n / (size_t)r) % (size_t)r2 == 0 && composite_inner_is_fast<T>(n / (size_t)r / (size_t)r2)) return r;
+    return 0;
+}
+template <typename T>
+int setup_composite(ssfft_plan *pl, int r) {
+    const size_t n = pl->n, m = n / (size_t)r;
+    int rc = ssfft_plan_create(&pl->comp_inner, SSFFT_C2C, pl->prec, m, pl->device);
+    if (rc) return rc;
+    pl->comp_r = r;
+    std::vector<T> h;
+    fill_composite_twiddles<T>(h, (size_t)r, m);
+    CU(cudaMalloc(&pl->d_comp_tw, h.size() * sizeof(T)));
+    CU(cudaMemcpy(pl->d_comp_tw, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+    // transforms per trip: the work buffer (written by the radix pass, transformed in place, read by the interleave
+    // pass) should stay in L2 between the launches
+    pl->comp_chunk = ((size_t)env_int("SSFFT_COMPOSITE_MB", 40) << 20) / (n * sizeof(cx<T>));
+    if (pl->comp_chunk < 1) pl->comp_chunk = 1;
+    CU(cudaMalloc(&pl->d_comp_work, pl->comp_chunk * n * sizeof(cx<T>)));
+    return SSFFT_OK;
+}
+template <typename T, int R>
+int launch_composite_passes(bool pre, const cx<T> *in, cx<T> *out, const cx<T> *tw, long long m, long long nb, int inverse, cudaStream_t s) {
+    int sms = 148, dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (pre) {
+        long long blocks = (m * nb + 255) / 256;
+        if (blocks > (long long)sms * 16) blocks = (long long)sms * 16;
+        radix_pass_kernel<T, R><<<(unsigned)blocks, 256, 0, s>>>(in, out, tw, m, nb, inverse);
+    } else {
+        constexpr int K2T = sizeof(T) == 8 ? 128 : 256;
+        long long blocks = ((m + K2T - 1) / K2T) * nb;
+        if (blocks > (long long)sms * 8) blocks = (long long)sms * 8;
+        interleave_kernel<T, R><<<(unsigned)blocks, 256, 0, s>>>(in, out, m, nb, inverse);
+    }
+    ++g_launches;
+    CU(cudaGetLastError());
+    return SSFFT_OK;
+}
+template <typename T>
+int composite_pass(int r, bool pre, const cx<T> *in, cx<T> *out, const cx<T> *tw, long long m, long long nb, int inverse, cudaStream_t s) {
+    switch (r) {
+        case 2: return launch_composite_passes<T, 2>(pre, in, out, tw, m, nb, inverse, s);
+        case 3: return launch_composite_passes<T, 3>(pre, in, out, tw, m, nb, inverse, s);
+        case 4: return launch_composite_passes<T, 4>(pre, in, out, tw, m, nb, inverse, s);
+        case 8: return launch_composite_passes<T, 8>(pre, in, out, tw, m, nb, inverse, s);
+        case 9: return launch_composite_passes<T, 9>(pre, in, out, tw, m, nb, inverse, s);
+        case 16: return launch_composite_passes<T, 16>(pre, in, out, tw, m, nb, inverse, s);
+    }
+    return SSFFT_ERR_INVALID;
+}
+template <typename T>
+int exec_composite(ssfft_plan *pl, const void *in, void *out, long long batch, int inverse, cudaStream_t s) {
+    const long long n = (long long)pl->n, r = pl->comp_r, m = n / r;
+    cx<T> *work = (cx<T> *)pl->d_comp_work;
+    for (long long b0 = 0; b0 < batch; b0 += (long long)pl->comp_chunk) {
+        const long long nb = batch - b0 < (long long)pl->comp_chunk ? batch - b0 : (long long)pl->comp_chunk;
+        int rc = composite_pass<T>((int)r, true, (const cx<T> *)in + b0 * n, work, (const cx<T> *)pl->d_comp_tw, m, nb, inverse, s);
+        if (rc) return rc;
+        // the re / im swap of an inverse transform is done by the two passes around it: the inner transform runs forward
+        rc = ssfft_exec_c2c(pl->comp_inner, work, work, (size_t)(nb * r), SSFFT_FORWARD, s);
+        if (rc) return rc;
+        rc = composite_pass<T>((int)r, false, work, (cx<T> *)out + b0 * n, nullptr, m, nb, inverse, s);
+        if (rc) return rc;
+    }
+    return SSFFT_OK;
+}
+
 // Bluestein: inner plan of length M = 2^k >= 2n - 1, chirp table, spectrum of the wrapped conjugate chirp, work buffers.
 template <typename T>
 int setup_bluestein(ssfft_plan *pl) {
@@ -535,6 +628,7 @@ int exec_complex(ssfft_plan *pl, const void *in, void *out, long long batch, int
     const long long n = (long long)pl->n;
     if (batch <= 0 || n == 0) return SSFFT_OK;
     if (pl->bs_inner) return exec_bluestein<T>(pl, in, out, batch, inverse, s);
+    if (pl->comp_inner) return exec_composite<T>(pl, in, out, batch, inverse, s);
     if (pl->flat_id >= 0 && pl->kind == SSFFT_C2C) {
         const int rc = exec_flat<T>(pl, in, out, batch, inverse, s);
         if (rc >= 0) return rc;
@@ -656,6 +750,15 @@ int build_plan_typed(ssfft_plan *pl) {
         else
             snprintf(buf, sizeof(buf), "n=%zu single-pass generic radices=%s tx=%d fpb=%d smem=%zu", n, rs.c_str(),
                      pl->direct.tx, pl->direct.fpb, pl->direct.smem_bytes);
+        pl->desc = buf;
+    } else if (const int comp_r = choose_composite_radix<T>(n)) {
+        int rc = setup_composite<T>(pl, comp_r);
+        if (rc) return rc;
+        char inner[400] = "";
+        ssfft_plan_describe(pl->comp_inner, inner, sizeof(inner));
+        snprintf(buf, sizeof(buf), "n=%zu composite: radix-%d pass + %d x (n=%zu) + interleave, %zu transform(s) per trip through a %.0f MiB "
+                 "work buffer; inner plan: %.300s", n, comp_r, comp_r, n / (size_t)comp_r, pl->comp_chunk,
+                 pl->comp_chunk * (double)n * sizeof(cx<T>) / 1048576.0, inner);
         pl->desc = buf;
     } else {
         GenericFourStep fs;
@@ -960,6 +1063,9 @@ int ssfft_plan_destroy(ssfft_plan *pl) {
         if (pl->d_cl_tw4[k]) cudaFree(pl->d_cl_tw4[k]);
     }
     if (pl->bs_inner) ssfft_plan_destroy(pl->bs_inner);
+    if (pl->comp_inner) ssfft_plan_destroy(pl->comp_inner);
+    for (void *p : {pl->d_comp_tw, pl->d_comp_work})
+        if (p) cudaFree(p);
     for (void *p : {pl->d_bs_chirp, pl->d_bs_filter, pl->d_bs_work[0], pl->d_bs_work[1]})
         if (p) cudaFree(p);
     for (int i = 0; i < ssfft_plan::kRing; ++i) {

@@ -60,6 +60,8 @@ def run(n, world, chunks, transposed, iters=5):
             tones.append(torch.complex(torch.cos(ph), torch.sin(ph)).to(torch.complex64))
             del idx, ph
         touts = [torch.empty_like(t) for t in tones]
+        for r in range(world):
+            torch.cuda.synchronize(r)  # the plan runs on its own streams: the tones must exist before it reads them
         plan.fft(tones, touts)
         plan.synchronize()
         e_all = sum((t.real.double() ** 2 + t.imag.double() ** 2).sum().item() for t in touts)
