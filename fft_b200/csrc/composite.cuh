@@ -12,8 +12,9 @@
 //   post  X[k1 + R k2] = Z[k1][k2]                                     (interleave_kernel: R rows in, one contiguous run out,
 //                                                                      staged through shared memory)
 //
-// in chunks of transforms small enough that y / Z stay in L2 between the three launches, so HBM is read once and written
-// once per transform whenever N * 8 bytes fits (N up to ~2^21); above that the passes stream through HBM.
+// Three trips through HBM instead of one: 15-25 % of the roofline where the pass interpreter reached 7-9 % (measured,
+// profiles/sweep_r02n_f32.txt).  Keeping y / Z in L2 between the launches (short trips) was measured slower than streaming.
+// The next step for these lengths is the ticket-queue four-step with a 3 * 2^k / 9 * 2^k row stage (two trips, one in L2).
 // Inverse transforms swap re / im on the way in and out, the same identity the other kernels use.
 #pragma once
 #include <cuda_runtime.h>

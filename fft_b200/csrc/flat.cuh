@@ -461,7 +461,7 @@ __device__ __forceinline__ void flat_stage_b_r2c(const FlatParams<T> &q, const c
 #pragma unroll
                 for (int r = 0; r < R / 2; ++r) {
                     const int k2 = t + TX * u + P * r;
-                    const int kp = row0 ? ((L - k2) & (L - 1)) : L - 1 - k2;
+                    const int kp = row0 ? (k2 ? L - k2 : 0) : L - 1 - k2;
                     zp[u * (R / 2) + r] = sm[kp * PITCH + pl];
                 }
             cx<T> zmid = mk<T>((T)0, (T)0);

@@ -86,6 +86,7 @@ void register_flat_f32_b(std::vector<FlatEntry> &);
 void register_flat_f32_c(std::vector<FlatEntry> &);
 void register_flat_f32_d(std::vector<FlatEntry> &);
 void register_flat_f32_e(std::vector<FlatEntry> &);
+void register_flat_f32_h(std::vector<FlatEntry> &);
 
 const std::vector<FlatEntry> &flat_registry() {
     static const std::vector<FlatEntry> reg = [] {
@@ -98,6 +99,7 @@ const std::vector<FlatEntry> &flat_registry() {
         register_flat_f32_c(v);
         register_flat_f32_d(v);
         register_flat_f32_e(v);
+        register_flat_f32_h(v);
         return v;
     }();
     return reg;

@@ -307,12 +307,21 @@ int setup_flat(ssfft_plan *pl, bool *ok) {
     *ok = false;
     const size_t n = pl->n;  // complex length (real plans: N / 2)
     const bool real = pl->kind == SSFFT_REAL;
-    if ((pl->kind != SSFFT_C2C && !real) || n == 0 || (n & (n - 1))) return SSFFT_OK;
+    if ((pl->kind != SSFFT_C2C && !real) || n == 0 || env_int("SSFFT_DISABLE_FLAT", 0)) return SSFFT_OK;
     if (real && env_int("SSFFT_DISABLE_FLAT_REAL", 0)) return SSFFT_OK;
-    int lg = 0;
-    while (((size_t)1 << lg) < n) ++lg;
-    if (lg < env_int("SSFFT_FLAT_MIN_LOG2", 15)) return SSFFT_OK;
-    const size_t n1 = (size_t)1 << (lg / 2), n2 = n / n1;
+    size_t n1 = 0, n2 = 0;
+    if ((n & (n - 1)) == 0) {
+        int lg = 0;
+        while (((size_t)1 << lg) < n) ++lg;
+        if (lg < env_int("SSFFT_FLAT_MIN_LOG2", 15)) return SSFFT_OK;
+        n1 = (size_t)1 << (lg / 2);
+        n2 = n / n1;
+    } else {
+        // 3 * 2^k: the registered (power of two) x (3 * 2^j) pair of this length, if there is one
+        for (const FlatEntry &e : flat_registry())
+            if (e.prec == (sizeof(T) == 4 ? 0 : 1) && (size_t)e.n1 * (size_t)e.n2 == n) { n1 = (size_t)e.n1; n2 = (size_t)e.n2; break; }
+        if (!n1) return SSFFT_OK;
+    }
     const int id = find_flat<T>(n1, n2, real ? 0 : -1);
     if (id < 0) return SSFFT_OK;
     const FlatEntry &e = flat_registry()[id];
@@ -517,9 +526,11 @@ int setup_composite(ssfft_plan *pl, int r) {
     fill_composite_twiddles<T>(h, (size_t)r, m);
     CU(cudaMalloc(&pl->d_comp_tw, h.size() * sizeof(T)));
     CU(cudaMemcpy(pl->d_comp_tw, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
-    // transforms per trip: the work buffer (written by the radix pass, transformed in place, read by the interleave
-    // pass) should stay in L2 between the launches
-    pl->comp_chunk = ((size_t)env_int("SSFFT_COMPOSITE_MB", 40) << 20) / (n * sizeof(cx<T>));
+    // transforms per trip through the work buffer.  MEASURED (profiles/sweep_r02n_mb_f32.txt): trips small enough to keep
+    // the buffer in L2 (16 / 40 / 96 MiB) are slower than streaming everything through HBM (49152: 16.7 / 21.2 / 23.1 vs
+    // 24.5 % of the roofline; 2^21: 11.7 / 15.4 / 17.9 vs 19.6 %) -- three short launches per trip cost more than the L2 hits
+    // save -- so the buffer is only bounded to keep its footprint reasonable
+    pl->comp_chunk = ((size_t)env_int("SSFFT_COMPOSITE_MB", 1024) << 20) / (n * sizeof(cx<T>));
     if (pl->comp_chunk < 1) pl->comp_chunk = 1;
     CU(cudaMalloc(&pl->d_comp_work, pl->comp_chunk * n * sizeof(cx<T>)));
     return SSFFT_OK;

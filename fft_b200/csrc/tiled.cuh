@@ -68,7 +68,8 @@ struct TileCfg {
     static constexpr size_t smem_bytes = (size_t)L * PITCH * sizeof(cx<T>);
     static_assert(R0_ * R1_ * R2_ == L_, "radices must multiply to L");
     static_assert(E % R0_ == 0 && E % R1_ == 0 && E % R2_ == 0, "E must be a multiple of every radix");
-    static_assert((L_ & (L_ - 1)) == 0, "tile kernels are power-of-two only");
+    // (the kernels of tiled.cuh / cluster.cuh are only instantiated for powers of two; flat.cuh also runs row stages of
+    // length 3 * 2^k, whose radices are not powers of two)
 };
 
 template <typename T>

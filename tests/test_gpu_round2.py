@@ -183,3 +183,43 @@ def test_single_process_distributed_plan_logical_ranks(oracle, cuda_device, worl
         assert oracle.rel_l2(t.T.reshape(1, n), ref) <= tol(n, np.complex64), (n, world, "transposed")
         plan.close()
         tp.close()
+
+
+@pytest.mark.parametrize("prec", ["float32", "float64"])
+@pytest.mark.parametrize("n", [24576, 18432, 49152, 147456, 786432, 1 << 21, 1 << 22, 3 << 21, 1 << 24])
+def test_composite_lengths_vs_oracle(oracle, cuda_device, prec, n):
+    """The reference's benchmark set (benchmark/benchmark.h:27-52: 2^k x {1, 3, 9} up to 2^24) beyond the specialised
+    kernels: one radix pass around a fast plan (composite.cuh).  Against the oracle, forward and inverse, batch > 1 for the
+    shorter lengths, plus the real transform of twice the length."""
+    if prec == "float64" and n > (1 << 22):
+        pytest.skip("covered in float32; keeps the suite short")
+    npdt = np.complex64 if prec == "float32" else np.complex128
+    f = fft_b200.FFT(n, dtype=prec)
+    assert "composite" in f.describe(), f.describe()
+    batch = 3 if n <= (1 << 20) else 1
+    x = oracle.uniform_complex((batch, n), 31, npdt)
+    xd = torch.from_numpy(x).cuda()
+    y = torch.empty_like(xd)
+    z = torch.empty_like(xd)
+    f.fft(xd, y)
+    f.ifft(y, z)
+    torch.cuda.synchronize()
+    want = oracle.run(oracle.KIND_C2C_FWD, x, n, threads=8)[0]
+    err = oracle.rel_l2(y.cpu().numpy(), want)
+    assert err <= tol(n, npdt), (n, prec, err, f.describe())
+    want_inv = oracle.run(oracle.KIND_C2C_INV, want, n, threads=8)[0]
+    assert oracle.rel_l2(z.cpu().numpy(), want_inv) <= 2 * tol(n, npdt), (n, prec)
+    assert torch.equal(xd.cpu(), torch.from_numpy(x)), "input was modified"
+    if n <= (1 << 21):
+        rdt = np.float32 if prec == "float32" else np.float64
+        r = fft_b200.RealFFT(2 * n, dtype=prec)
+        xr = oracle.uniform(2 * n, 32, rdt).reshape(1, 2 * n)
+        xrd = torch.from_numpy(xr).cuda()
+        spec = torch.empty((1, n), dtype=xd.dtype, device="cuda")
+        back = torch.empty_like(xrd)
+        r.fft(xrd, spec)
+        r.ifft(spec, back)
+        torch.cuda.synchronize()
+        want_r = oracle.run(oracle.KIND_R2C, xr, 2 * n, threads=8)[0]
+        assert oracle.rel_l2(spec.cpu().numpy(), want_r) <= tol(2 * n, npdt), (2 * n, prec, r.describe())
+        assert oracle.rel_l2(back.cpu().numpy() / (2 * n), xr) <= 2 * tol(2 * n, npdt)
