@@ -14,12 +14,12 @@ void register_flat_f32_h(std::vector<FlatEntry> &v) {
     using B192 = TileCfg<float, 192, 4, 4, 12, 16, 16, 3>;  // 12 points per thread
     using B384 = TileCfg<float, 384, 8, 6, 8, 16, 16, 2>;   // 24 points per thread: 2 CTAs/SM
     using B768 = TileCfg<float, 768, 8, 12, 8, 32, 8, 2>;   // 24 points per thread: 2 CTAs/SM
-    v.push_back(make_flat_entry<A128, B96, 2, 3, true, 0>("float_flat_128x96_r2c3i"));      // 12288
-    v.push_back(make_flat_entry<A128, B192, 2, 3, true, 0>("float_flat_128x192_r2c3i"));    // 24576
-    v.push_back(make_flat_entry<A256, B192, 2, 3, true, 0>("float_flat_256x192_r2c3i"));    // 49152
-    v.push_back(make_flat_entry<A256, B384, 2, 2, true, 0>("float_flat_256x384_r2c2i"));    // 98304
-    v.push_back(make_flat_entry<A256, B768, 2, 2, true, 0>("float_flat_256x768_r2c2i"));    // 196608
-    v.push_back(make_flat_entry<A512, B768, 2, 2, true, 0>("float_flat_512x768_r2c2i"));    // 393216
-    v.push_back(make_flat_entry<A1024, B768, 2, 2, true, 0>("float_flat_1024x768_r2c2i"));  // 786432
+    v.push_back(make_flat_entry<A128, B96, 2, 3, true, 3>("float_flat_128x96_r2c3i"));      // 12288
+    v.push_back(make_flat_entry<A128, B192, 2, 3, true, 3>("float_flat_128x192_r2c3i"));    // 24576
+    v.push_back(make_flat_entry<A256, B192, 2, 3, true, 3>("float_flat_256x192_r2c3i"));    // 49152
+    v.push_back(make_flat_entry<A256, B384, 2, 2, true, 3>("float_flat_256x384_r2c2i"));    // 98304
+    v.push_back(make_flat_entry<A256, B768, 2, 2, true, 3>("float_flat_256x768_r2c2i"));    // 196608
+    v.push_back(make_flat_entry<A512, B768, 2, 2, true, 3>("float_flat_512x768_r2c2i"));    // 393216
+    v.push_back(make_flat_entry<A1024, B768, 2, 2, true, 3>("float_flat_1024x768_r2c2i"));  // 786432
 }
 }  // namespace ssfft

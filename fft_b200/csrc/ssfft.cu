@@ -638,12 +638,12 @@ template <typename T>
 int exec_complex(ssfft_plan *pl, const void *in, void *out, long long batch, int inverse, cudaStream_t s) {
     const long long n = (long long)pl->n;
     if (batch <= 0 || n == 0) return SSFFT_OK;
-    if (pl->bs_inner) return exec_bluestein<T>(pl, in, out, batch, inverse, s);
-    if (pl->comp_inner) return exec_composite<T>(pl, in, out, batch, inverse, s);
-    if (pl->flat_id >= 0 && pl->kind == SSFFT_C2C) {
+    if (pl->flat_id >= 0 && pl->kind == SSFFT_C2C) {  // first: the other paths of such a plan are its fallback
         const int rc = exec_flat<T>(pl, in, out, batch, inverse, s);
         if (rc >= 0) return rc;
     }
+    if (pl->bs_inner) return exec_bluestein<T>(pl, in, out, batch, inverse, s);
+    if (pl->comp_inner) return exec_composite<T>(pl, in, out, batch, inverse, s);
     if (pl->clustered && pl->kind == SSFFT_C2C) return exec_clustered<T>(pl, 0, in, out, batch, inverse, s);
     if (pl->tiled && pl->kind == SSFFT_C2C) return exec_tiled<T>(pl, 0, in, out, batch, inverse, s);
     if (!pl->four_step) {

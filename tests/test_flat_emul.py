@@ -22,15 +22,25 @@ HOST = os.path.join(ROOT, "tests", "host")
 _PAIR = re.compile(r'make_flat_entry<TileCfg<([^>]*)>,\s*TileCfg<([^>]*)>,\s*(\d+),\s*(\d+)(?:,\s*\w+)*>\("([^"]*)"\)')
 
 
+_ALIAS = re.compile(r'using\s+(\w+)\s*=\s*(TileCfg<[^>]*>)\s*;')
+
+
 def registered_pairs():
     out = {}
     for name in sorted(os.listdir(CSRC)):
         if not re.match(r"flat_f(32|64)_[a-z]\.cu$", name):
             continue
+        aliases = {}
         for line in open(os.path.join(CSRC, name)):
             line = line.split("//")[0]
+            a = _ALIAS.search(line)
+            if a:
+                aliases[a.group(1)] = a.group(2)
+                continue
             if "push_back" not in line:
                 continue
+            for alias, full in aliases.items():  # `using A256 = TileCfg<...>;` names used in the entries
+                line = re.sub(r"\b%s\b" % alias, full, line)
             m = _PAIR.search(line)
             assert m, f"unparsed registry line in {name}: {line}"
             out.setdefault((m.group(1), m.group(2)), m.group(5))  # ring depth / CTAs per SM do not matter on the CPU

@@ -153,3 +153,41 @@ def test_flat_real_large_batch_round_trip(oracle, cuda_device):
     assert err <= 2 * tol(n), err
     idx = [0, 1, batch // 2, batch - 1]
     assert oracle.rel_l2(spec[idx].cpu().numpy(), oracle.rfft(xd[idx].cpu().numpy())) <= tol(n)
+
+
+@pytest.mark.parametrize("n", [12288, 24576, 49152, 98304, 196608, 393216, 786432])
+def test_flat_three_times_power_of_two(oracle, cuda_device, n):
+    """Row stages of length 3 * 2^j (flat_f32_h.cu): the 2^k * 3 half of the reference's benchmark sizes
+    (benchmark/benchmark.h:27-52) above the single-pass kernels, forward and inverse, several batch shapes, in place, and
+    the real transform of twice the length (complex core on these kernels)."""
+    f = fft_b200.FFT(n)
+    assert "ticket-queue" in f.describe(), f.describe()
+    for batch in (1, 5, max(2, 2 ** 23 // n)):
+        x = oracle.uniform_complex((batch, n), 41 + batch, np.complex64)
+        xd = torch.from_numpy(x).cuda()
+        out = torch.empty_like(xd)
+        for inverse in (False, True):
+            out.zero_()
+            (f.ifft if inverse else f.fft)(xd, out)
+            torch.cuda.synchronize()
+            assert torch.equal(xd.cpu(), torch.from_numpy(x)), "input was changed"
+            ref = oracle.run(oracle.KIND_C2C_INV if inverse else oracle.KIND_C2C_FWD, x, n, threads=8)[0]
+            err = oracle.rel_l2(out.cpu().numpy(), ref)
+            assert err <= tol(n), (n, batch, inverse, err, f.describe())
+    x = oracle.uniform_complex((7, n), 6, np.complex64)
+    xd = torch.from_numpy(x).cuda()
+    launches = fft_b200.launch_count()
+    f.fft(xd, xd)
+    torch.cuda.synchronize()
+    assert fft_b200.launch_count() - launches == 1, "the plan's fallback path ran instead of the one persistent launch"
+    assert oracle.rel_l2(xd.cpu().numpy(), oracle.run(oracle.KIND_C2C_FWD, x, n, threads=8)[0]) <= tol(n)
+    r = fft_b200.RealFFT(2 * n)
+    xr = oracle.uniform(3 * 2 * n, 8, np.float32).reshape(3, 2 * n)
+    xrd = torch.from_numpy(xr).cuda()
+    spec = torch.empty((3, n), dtype=torch.complex64, device="cuda")
+    back = torch.empty_like(xrd)
+    r.fft(xrd, spec)
+    r.ifft(spec, back)
+    torch.cuda.synchronize()
+    assert oracle.rel_l2(spec.cpu().numpy(), oracle.run(oracle.KIND_R2C, xr, 2 * n, threads=8)[0]) <= tol(2 * n), r.describe()
+    assert oracle.rel_l2(back.cpu().numpy() / (2 * n), xr) <= 2 * tol(2 * n)

@@ -86,7 +86,7 @@ def main():
     for world in (2, 4, 8):
         if world > ngpu:
             continue
-        for chunks in (1, 2, 4, 8):
+        for chunks in [int(c) for c in os.environ.get("SSFFT_BENCH_DIST_CHUNKS", "1,2,4,8").split(",")]:
             for transposed in (False, True):
                 if transposed and chunks not in (1, 4):
                     continue
