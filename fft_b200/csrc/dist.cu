@@ -97,7 +97,12 @@ int ssfft_dist_plan_create(ssfft_dist_plan **out, int precision, size_t n, int n
     p->prec = precision; p->ndev = ndev; p->flags = flags; p->n = n; p->n1 = best1; p->n2 = n / best1;
     p->a = p->n1 / ndev; p->b = p->n2 / ndev;
     p->elem = precision == SSFFT_F32 ? 8 : 16;
-    int chunks = 4;
+    // chunks per phase.  MEASURED (profiles/bench_dist_local_8gpu_r02q.txt, bench_dist_share_r02r.txt): the exchange of
+    // chunk c does not run beside the transform of chunk c + 1 to any effect -- 2 GPUs 13.9 / 14.1 / 14.0 / 14.1 ms with
+    // 1 / 2 / 4 / 8 chunks, 8 GPUs 5.46 vs 5.67 ms with 1 vs 4, the same with the transforms capped at 2 of 3 CTAs per SM
+    // and a higher stream priority: both kernels want the whole SM (the transforms are bound by instruction issue, the
+    // exchange needs its full occupancy to keep NVLink busy), so sharing only time-slices them.  Default: one chunk.
+    int chunks = 1;
     if (const char *e = getenv("SSFFT_DIST_CHUNKS")) chunks = atoi(e);
     while (chunks > 1 && (p->a % chunks || p->b % chunks)) --chunks;
     p->chunks = chunks < 1 ? 1 : chunks;
@@ -125,8 +130,17 @@ int ssfft_dist_plan_create(ssfft_dist_plan **out, int precision, size_t n, int n
             rc = SSFFT_ERR_ALLOC;
             break;
         }
-        bool ok = cudaStreamCreateWithFlags(&d.s_fft, cudaStreamNonBlocking) == cudaSuccess &&
-                  cudaStreamCreateWithFlags(&d.s_x, cudaStreamNonBlocking) == cudaSuccess &&
+        // the exchange of a chunk runs BESIDE the transform of the next one only if both fit an SM together: the
+        // transforms leave a third of every SM free (2 of 3 CTAs; measured no slower), and their stream has the higher
+        // priority, so the short-lived exchange CTAs of the stream below never queue in front of them
+        if (p->chunks > 1 && !getenv("SSFFT_DIST_NO_SHARE")) {
+            ssfft_plan_limit_ctas(d.p1, 2);
+            ssfft_plan_limit_ctas(d.p2, 2);
+        }
+        int prio_least = 0, prio_greatest = 0;
+        cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest);
+        bool ok = cudaStreamCreateWithPriority(&d.s_fft, cudaStreamNonBlocking, prio_greatest) == cudaSuccess &&
+                  cudaStreamCreateWithPriority(&d.s_x, cudaStreamNonBlocking, prio_least) == cudaSuccess &&
                   cudaEventCreateWithFlags(&d.e_x1, cudaEventDisableTiming) == cudaSuccess &&
                   cudaEventCreateWithFlags(&d.e_x2, cudaEventDisableTiming) == cudaSuccess &&
                   cudaEventCreateWithFlags(&d.e_done, cudaEventDisableTiming) == cudaSuccess;

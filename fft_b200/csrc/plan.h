@@ -64,6 +64,7 @@ struct ssfft_plan {
     int flat_id_inv = -1;                  // real plans: entry of the inverse transform (same tiles, maybe another ring)
     int flat_ctas = 0;                     // co-resident CTAs of the persistent launch (real plans: forward)
     int flat_ctas_inv = 0;
+    int flat_ctas_max = 0, flat_ctas_inv_max = 0;  // what the device can hold (ssfft_plan_limit_ctas lowers flat_ctas below it)
     int flat_slots = 0;                    // scratch slots (transforms) allocated
     void *d_flat_ga[2] = {nullptr, nullptr}, *d_flat_gb[2] = {nullptr, nullptr}, *d_flat_s4 = nullptr, *d_flat_twb = nullptr;
     void *d_flat_scratch = nullptr, *d_flat_ctrl = nullptr;

@@ -368,6 +368,7 @@ int setup_flat(ssfft_plan *pl, bool *ok) {
     CU(cudaMalloc(&pl->d_flat_ctrl, (size_t)(32 + 2 * pl->flat_cap) * sizeof(unsigned)));
     pl->flat_id = id; pl->flat_ctas = ctas; pl->flat_slots = slots;
     pl->flat_id_inv = id_inv; pl->flat_ctas_inv = ctas_inv;
+    pl->flat_ctas_max = ctas; pl->flat_ctas_inv_max = ctas_inv;
     if (!pl->n1 && !real) { pl->n1 = n1; pl->n2 = n2; }
     *ok = true;
     return SSFFT_OK;
@@ -1099,6 +1100,17 @@ int ssfft_plan_destroy(ssfft_plan *pl) {
 size_t ssfft_plan_size(const ssfft_plan *pl) {
     if (!pl) return 0;
     return pl->kind == SSFFT_C2C ? pl->n : pl->n_real;
+}
+
+int ssfft_plan_limit_ctas(ssfft_plan *pl, int ctas_per_sm) {
+    if (!pl || ctas_per_sm < 0) return SSFFT_ERR_INVALID;
+    if (pl->flat_id < 0) return SSFFT_OK;
+    int sms = 0;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, pl->device) != cudaSuccess || sms < 1) { cudaGetLastError(); return SSFFT_ERR_CUDA; }
+    auto cap = [&](int most) { return ctas_per_sm == 0 || ctas_per_sm * sms > most ? most : ctas_per_sm * sms; };
+    pl->flat_ctas = cap(pl->flat_ctas_max);
+    pl->flat_ctas_inv = cap(pl->flat_ctas_inv_max);
+    return SSFFT_OK;
 }
 
 int ssfft_plan_describe(const ssfft_plan *pl, char *buf, size_t buflen) {

@@ -189,6 +189,12 @@ SSFFT_API int ssfft_dist_exec_c2c(ssfft_dist_plan *plan, void *const *d_in_shard
 SSFFT_API int ssfft_dist_synchronize(ssfft_dist_plan *plan);
 SSFFT_API int ssfft_dist_wait(ssfft_dist_plan *plan, int r, void *stream);
 
+/* ---- sharing the device with kernels of other streams ----
+ * The four-step kernels are persistent launches that fill every SM.  A caller that wants another kernel to run beside
+ * them (the distributed plan below overlaps its NVLink exchanges with its transforms this way) caps the launch at
+ * ctas_per_sm CTAs per SM; 0 restores the default.  Plans without a persistent kernel ignore the call. */
+SSFFT_API int ssfft_plan_limit_ctas(ssfft_plan *plan, int ctas_per_sm);
+
 /* ---- diagnostics ---- */
 SSFFT_API const char *ssfft_error_string(int status);
 SSFFT_API const char *ssfft_last_cuda_error(void);

@@ -37,6 +37,7 @@ inline double2 make_double2(double x, double y) { return double2{x, y}; }
 inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
 
 typedef struct simt_stream_st *cudaStream_t;
+typedef struct simt_event_st *cudaEvent_t;
 typedef int cudaError_t;
 enum { cudaSuccess = 0 };
 
