@@ -68,6 +68,12 @@ constexpr int kFlatHelpers = 64;  // two helper warps per CTA: the TMA producer 
 
 __host__ __device__ constexpr int flat_ilog2(int v) { return v <= 1 ? 0 : 1 + flat_ilog2(v / 2); }
 __host__ __device__ constexpr int flat_topbit(int v) { return 1 << flat_ilog2(v); }
+// rows per TMA box of a column tile: the largest divisor of the column length that a box can have (at most 256)
+__host__ __device__ constexpr int flat_box_rows(int n1) {
+    int r = n1 > 256 ? 256 : n1;
+    while (n1 % r) --r;
+    return r;
+}
 
 // shared-memory map of a CTA (bytes).  INPLACE: a ring slot is also the exchange buffer of the tile it holds (the TMA
 // copy lands dense at its start, the passes overwrite it with the padded image, the tile's slice of s4 sits behind it),
@@ -251,7 +257,10 @@ __device__ __forceinline__ void flat_stage_a(const FlatParams<T> &q, const cx<T>
         constexpr int ps = decltype(pc)::value;
         constexpr int R = Cfg::radix(ps), P = Cfg::prod(ps), NR = L / R, U = E / R, LOG = flat_ilog2(R);
         constexpr bool first = ps == 0, last = ps == NP - 1;
-        static_assert((1 << LOG) == R && (P & (P - 1)) == 0, "power-of-two radices");
+        // every pass but the last takes its twiddles as powers of one number (tables per bit of the digit): powers of
+        // two there; the last pass multiplies by a table row and may carry a factor 3 (column lengths 3 * 2^j)
+        static_assert(last || (1 << LOG) == R, "power-of-two radices before the last pass");
+        static_assert((P & (P - 1)) == 0, "the digits below the last one are powers of two");
         const int tt = last ? t2 : t, cc = last ? c2 : c;
         if constexpr (first && KIND == 2) {
             // ring slot: low columns [L][H], partner box [L][H + 2] (column N2 - n2 of low column n2 = H tile + i sits at
@@ -274,7 +283,7 @@ __device__ __forceinline__ void flat_stage_a(const FlatParams<T> &q, const cx<T>
 #pragma unroll
                 for (int j = 0; j < R; ++j) {
                     const int n1 = t + TX * u + NR * j;
-                    const int n1p = lane_self0 ? ((L - n1) & (L - 1)) : L - 1 - n1;
+                    const int n1p = lane_self0 ? (n1 ? L - n1 : 0) : L - 1 - n1;
                     const cx<T> xo = own[n1 * own_pitch], xp = par[n1p * par_pitch];
                     const cx<T> tc = cmul(ld_table(q.ra + n1), cb);  // conj(-i W_N^n)
                     const cx<T> sum = mk<T>(xo.x + xp.x, xo.y - xp.y), dif = mk<T>(xo.x - xp.x, xo.y + xp.y);  // X +- conj X'
@@ -470,7 +479,7 @@ __device__ __forceinline__ void flat_stage_b_r2c(const FlatParams<T> &q, const c
             // and no consumer touches it again before that copy has landed)
             if constexpr (INPLACE) release();
             else consumer_barrier(NC);
-            const int kph = (N1C - k1) & (N1C - 1);  // partner row (0 for row 0)
+            const int kph = k1 ? N1C - k1 : 0;  // partner row (0 for row 0)
 #pragma unroll
             for (int u = 0; u < U; ++u)
 #pragma unroll
@@ -684,7 +693,7 @@ fourstep_flat_kernel(FlatParams<typename CfgA::T> q, const __grid_constant__ CUt
                         desc[s] = cur;
                         hist[issued % NDONE] = cur;
                         cx<T> *slot = reinterpret_cast<cx<T> *>(ssfft_smem + Lay::oSlots + (size_t)s * Lay::kSlot);
-                        constexpr int kBoxRows = N1 > 256 ? 256 : N1;
+                        constexpr int kBoxRows = flat_box_rows(N1);
                         if (cur.kind == 0 && KIND == 2) {
                             // low columns [H t, H t + H); their partners [N2 - H t - H + 1, N2 - H t] inside the box of H + 2
                             // columns that starts at the even column N2 - H t - H (for t = 0 its last two columns are outside

@@ -43,7 +43,7 @@ int launch_flat(const void *params, int ctas, cudaStream_t s) {
     CUtensorMap tmap, tmap2;
     memset(&tmap, 0, sizeof(tmap));
     memset(&tmap2, 0, sizeof(tmap2));
-    constexpr int kBoxRows = CfgA::L > 256 ? 256 : CfgA::L;
+    constexpr int kBoxRows = flat_box_rows(CfgA::L);
     constexpr int kBoxCols = KIND == 2 ? CfgA::CT / 2 : CfgA::CT;
     if (!encode_tensor_map_3d(&tmap, q.in, q.batch, CfgA::L, CfgB::L, kBoxRows, kBoxCols)) return 3;
     if (KIND == 2 && !encode_tensor_map_3d(&tmap2, q.in, q.batch, CfgA::L, CfgB::L, kBoxRows, CfgA::CT / 2 + 2)) return 3;

@@ -87,6 +87,7 @@ void register_flat_f32_c(std::vector<FlatEntry> &);
 void register_flat_f32_d(std::vector<FlatEntry> &);
 void register_flat_f32_e(std::vector<FlatEntry> &);
 void register_flat_f32_h(std::vector<FlatEntry> &);
+void register_flat_f32_i(std::vector<FlatEntry> &);
 
 const std::vector<FlatEntry> &flat_registry() {
     static const std::vector<FlatEntry> reg = [] {
@@ -100,6 +101,7 @@ const std::vector<FlatEntry> &flat_registry() {
         register_flat_f32_d(v);
         register_flat_f32_e(v);
         register_flat_f32_h(v);
+        register_flat_f32_i(v);
         return v;
     }();
     return reg;

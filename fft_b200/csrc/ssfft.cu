@@ -496,7 +496,10 @@ int exec_clustered(ssfft_plan *pl, int kind, const void *in, void *out, long lon
 template <typename T>
 bool composite_inner_is_fast(size_t m) {
     if (find_fused<T>(m, 0) >= 0) return true;
-    return m >= ((size_t)1 << 14) && m <= ((size_t)1 << 20) && (m & (m - 1)) == 0;
+    if (m >= ((size_t)1 << 14) && m <= ((size_t)1 << 20) && (m & (m - 1)) == 0) return true;
+    for (const FlatEntry &e : flat_registry())  // 3 * 2^k, 9 * 2^k on the ticket-queue kernels
+        if (e.prec == (sizeof(T) == 4 ? 0 : 1) && (size_t)e.n1 * (size_t)e.n2 == m) return true;
+    return false;
 }
 template <typename T>
 int choose_composite_radix(size_t n) {

@@ -155,9 +155,10 @@ def test_flat_real_large_batch_round_trip(oracle, cuda_device):
     assert oracle.rel_l2(spec[idx].cpu().numpy(), oracle.rfft(xd[idx].cpu().numpy())) <= tol(n)
 
 
-@pytest.mark.parametrize("n", [12288, 24576, 49152, 98304, 196608, 393216, 786432])
+@pytest.mark.parametrize("n", [12288, 24576, 49152, 98304, 196608, 393216, 786432, 18432, 36864, 73728, 147456, 294912, 589824])
 def test_flat_three_times_power_of_two(oracle, cuda_device, n):
-    """Row stages of length 3 * 2^j (flat_f32_h.cu): the 2^k * 3 half of the reference's benchmark sizes
+    """Row stages of length 3 * 2^j (flat_f32_h.cu) and, for 9 * 2^k, column stages with a factor 3 in their last pass
+    (flat_f32_i.cu): the 2^k * {3, 9} part of the reference's benchmark sizes
     (benchmark/benchmark.h:27-52) above the single-pass kernels, forward and inverse, several batch shapes, in place, and
     the real transform of twice the length (complex core on these kernels)."""
     f = fft_b200.FFT(n)
