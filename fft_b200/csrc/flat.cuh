@@ -162,14 +162,15 @@ __device__ __forceinline__ void consumer_barrier(int n) { asm volatile("bar.sync
 __device__ __forceinline__ void producer_idle() { __nanosleep(64); }
 __device__ __forceinline__ void producer_moved() {}
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
-// box [box_rows][ct] at (col0, row0) of transform b of the (batch, N1, N2) input (tensor map built by the launcher)
+// box [box_rows][ct] at (col0, row0) of transform b of the (batch, N1, N2) input (tensor map built by the launcher; its
+// elements are 8-byte words: a double-precision complex value is two of them)
 template <typename T>
 __device__ __forceinline__ void tma_tile_3d(cx<T> *dst, const void *tmap, const cx<T> *, int, int, int, int, int col0, int row0,
                                             long long b, unsigned long long *bar) {
     asm volatile(
         "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
             smem_u32(dst)),
-        "l"(reinterpret_cast<unsigned long long>(tmap)), "r"(col0), "r"(row0), "r"((int)b), "r"(smem_u32(bar))
+        "l"(reinterpret_cast<unsigned long long>(tmap)), "r"(col0 * (int)(sizeof(cx<T>) / 8)), "r"(row0), "r"((int)b), "r"(smem_u32(bar))
         : "memory");
 }
 #endif

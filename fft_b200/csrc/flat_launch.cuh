@@ -45,8 +45,8 @@ int launch_flat(const void *params, int ctas, cudaStream_t s) {
     memset(&tmap2, 0, sizeof(tmap2));
     constexpr int kBoxRows = flat_box_rows(CfgA::L);
     constexpr int kBoxCols = KIND == 2 ? CfgA::CT / 2 : CfgA::CT;
-    if (!encode_tensor_map_3d(&tmap, q.in, q.batch, CfgA::L, CfgB::L, kBoxRows, kBoxCols)) return 3;
-    if (KIND == 2 && !encode_tensor_map_3d(&tmap2, q.in, q.batch, CfgA::L, CfgB::L, kBoxRows, CfgA::CT / 2 + 2)) return 3;
+    if (!encode_tensor_map_3d(&tmap, q.in, q.batch, CfgA::L, CfgB::L, kBoxRows, kBoxCols, (int)sizeof(cx<T>))) return 3;
+    if (KIND == 2 && !encode_tensor_map_3d(&tmap2, q.in, q.batch, CfgA::L, CfgB::L, kBoxRows, CfgA::CT / 2 + 2, (int)sizeof(cx<T>))) return 3;
     fourstep_flat_kernel<CfgA, CfgB, INV, NSTAGE, MINB, INPLACE, KIND><<<(unsigned)ctas, CfgA::THREADS + kFlatHelpers, Lay::smem_bytes, s>>>(q, tmap, tmap2);
     return cudaGetLastError() == cudaSuccess ? 0 : 2;
 }

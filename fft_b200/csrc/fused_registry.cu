@@ -88,6 +88,7 @@ void register_flat_f32_d(std::vector<FlatEntry> &);
 void register_flat_f32_e(std::vector<FlatEntry> &);
 void register_flat_f32_h(std::vector<FlatEntry> &);
 void register_flat_f32_i(std::vector<FlatEntry> &);
+void register_flat_f64_a(std::vector<FlatEntry> &);
 
 const std::vector<FlatEntry> &flat_registry() {
     static const std::vector<FlatEntry> reg = [] {
@@ -102,6 +103,7 @@ const std::vector<FlatEntry> &flat_registry() {
         register_flat_f32_e(v);
         register_flat_f32_h(v);
         register_flat_f32_i(v);
+        register_flat_f64_a(v);
         return v;
     }();
     return reg;

@@ -25,15 +25,18 @@ inline ssfft_encode_tiled_fn tensor_map_encoder() {
     return fn;
 }
 
-// `base` viewed as [batch][rows][cols] elements of 8 bytes (one fp32 complex), copied in boxes of [1][box_rows][box_cols]
+// `base` viewed as [batch][rows][cols] complex elements of elem_bytes (8: fp32, 16: fp64), copied in boxes of
+// [1][box_rows][box_cols].  The map itself counts 8-byte words (a fp64 element is two): the kernel scales its column
+// coordinate the same way.
 inline bool encode_tensor_map_3d(CUtensorMap *tm, const void *base, long long batch, int rows, int cols, int box_rows,
-                                 int box_cols) {
+                                 int box_cols, int elem_bytes = 8) {
     ssfft_encode_tiled_fn enc = tensor_map_encoder();
-    if (!enc || (reinterpret_cast<uintptr_t>(base) & 15u) || batch <= 0 || batch > 0x7fffffffLL) return false;
-    if (box_rows > 256 || box_cols > 256 || (box_cols * 8) % 16) return false;
-    const cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)batch};
-    const cuuint64_t strides[2] = {(cuuint64_t)cols * 8, (cuuint64_t)cols * rows * 8};
-    const cuuint32_t box[3] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows, 1u};
+    const int w = elem_bytes / 8;  // words per element
+    if (!enc || (reinterpret_cast<uintptr_t>(base) & 15u) || batch <= 0 || batch > 0x7fffffffLL || (w != 1 && w != 2)) return false;
+    if (box_rows > 256 || box_cols * w > 256 || (box_cols * elem_bytes) % 16) return false;
+    const cuuint64_t dims[3] = {(cuuint64_t)cols * w, (cuuint64_t)rows, (cuuint64_t)batch};
+    const cuuint64_t strides[2] = {(cuuint64_t)cols * elem_bytes, (cuuint64_t)cols * rows * elem_bytes};
+    const cuuint32_t box[3] = {(cuuint32_t)(box_cols * w), (cuuint32_t)box_rows, 1u};
     const cuuint32_t estr[3] = {1u, 1u, 1u};
     return enc(tm, CU_TENSOR_MAP_DATA_TYPE_UINT64, 3, const_cast<void *>(base), dims, strides, box, estr,
                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,

@@ -192,3 +192,43 @@ def test_flat_three_times_power_of_two(oracle, cuda_device, n):
     torch.cuda.synchronize()
     assert oracle.rel_l2(spec.cpu().numpy(), oracle.run(oracle.KIND_R2C, xr, 2 * n, threads=8)[0]) <= tol(2 * n), r.describe()
     assert oracle.rel_l2(back.cpu().numpy() / (2 * n), xr) <= 2 * tol(2 * n)
+
+
+@pytest.mark.parametrize("n", [2 ** 14, 2 ** 15, 2 ** 16, 2 ** 17, 2 ** 18, 12288, 24576, 49152, 18432, 36864])
+def test_flat_double_precision(oracle, cuda_device, n):
+    """fp64 on the ticket-queue kernels (flat_f64_a.cu: TMA boxes of two 8-byte words per element): complex forward /
+    inverse / in place and the real transform of twice the length, against the oracle at 1e-14 * log2 N."""
+    lim = 1e-14 * math.log2(n)
+    f = fft_b200.FFT(n, dtype="float64")
+    assert "ticket-queue" in f.describe(), f.describe()
+    for batch in (1, 3, max(2, 2 ** 22 // n)):
+        x = oracle.uniform_complex((batch, n), 51 + batch, np.complex128)
+        xd = torch.from_numpy(x).cuda()
+        out = torch.empty_like(xd)
+        for inverse in (False, True):
+            out.zero_()
+            launches = fft_b200.launch_count()
+            (f.ifft if inverse else f.fft)(xd, out)
+            torch.cuda.synchronize()
+            assert fft_b200.launch_count() - launches == 1
+            assert torch.equal(xd.cpu(), torch.from_numpy(x)), "input was changed"
+            ref = oracle.run(oracle.KIND_C2C_INV if inverse else oracle.KIND_C2C_FWD, x, n, threads=8)[0]
+            err = oracle.rel_l2(out.cpu().numpy(), ref)
+            assert err <= lim, (n, batch, inverse, err, f.describe())
+    x = oracle.uniform_complex((5, n), 7, np.complex128)
+    xd = torch.from_numpy(x).cuda()
+    f.fft(xd, xd)
+    torch.cuda.synchronize()
+    assert oracle.rel_l2(xd.cpu().numpy(), oracle.run(oracle.KIND_C2C_FWD, x, n, threads=8)[0]) <= lim
+    r = fft_b200.RealFFT(2 * n, dtype="float64")
+    if n & (n - 1) == 0:  # the fp64 entries of 3 * 2^k / 9 * 2^k carry no real kernels: their real transforms wrap the complex one
+        assert "ticket-queue" in r.describe(), r.describe()
+    xr = oracle.uniform(3 * 2 * n, 9, np.float64).reshape(3, 2 * n)
+    xrd = torch.from_numpy(xr).cuda()
+    spec = torch.empty((3, n), dtype=torch.complex128, device="cuda")
+    back = torch.empty_like(xrd)
+    r.fft(xrd, spec)
+    r.ifft(spec, back)
+    torch.cuda.synchronize()
+    assert oracle.rel_l2(spec.cpu().numpy(), oracle.run(oracle.KIND_R2C, xr, 2 * n, threads=8)[0]) <= 1e-14 * math.log2(2 * n), r.describe()
+    assert oracle.rel_l2(back.cpu().numpy() / (2 * n), xr) <= 2e-14 * math.log2(2 * n)
