@@ -77,4 +77,4 @@ def test_every_flat_kernel_runs_on_cpu(tmp_path, oracle):
         runs += int(res.stdout.split(" runs,")[0].split()[-1])
     # (ring 1, 2 separate exchange buffer + ring 1, 2, 3 in place) x 4 shapes x forward / inverse, + RealFFT forward / inverse
     # x 3 shapes x ring 1, 2 for the pairs that carry the real kernels
-    assert runs >= 30 * len(pairs)  # wide tiles: the deeper rings do not fit one CTA and are skipped
+    assert runs >= 16 * len(pairs)  # lengths from 2^18 on run two ring variants (+ one real), wide tiles skip rings that do not fit
