@@ -220,7 +220,11 @@ def run_reference(args):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32" if dtype == "float32" else "f64",
         "data": "synthetic uniform[-0.5,0.5), counter-based generator, seed %d" % SEED,
-        "config": {"workload": f"{args.workload}: {kind} {dtype} N={n} x {batch} (CPU sample {sample} per step)"},
+        # the same workload string as the GPU arm prints (the driver compares them); what a step really covers is a
+        # bounded sample of that workload, stated next to it and in cpu_baseline.sample
+        "config": {"workload": f"{args.workload}: {kind} {dtype} N={n} x {batch} transforms per GPU"
+                               + (" (forward + inverse per step)" if kind != "c2c" else " (forward)"),
+                   "sample_per_step": sample},
         "cpu_baseline": {"value": value, "unit": "GFLOP/s", "cores": cores, "kind": impl,
                          "sample": f"{sample} transforms of N={n} per step, batch split over {cores} host threads, "
                                    "one FFT object per thread, plan build excluded"},
