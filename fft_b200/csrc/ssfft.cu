@@ -306,7 +306,7 @@ template <typename T>
 int setup_flat(ssfft_plan *pl, bool *ok) {
     *ok = false;
     const size_t n = pl->n;  // complex length (real plans: N / 2)
-    const bool real = pl->kind == SSFFT_REAL;
+    bool real = pl->kind == SSFFT_REAL;
     if ((pl->kind != SSFFT_C2C && !real) || n == 0 || env_int("SSFFT_DISABLE_FLAT", 0)) return SSFFT_OK;
     if (real && env_int("SSFFT_DISABLE_FLAT_REAL", 0)) return SSFFT_OK;
     size_t n1 = 0, n2 = 0;
@@ -323,6 +323,9 @@ int setup_flat(ssfft_plan *pl, bool *ok) {
             if (e.prec == (sizeof(T) == 4 ? 0 : 1) && (size_t)e.n1 * (size_t)e.n2 == n) { n1 = (size_t)e.n1; n2 = (size_t)e.n2; break; }
         if (!n1) return SSFFT_OK;
     }
+    // a real plan whose length has no RealFFT kernels registered (fp64 3 * 2^k, 9 * 2^k) still runs its complex core
+    // on these kernels, between the stand-alone twiddle passes
+    if (real && (find_flat<T>(n1, n2, 0) < 0 || find_flat<T>(n1, n2, 1) < 0)) real = false;
     const int id = find_flat<T>(n1, n2, real ? 0 : -1);
     if (id < 0) return SSFFT_OK;
     const FlatEntry &e = flat_registry()[id];
@@ -643,7 +646,7 @@ template <typename T>
 int exec_complex(ssfft_plan *pl, const void *in, void *out, long long batch, int inverse, cudaStream_t s) {
     const long long n = (long long)pl->n;
     if (batch <= 0 || n == 0) return SSFFT_OK;
-    if (pl->flat_id >= 0 && pl->kind == SSFFT_C2C) {  // first: the other paths of such a plan are its fallback
+    if (pl->flat_id >= 0 && !pl->flat_real) {  // first: the other paths of such a plan are its fallback
         const int rc = exec_flat<T>(pl, in, out, batch, inverse, s);
         if (rc >= 0) return rc;
     }
