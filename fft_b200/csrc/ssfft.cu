@@ -17,6 +17,7 @@
 
 #include "bluestein.cuh"
 #include "composite.cuh"
+#include "exchange_tma.cuh"
 #include "cluster.cuh"
 #include "ex_request.h"
 #include "flat.cuh"
@@ -1433,6 +1434,20 @@ int ssfft_exchange_transpose(const void *d_src, void *const *d_dst_ptrs, int wor
                              void *stream) {
     if (!rows || !cols) return SSFFT_OK;
     if (!d_src || !d_dst_ptrs || world < 1 || world > kMaxPeers || cols % (size_t)world) return SSFFT_ERR_INVALID;
+    // experiment, off by default: the TMA-driven kernel (exchange_tma.cuh), a few CTAs per SM instead of 64 warps per SM.
+    // MEASURED SLOWER (profiles/bench_dist_tma_r02y.txt, 2^30 over 2 GPUs): 14.9 / 16.2 / 14.8 ms with 2 / 1 / 4 CTAs per SM
+    // against 13.9 ms, and chunked phases still gain nothing beside it (14.5 ms at best)
+    if (env_int("SSFFT_EXCHANGE_TMA", 0) && (precision == SSFFT_F32 || precision == SSFFT_F64)) {
+        int dev = 0, sms = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        const int max_ctas = sms * env_int("SSFFT_EXCHANGE_CTAS_PER_SM", 2);
+        const int rc = precision == SSFFT_F32
+                           ? launch_exchange_tma<float>(d_src, d_dst_ptrs, world, rows, cols, dst_pitch, dst_col0, row0, n_total, inverse, max_ctas, (cudaStream_t)stream)
+                           : launch_exchange_tma<double>(d_src, d_dst_ptrs, world, rows, cols, dst_pitch, dst_col0, row0, n_total, inverse, max_ctas, (cudaStream_t)stream);
+        if (rc == 0) { ++g_launches; return SSFFT_OK; }
+        if (rc == 2) return cuda_fail(cudaGetLastError(), "exchange_tma_kernel launch");
+    }
     const size_t row_blocks = (rows + 32 * kRowTiles - 1) / (32 * kRowTiles);
     if (row_blocks > 65535) return SSFFT_ERR_INVALID;
     dim3 grid((unsigned)((cols + 31) / 32), (unsigned)row_blocks), block(32, 8);
