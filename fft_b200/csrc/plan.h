@@ -73,6 +73,7 @@ struct ssfft_plan {
     void *d_flat_ra[2] = {nullptr, nullptr}, *d_flat_rb[2] = {nullptr, nullptr};  // post- / pre-twiddle factors [fwd, inv]
 
     // Bluestein (bluestein.cuh): lengths whose largest prime factor fits no on-chip path run as a convolution through
+    bool tiny = false;                      // N <= 24 complex: one thread per transform (tiny.cuh)
     // composite plan (composite.cuh): N = comp_r * M, one radix pass + the plan of length M + an interleave pass
     ssfft_plan *comp_inner = nullptr;
     int comp_r = 0;

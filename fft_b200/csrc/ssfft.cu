@@ -18,6 +18,7 @@
 #include "bluestein.cuh"
 #include "composite.cuh"
 #include "exchange_tma.cuh"
+#include "tiny.cuh"
 #include "cluster.cuh"
 #include "ex_request.h"
 #include "flat.cuh"
@@ -647,6 +648,11 @@ template <typename T>
 int exec_complex(ssfft_plan *pl, const void *in, void *out, long long batch, int inverse, cudaStream_t s) {
     const long long n = (long long)pl->n;
     if (batch <= 0 || n == 0) return SSFFT_OK;
+    if (pl->tiny) {
+        const int rc = launch_tiny<T>((size_t)n, in, out, batch, inverse, s);
+        if (rc == 0) { ++g_launches; return SSFFT_OK; }
+        if (rc == 2) return cuda_fail(cudaGetLastError(), "tiny_fft_kernel launch");
+    }
     if (pl->flat_id >= 0 && !pl->flat_real) {  // first: the other paths of such a plan are its fallback
         const int rc = exec_flat<T>(pl, in, out, batch, inverse, s);
         if (rc >= 0) return rc;
@@ -765,7 +771,11 @@ int build_plan_typed(ssfft_plan *pl) {
         }
         std::string rs;
         for (int r : pl->direct.radix) { rs += (rs.empty() ? "" : "x"); rs += std::to_string(r); }
-        if (pl->fused.id >= 0)
+        // a handful of points: one thread per transform (the interpreter stays built as the path of the real wrappers)
+        pl->tiny = pl->kind == SSFFT_C2C && pl->fused.id < 0 && tiny_supported(n) && !env_int("SSFFT_DISABLE_TINY", 0);
+        if (pl->tiny)
+            snprintf(buf, sizeof(buf), "n=%zu one thread per transform (register codelet, 256 transforms per CTA through shared memory)", n);
+        else if (pl->fused.id >= 0)
             snprintf(buf, sizeof(buf), "n=%zu single-pass fused kernel %s", n, fused_name(pl->fused.id));
         else
             snprintf(buf, sizeof(buf), "n=%zu single-pass generic radices=%s tx=%d fpb=%d smem=%zu", n, rs.c_str(),
@@ -1132,6 +1142,8 @@ int ssfft_exec_c2c(ssfft_plan *pl, const void *d_in, void *d_out, size_t batch, 
     if (direction != SSFFT_FORWARD && direction != SSFFT_INVERSE) return SSFFT_ERR_INVALID;
     if (batch == 0 || pl->n == 0) return SSFFT_OK;
     if (!d_in || !d_out) return SSFFT_ERR_INVALID;
+    // the kernels move whole complex values (real data as pairs): a pointer that is not aligned to one would fault
+    if ((reinterpret_cast<uintptr_t>(d_in) | reinterpret_cast<uintptr_t>(d_out)) % pl->elem) return SSFFT_ERR_INVALID;
     DeviceGuard guard(pl->device);
     const int inv = direction == SSFFT_INVERSE;
     if (plan_is_stateful(pl)) {
@@ -1147,6 +1159,8 @@ int ssfft_exec_r2c(ssfft_plan *pl, const void *d_in, void *d_out, size_t batch, 
     if (!pl || pl->kind == SSFFT_C2C) return SSFFT_ERR_INVALID;
     if (batch == 0 || pl->n == 0) return SSFFT_OK;
     if (!d_in || !d_out) return SSFFT_ERR_INVALID;
+    // the kernels move whole complex values (real data as pairs): a pointer that is not aligned to one would fault
+    if ((reinterpret_cast<uintptr_t>(d_in) | reinterpret_cast<uintptr_t>(d_out)) % pl->elem) return SSFFT_ERR_INVALID;
     DeviceGuard guard(pl->device);
     PlanExec order(pl, (cudaStream_t)stream);
     return pl->prec == SSFFT_F32 ? exec_r2c_typed<float>(pl, d_in, d_out, (long long)batch, (cudaStream_t)stream)
@@ -1157,6 +1171,8 @@ int ssfft_exec_c2r(ssfft_plan *pl, const void *d_in, void *d_out, size_t batch, 
     if (!pl || pl->kind == SSFFT_C2C) return SSFFT_ERR_INVALID;
     if (batch == 0 || pl->n == 0) return SSFFT_OK;
     if (!d_in || !d_out) return SSFFT_ERR_INVALID;
+    // the kernels move whole complex values (real data as pairs): a pointer that is not aligned to one would fault
+    if ((reinterpret_cast<uintptr_t>(d_in) | reinterpret_cast<uintptr_t>(d_out)) % pl->elem) return SSFFT_ERR_INVALID;
     DeviceGuard guard(pl->device);
     PlanExec order(pl, (cudaStream_t)stream);
     return pl->prec == SSFFT_F32 ? exec_c2r_typed<float>(pl, d_in, d_out, (long long)batch, (cudaStream_t)stream)

@@ -74,7 +74,10 @@ SSFFT_API size_t ssfft_plan_size(const ssfft_plan *plan);
 /* human-readable plan: factors, passes, kernel choice (tests pin the plan builder with this) */
 SSFFT_API int ssfft_plan_describe(const ssfft_plan *plan, char *buf, size_t buflen);
 
-/* ---- execution on DEVICE pointers, asynchronous on `stream` (a cudaStream_t, may be NULL) ---- */
+/* ---- execution on DEVICE pointers, asynchronous on `stream` (a cudaStream_t, may be NULL) ----
+ * Both buffers of a call must be aligned to a whole complex<V> (8 bytes in float, 16 in double) -- the real side too,
+ * whose samples move as pairs; other pointers return SSFFT_ERR_INVALID.  Buffers aligned to 16 bytes take the fastest
+ * path for the four-step lengths (their tiles are fetched by tensor copies); others run the plan's other path. */
 /* FFT<V>::fft (:374-379) when direction == SSFFT_FORWARD, FFT<V>::ifft (:381-386) when SSFFT_INVERSE */
 SSFFT_API int ssfft_exec_c2c(ssfft_plan *plan, const void *d_in, void *d_out, size_t batch, int direction,
                              void *stream);

@@ -78,8 +78,11 @@ def test_flat_scheduling_extremes(oracle, cuda_device, flat_env, n):
         assert err <= tol(n), (n, delay, slots, err)
 
 
-def test_flat_falls_back_for_unaligned_input(oracle, cuda_device):
-    n, batch = 65536, 5
+@pytest.mark.parametrize("n", [65536, 12288, 24576, 18432])
+def test_flat_falls_back_for_unaligned_input(oracle, cuda_device, n):
+    """A tensor map needs a 16-byte aligned input: other inputs run the plan's other path (round-1 kernels for powers of
+    two, the single-pass interpreter or the composite plan for 3 * 2^k / 9 * 2^k) -- complex and real."""
+    batch = 5
     x = oracle.uniform_complex((batch, n), 9, np.complex64)
     buf = torch.zeros(batch * n + 1, dtype=torch.complex64, device="cuda")
     xin = buf[1:].view(batch, n)
@@ -87,9 +90,30 @@ def test_flat_falls_back_for_unaligned_input(oracle, cuda_device):
     assert xin.data_ptr() % 16 == 8
     out = torch.empty((batch, n), dtype=torch.complex64, device="cuda")
     f = fft_b200.FFT(n)
+    assert "ticket-queue" in f.describe()
     f.fft(xin, out)
     torch.cuda.synchronize()
     assert oracle.rel_l2(out.cpu().numpy(), oracle.run(oracle.KIND_C2C_FWD, x, n, threads=4)[0]) <= tol(n)
+    nr = 2 * n
+    xr = oracle.uniform(batch * nr, 10, np.float32).reshape(batch, nr)
+    rbuf = torch.zeros(batch * nr + 2, dtype=torch.float32, device="cuda")
+    rin = rbuf[2:].view(batch, nr)
+    rin.copy_(torch.from_numpy(xr))
+    assert rin.data_ptr() % 16 == 8
+    spec = torch.empty((batch, n), dtype=torch.complex64, device="cuda")
+    r = fft_b200.RealFFT(nr)
+    with pytest.raises(fft_b200.SsfftError):  # samples move as pairs: a real buffer must be aligned to one complex value
+        r.fft(rbuf[1:batch * nr + 1].view(batch, nr), spec)
+    r.fft(rin, spec)
+    torch.cuda.synchronize()
+    assert oracle.rel_l2(spec.cpu().numpy(), oracle.run(oracle.KIND_R2C, xr, nr, threads=4)[0]) <= tol(nr), r.describe()
+    sbuf = torch.zeros(batch * n + 1, dtype=torch.complex64, device="cuda")
+    sin = sbuf[1:].view(batch, n)
+    sin.copy_(spec)
+    back = torch.empty((batch, nr), dtype=torch.float32, device="cuda")
+    r.ifft(sin, back)
+    torch.cuda.synchronize()
+    assert oracle.rel_l2(back.cpu().numpy() / nr, xr) <= 2 * tol(nr), r.describe()
 
 
 @pytest.mark.parametrize("n", SIZES)

@@ -223,3 +223,33 @@ def test_composite_lengths_vs_oracle(oracle, cuda_device, prec, n):
         want_r = oracle.run(oracle.KIND_R2C, xr, 2 * n, threads=8)[0]
         assert oracle.rel_l2(spec.cpu().numpy(), want_r) <= tol(2 * n, npdt), (2 * n, prec, r.describe())
         assert oracle.rel_l2(back.cpu().numpy() / (2 * n), xr) <= 2 * tol(2 * n, npdt)
+
+
+@pytest.mark.parametrize("prec", ["float32", "float64"])
+def test_tiny_lengths_one_thread_per_transform(oracle, cuda_device, prec):
+    """N <= 24 (tiny.cuh): every supported length, forward / inverse / in place, batches that are not multiples of a CTA's
+    256 transforms, against the oracle; the first sizes of the reference's benchmark (benchmark/benchmark.h:27-52)."""
+    npdt = np.complex64 if prec == "float32" else np.complex128
+    eps = 1e-6 if prec == "float32" else 1e-14
+    for n in list(range(1, 17)) + [18, 20, 24]:
+        f = fft_b200.FFT(n, dtype=prec)
+        assert "one thread per transform" in f.describe(), f.describe()
+        for batch in (1, 255, 257, 5000):
+            x = oracle.uniform_complex((batch, n), 60 + n, npdt)
+            xd = torch.from_numpy(x).cuda()
+            y = torch.empty_like(xd)
+            z = torch.empty_like(xd)
+            launches = fft_b200.launch_count()
+            f.fft(xd, y)
+            assert fft_b200.launch_count() - launches == 1
+            f.ifft(y, z)
+            torch.cuda.synchronize()
+            lim = eps * max(1.0, math.log2(n))
+            want = oracle.run(oracle.KIND_C2C_FWD, x, n, threads=2)[0]
+            assert oracle.rel_l2(y.cpu().numpy(), want) <= lim, (n, batch, prec)
+            assert oracle.rel_l2(z.cpu().numpy(), oracle.run(oracle.KIND_C2C_INV, want, n, threads=2)[0]) <= 2 * lim, (n, batch, prec)
+            assert torch.equal(xd.cpu(), torch.from_numpy(x))
+        xi = torch.from_numpy(x).cuda()
+        f.fft(xi, xi)
+        torch.cuda.synchronize()
+        assert oracle.rel_l2(xi.cpu().numpy(), want) <= lim, (n, "in place")
