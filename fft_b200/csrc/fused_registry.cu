@@ -13,6 +13,7 @@ void register_fused_f64_a(std::vector<FusedEntry> &);
 void register_fused_f64_b(std::vector<FusedEntry> &);
 void register_fused_f32_d(std::vector<FusedEntry> &);
 void register_fused_f64_c(std::vector<FusedEntry> &);
+void register_fused_f32_e(std::vector<FusedEntry> &);
 
 const std::vector<FusedEntry> &fused_registry() {
     static const std::vector<FusedEntry> reg = [] {
@@ -28,6 +29,7 @@ const std::vector<FusedEntry> &fused_registry() {
         register_fused_f64_b(v);
         register_fused_f32_d(v);
         register_fused_f64_c(v);
+        register_fused_f32_e(v);
         return v;
     }();
     return reg;
