@@ -111,7 +111,7 @@ def measured_peak():
 def profiled_traffic(workload):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed
     `ncu --set full` summary of the same command (profiles/*_traffic.json, made by tools/summarize_ncu.py)."""
-    files = {"c2": "c2_fused4096_tma_r01_traffic.json"}
+    files = {"c2": "c2_fused4096_tma_r02_traffic.json"}
     name = files.get(workload)
     if not name:
         return None, None
