@@ -551,14 +551,18 @@ int launch_composite_passes(bool pre, const cx<T> *in, cx<T> *out, const cx<T> *
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     if (pre) {
-        long long blocks = (m * nb + 255) / 256;
+        const long long per_thread = sizeof(T) == 4 ? 2 : 1;  // columns per thread (16-byte accesses)
+        const bool vec = m % per_thread == 0 && ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(tw)) & 15u) == 0;
+        long long blocks = ((vec ? m / per_thread : m) * nb + 255) / 256;
         if (blocks > (long long)sms * 16) blocks = (long long)sms * 16;
-        radix_pass_kernel<T, R><<<(unsigned)blocks, 256, 0, s>>>(in, out, tw, m, nb, inverse);
+        if (vec) radix_pass_kernel<T, R><<<(unsigned)blocks, 256, 0, s>>>(in, out, tw, m, nb, inverse);
+        else radix_pass_scalar_kernel<T, R><<<(unsigned)blocks, 256, 0, s>>>(in, out, tw, m, nb, inverse);
     } else {
-        constexpr int K2T = sizeof(T) == 8 ? 128 : 256;
-        long long blocks = ((m + K2T - 1) / K2T) * nb;
-        if (blocks > (long long)sms * 8) blocks = (long long)sms * 8;
-        interleave_kernel<T, R><<<(unsigned)blocks, 256, 0, s>>>(in, out, m, nb, inverse);
+        constexpr int kW = sizeof(T) == 8 ? 16 : 32;  // k2 per warp tile
+        long long blocks = (((m + kW - 1) / kW) * nb + 7) / 8;
+        if (blocks > (long long)sms * 6) blocks = (long long)sms * 6;
+        const int vec_ok = (reinterpret_cast<uintptr_t>(out) & 15u) == 0 && (m * R) % 2 == 0;
+        interleave_kernel<T, R><<<(unsigned)blocks, 256, 0, s>>>(in, out, m, nb, inverse, vec_ok);
     }
     ++g_launches;
     CU(cudaGetLastError());
