@@ -12,6 +12,10 @@ void register_flat_f64_a(std::vector<FlatEntry> &v) {
     v.push_back(make_flat_entry<D256, D256, 2, 2, true, 3>("double_flat_256x256_r2c2i"));  // 2^16
     v.push_back(make_flat_entry<D256, D512, 2, 2, true, 3>("double_flat_256x512_r2c2i"));  // 2^17
     v.push_back(make_flat_entry<D512, D512, 2, 2, true, 3>("double_flat_512x512_r2c2i"));  // 2^18
+    // 2^19, 2^20: the 1024-point leg holds 16 points per thread (64 registers of data): ring of one in-place slot
+    using D1024 = TileCfg<double, 1024, 4, 16, 16, 64, 4, 2>;
+    v.push_back(make_flat_entry<D512, D1024, 1, 2, true, 3>("double_flat_512x1024_r1c2i"));    // 2^19
+    v.push_back(make_flat_entry<D1024, D1024, 1, 2, true, 3>("double_flat_1024x1024_r1c2i"));  // 2^20
     // 3 * 2^k and 9 * 2^k as far as 12 points per thread reach (the 384- and 768-point legs would need 24)
     using D96 = TileCfg<double, 96, 4, 4, 6, 8, 32, 2>;
     using D192 = TileCfg<double, 192, 4, 4, 12, 16, 16, 2>;
