@@ -24,5 +24,7 @@ void register_flat_f64_a(std::vector<FlatEntry> &v) {
     v.push_back(make_flat_entry<D256, D192, 2, 2, true, 0>("double_flat_256x192_r2c2i"));  // 49152
     v.push_back(make_flat_entry<D96, D192, 2, 2, true, 0>("double_flat_96x192_r2c2i"));    // 18432
     v.push_back(make_flat_entry<D192, D192, 2, 2, true, 0>("double_flat_192x192_r2c2i"));  // 36864
+    v.push_back(make_flat_entry<D512, D192, 2, 2, true, 0>("double_flat_512x192_r2c2i"));  // 98304
+    v.push_back(make_flat_entry<D1024, D192, 1, 2, true, 0>("double_flat_1024x192_r1c2i"));  // 196608
 }
 }  // namespace ssfft

@@ -218,7 +218,7 @@ def test_flat_three_times_power_of_two(oracle, cuda_device, n):
     assert oracle.rel_l2(back.cpu().numpy() / (2 * n), xr) <= 2 * tol(2 * n)
 
 
-@pytest.mark.parametrize("n", [2 ** 14, 2 ** 15, 2 ** 16, 2 ** 17, 2 ** 18, 2 ** 19, 2 ** 20, 12288, 24576, 49152, 18432, 36864])
+@pytest.mark.parametrize("n", [2 ** 14, 2 ** 15, 2 ** 16, 2 ** 17, 2 ** 18, 2 ** 19, 2 ** 20, 12288, 24576, 49152, 18432, 36864, 98304, 196608])
 def test_flat_double_precision(oracle, cuda_device, n):
     """fp64 on the ticket-queue kernels (flat_f64_a.cu: TMA boxes of two 8-byte words per element): complex forward /
     inverse / in place and the real transform of twice the length, against the oracle at 1e-14 * log2 N."""
