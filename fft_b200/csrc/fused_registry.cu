@@ -90,6 +90,7 @@ void register_flat_f32_d(std::vector<FlatEntry> &);
 void register_flat_f32_e(std::vector<FlatEntry> &);
 void register_flat_f32_h(std::vector<FlatEntry> &);
 void register_flat_f32_i(std::vector<FlatEntry> &);
+void register_flat_f32_j(std::vector<FlatEntry> &);
 void register_flat_f64_a(std::vector<FlatEntry> &);
 
 const std::vector<FlatEntry> &flat_registry() {
@@ -105,6 +106,7 @@ const std::vector<FlatEntry> &flat_registry() {
         register_flat_f32_e(v);
         register_flat_f32_h(v);
         register_flat_f32_i(v);
+        register_flat_f32_j(v);
         register_flat_f64_a(v);
         return v;
     }();

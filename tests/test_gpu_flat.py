@@ -18,6 +18,7 @@ pytestmark = pytest.mark.gpu
 import fft_b200  # noqa: E402
 
 SIZES = [32768, 65536, 2 ** 17, 2 ** 18, 2 ** 19, 2 ** 20]
+LONG_SIZES = [2 ** 21, 2 ** 22, 3 * 2 ** 19]  # 2048-point leg (flat_f32_j.cu)
 VARIANTS = ["1,3,0", "2,3,1"]  # ring, CTAs per SM, in-place exchange
 
 
@@ -256,3 +257,25 @@ def test_flat_double_precision(oracle, cuda_device, n):
     torch.cuda.synchronize()
     assert oracle.rel_l2(spec.cpu().numpy(), oracle.run(oracle.KIND_R2C, xr, 2 * n, threads=8)[0]) <= 1e-14 * math.log2(2 * n), r.describe()
     assert oracle.rel_l2(back.cpu().numpy() / (2 * n), xr) <= 2e-14 * math.log2(2 * n)
+
+
+@pytest.mark.parametrize("n", LONG_SIZES)
+def test_flat_2048_point_leg(oracle, cuda_device, n):
+    """2^21, 2^22, 3 * 2^19 on the ticket-queue kernels: forward / inverse, batch 1 and 5, in place."""
+    f = fft_b200.FFT(n)
+    assert "ticket-queue" in f.describe(), f.describe()
+    for batch in (1, 5):
+        x = oracle.uniform_complex((batch, n), 71 + batch, np.complex64)
+        xd = torch.from_numpy(x).cuda()
+        out = torch.empty_like(xd)
+        for inverse in (False, True):
+            out.zero_()
+            launches = fft_b200.launch_count()
+            (f.ifft if inverse else f.fft)(xd, out)
+            torch.cuda.synchronize()
+            assert fft_b200.launch_count() - launches == 1
+            ref = oracle.run(oracle.KIND_C2C_INV if inverse else oracle.KIND_C2C_FWD, x, n, threads=8)[0]
+            assert oracle.rel_l2(out.cpu().numpy(), ref) <= tol(n), (n, batch, inverse)
+    f.fft(xd, xd)
+    torch.cuda.synchronize()
+    assert oracle.rel_l2(xd.cpu().numpy(), oracle.run(oracle.KIND_C2C_FWD, x, n, threads=8)[0]) <= tol(n)
