@@ -18,7 +18,7 @@ pytestmark = pytest.mark.gpu
 import fft_b200  # noqa: E402
 
 SIZES = [32768, 65536, 2 ** 17, 2 ** 18, 2 ** 19, 2 ** 20]
-LONG_SIZES = [2 ** 21, 2 ** 22, 3 * 2 ** 19]  # 2048-point leg (flat_f32_j.cu)
+LONG_SIZES = [2 ** 21, 2 ** 22, 3 * 2 ** 19, 3 * 2 ** 20, 9 * 2 ** 17, 9 * 2 ** 18]  # 2048-point leg (flat_f32_j.cu)
 VARIANTS = ["1,3,0", "2,3,1"]  # ring, CTAs per SM, in-place exchange
 
 
