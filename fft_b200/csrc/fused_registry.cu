@@ -91,6 +91,7 @@ void register_flat_f32_e(std::vector<FlatEntry> &);
 void register_flat_f32_h(std::vector<FlatEntry> &);
 void register_flat_f32_i(std::vector<FlatEntry> &);
 void register_flat_f32_j(std::vector<FlatEntry> &);
+void register_flat_f32_k(std::vector<FlatEntry> &);
 void register_flat_f64_a(std::vector<FlatEntry> &);
 
 const std::vector<FlatEntry> &flat_registry() {
@@ -107,6 +108,7 @@ const std::vector<FlatEntry> &flat_registry() {
         register_flat_f32_h(v);
         register_flat_f32_i(v);
         register_flat_f32_j(v);
+        register_flat_f32_k(v);
         register_flat_f64_a(v);
         return v;
     }();

@@ -319,6 +319,11 @@ int setup_flat(ssfft_plan *pl, bool *ok) {
         if (lg < env_int("SSFFT_FLAT_MIN_LOG2", sizeof(T) == 8 ? 14 : 15)) return SSFFT_OK;
         n1 = (size_t)1 << (lg / 2);
         n2 = n / n1;
+        // another registered split of the same length, by (part of) its name -- or the measured default of the length
+        const char *want = getenv("SSFFT_FLAT_NAME");
+        for (const FlatEntry &e : flat_registry())
+            if (e.prec == (sizeof(T) == 4 ? 0 : 1) && (size_t)e.n1 * (size_t)e.n2 == n && (!real || (e.launch_real[0] && e.launch_real[1])) &&
+                ((want && *want && strstr(e.name, want)) || (!want && strstr(e.name, "_dflt")))) { n1 = (size_t)e.n1; n2 = (size_t)e.n2; break; }
     } else {
         // 3 * 2^k: the registered (power of two) x (3 * 2^j) pair of this length, if there is one
         for (const FlatEntry &e : flat_registry())
