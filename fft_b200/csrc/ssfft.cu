@@ -326,8 +326,15 @@ int setup_flat(ssfft_plan *pl, bool *ok) {
                 ((want && *want && strstr(e.name, want)) || (!want && strstr(e.name, "_dflt")))) { n1 = (size_t)e.n1; n2 = (size_t)e.n2; break; }
     } else {
         // 3 * 2^k: the registered (power of two) x (3 * 2^j) pair of this length, if there is one
-        for (const FlatEntry &e : flat_registry())
-            if (e.prec == (sizeof(T) == 4 ? 0 : 1) && (size_t)e.n1 * (size_t)e.n2 == n) { n1 = (size_t)e.n1; n2 = (size_t)e.n2; break; }
+        // (by name with SSFFT_FLAT_NAME, else the split marked "_dflt", else the first one registered)
+        const char *want = getenv("SSFFT_FLAT_NAME");
+        int rank_best = 0;
+        for (const FlatEntry &e : flat_registry()) {
+            if (e.prec != (sizeof(T) == 4 ? 0 : 1) || (size_t)e.n1 * (size_t)e.n2 != n) continue;
+            const bool real_fit = !real || (e.launch_real[0] && e.launch_real[1]);
+            const int rank = (want && *want && strstr(e.name, want)) ? 3 : (!want && strstr(e.name, "_dflt") && real_fit) ? 2 : 1;
+            if (rank > rank_best) { rank_best = rank; n1 = (size_t)e.n1; n2 = (size_t)e.n2; }
+        }
         if (!n1) return SSFFT_OK;
     }
     // a real plan whose length has no RealFFT kernels registered (fp64 3 * 2^k, 9 * 2^k) still runs its complex core
