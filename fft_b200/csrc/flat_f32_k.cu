@@ -10,6 +10,8 @@ void register_flat_f32_k(std::vector<FlatEntry> &v) {
     using A1024 = TileCfg<float, 1024, 4, 16, 16, 64, 4, 3>;
     using B256 = TileCfg<float, 256, 16, 16, 1, 16, 16, 3>;
     v.push_back(make_flat_entry<A1024, B256, 2, 3, true, 0>("float_flat_1024x256_dflt_r2c3i"));  // 2^18
+    using B512 = TileCfg<float, 512, 8, 8, 8, 32, 8, 3>;
+    v.push_back(make_flat_entry<A1024, B512, 2, 3, true, 0>("float_flat_1024x512_dflt_r2c3i"));  // 2^19: 36.1 -> 37.6 % (profiles/sweep_r02ao_2p19_float32.txt)
     // the same for 3 * 2^k / 9 * 2^k (profiles/sweep_r02am_unbalanced_3x9_float32.txt): only 294912 as 768 x 384 gained (41.3 -> 43.6 %);
     // 98304 as 384 x 256 (46.6 vs 51.2 %), 196608 as 768 x 256 (42.7 vs 44.3), 393216 as 1536 x 256 (38.9 vs 38.8), 589824 as
     // 1536 x 384 (37.3 vs 38.3) did not and were dropped
